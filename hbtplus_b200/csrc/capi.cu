@@ -1,0 +1,477 @@
+// capi.cu - the extern "C" entry points of include/hbt_unbind.h.
+//
+// Validation, device/stream ownership, host<->device staging and error translation only; the
+// algorithm is in unbind_batch.cu / tree_build.cu / walk.cu.  No entry point has a CPU path: if no
+// sm_100 device is usable hbtu_create fails with HBTU_ERR_NODEVICE.
+#include <cub/cub.cuh>
+
+#include <cstring>
+#include <new>
+
+#include "context.cuh"
+
+using namespace hbt;
+
+namespace
+{
+thread_local std::string g_create_error;
+
+template <class T>
+void grow(T *&p, int64_t &cap, int64_t need)
+{
+  if (need <= cap) return;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  int64_t ncap = need + need / 8 + 1024;
+  HBT_CUDA(cudaMalloc(&p, sizeof(T) * (size_t)ncap));
+  cap = ncap;
+}
+
+template <class F>
+int guarded(hbtu_ctx *ctx, F &&f)
+{
+  if (!ctx) return HBTU_ERR_INVALID;
+  try
+  {
+    cudaError_t e = cudaSetDevice(ctx->c.device);
+    if (e != cudaSuccess) throw CudaError{HBTU_ERR_NODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    f(ctx->c);
+    return HBTU_OK;
+  }
+  catch (const CudaError &e)
+  {
+    ctx->c.last_error = e.what;
+    cudaGetLastError();
+    return e.code;
+  }
+  catch (const std::bad_alloc &)
+  {
+    ctx->c.last_error = "host allocation failed";
+    return HBTU_ERR_NOMEM;
+  }
+  catch (const std::exception &e)
+  {
+    ctx->c.last_error = e.what();
+    return HBTU_ERR_INVALID;
+  }
+}
+
+void build_forest(Context &c, int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list)
+{
+  c.subs.assign((size_t)nsub, SubHost());
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    int64_t n = part_offset[s + 1] - part_offset[s];
+    if (n < 0 || n > 0x3fffffff) throw CudaError{HBTU_ERR_INVALID, "part_offset must be non-decreasing with < 2^30 particles per subhalo"};
+    c.subs[s].part_begin = part_offset[s];
+    c.subs[s].n_own = (int)n;
+  }
+  if (nest_offset)
+    for (int64_t s = 0; s < nsub; s++)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++)
+      {
+        int ch = nest_list[k];
+        if (ch < 0 || ch >= nsub || ch == s || c.subs[ch].parent != -1)
+          throw CudaError{HBTU_ERR_INVALID, "nest lists must form a forest of batch-local subhalo indices"};
+        c.subs[ch].parent = (int)s;
+        c.subs[s].children.push_back(ch);
+      }
+  // depth, with cycle detection (a cycle has no root, so its members never get a depth)
+  c.max_depth = 0;
+  std::vector<int> order;
+  order.reserve((size_t)nsub);
+  for (int64_t s = 0; s < nsub; s++)
+    if (c.subs[s].parent < 0) order.push_back((int)s);
+  for (size_t i = 0; i < order.size(); i++)
+  {
+    SubHost &h = c.subs[order[i]];
+    for (int ch : h.children)
+    {
+      c.subs[ch].depth = h.depth + 1;
+      if (c.subs[ch].depth > c.max_depth) c.max_depth = c.subs[ch].depth;
+      order.push_back(ch);
+    }
+  }
+  if ((int64_t)order.size() != nsub) throw CudaError{HBTU_ERR_INVALID, "nest lists contain a cycle"};
+  // capacity: own particles plus everything descendants can feed upwards
+  for (size_t i = order.size(); i-- > 0;)
+  {
+    SubHost &h = c.subs[order[i]];
+    h.cap += h.n_own;
+    if (h.parent >= 0) c.subs[h.parent].cap += h.cap;
+  }
+  int64_t slot = 0;
+  c.levels.assign((size_t)c.max_depth + 1, std::vector<int>());
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    c.subs[s].slot_base = slot;
+    slot += c.subs[s].cap;
+    c.levels[c.subs[s].depth].push_back((int)s);
+  }
+  c.total_cap = slot;
+  if (slot > 0x7fffffff00ll) throw CudaError{HBTU_ERR_UNSUPPORTED, "batch too large"};
+}
+
+void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, const float *vel,
+           const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags)
+{
+  if (!epoch || nsub < 0 || !part_offset || (nsub > 0 && !io)) throw CudaError{HBTU_ERR_INVALID, "null argument"};
+  if (nsub > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
+  c.staged = c.executed = false;
+  const int64_t N = nsub > 0 ? part_offset[nsub] - part_offset[0] : 0;
+  if (part_offset[0] != 0) throw CudaError{HBTU_ERR_INVALID, "part_offset[0] must be 0"};
+  if (N > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "more than 2^31 particles in one batch: split the batch"};
+  if (N > 0 && (!pos_mass || !vel)) throw CudaError{HBTU_ERR_INVALID, "null particle arrays"};
+  build_forest(c, nsub, part_offset, nest_offset, nest_list);
+  c.nsub = nsub;
+  c.N = N;
+  c.flags = flags;
+  c.cfg.scale_factor = (float)epoch->scale_factor;
+  c.cfg.hz = (float)epoch->hz;
+  c.cfg.snapshot_index = epoch->snapshot_index;
+  c.io_in.assign(io, io + nsub);
+
+  cudaStream_t st = c.stream;
+  grow(c.d_pos, c.cap_particles, N);
+  grow(c.d_vel, c.cap_vel, N);
+  {
+    int64_t cap0 = c.cap_slots, cap1 = c.cap_slots, cap2 = c.cap_slots;
+    grow(c.d_ids, cap0, c.total_cap);
+    grow(c.d_ids_orig, cap1, c.total_cap);
+    grow(c.d_E, cap2, c.total_cap);
+    c.cap_slots = cap0;
+  }
+  {
+    int64_t cap0 = c.cap_subs, cap1 = c.cap_subs, cap2 = c.cap_subs;
+    grow(c.d_subs, cap0, nsub + 1);
+    grow(c.d_part_offset, cap1, nsub + 1);
+    grow(c.d_slot_base, cap2, nsub + 1);
+    c.cap_subs = cap0;
+  }
+  HBT_CUDA(cudaEventRecord(c.ev[0], st));
+  if (N > 0)
+  {
+    HBT_CUDA(cudaMemcpyAsync(c.d_pos, pos_mass, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
+    HBT_CUDA(cudaMemcpyAsync(c.d_vel, vel, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
+  }
+  std::vector<int64_t> sb((size_t)nsub + 1, 0);
+  for (int64_t s = 0; s < nsub; s++) sb[s] = c.subs[s].slot_base;
+  sb[nsub] = c.total_cap;
+  HBT_CUDA(cudaMemcpyAsync(c.d_part_offset, part_offset, sizeof(int64_t) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
+  HBT_CUDA(cudaMemcpyAsync(c.d_slot_base, sb.data(), sizeof(int64_t) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
+  HBT_CUDA(cudaEventRecord(c.ev[1], st));
+  HBT_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+  c.stats.h2d_ms = ms;
+  c.stats.h2d_bytes = N * 32 + (nsub + 1) * 16;
+  c.staged = true;
+}
+
+// ---- stand-alone GravityTree_t::Build + EvaluatePotential / BindingEnergy -------------------------
+__global__ void fill_seg0_kernel(int *ts_seg, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ts_seg[i] = 0;
+}
+__global__ void target_keys_kernel(const float4 *tgt, int n, const SegRoot *roots, uint64_t *key, int *val)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = tgt[i];
+  key[i] = morton_key(p.x, p.y, p.z, roots[0]);
+  val[i] = i;
+}
+__global__ void target_gather_kernel(const int *perm, const float4 *tgt, const float *self_mass, const float4 *vel, int n,
+                                     float4 *tgt_pm, float4 *tgt_vel)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int src = perm[i];
+  float4 p = tgt[src];
+  p.w = self_mass ? self_mass[src] : 0.f;
+  tgt_pm[i] = p;
+  if (vel) tgt_vel[i] = vel[src];
+}
+__global__ void scatter_out_kernel(const int *perm, const double *sorted_out, int n, double *out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = sorted_out[i];
+}
+
+void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const float *src_pos_mass, int64_t ntgt, const float *tgt_pos,
+                    const float *tgt_self_mass, const float *tgt_vel, const double *ref_pos, const double *ref_vel, double *out)
+{
+  if (!epoch || nsrc < 1 || ntgt < 0 || !src_pos_mass || (ntgt > 0 && (!tgt_pos || !out)))
+    throw CudaError{HBTU_ERR_INVALID, "bad argument"};
+  if (tgt_vel && (!ref_pos || !ref_vel)) throw CudaError{HBTU_ERR_INVALID, "binding energy needs a reference frame"};
+  if (nsrc > 0x3fffffff || ntgt > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many particles"};
+  c.staged = c.executed = false; // the arena is shared with a staged batch's rounds
+  DevConfig cfg = c.cfg;
+  cfg.scale_factor = (float)epoch->scale_factor;
+  cfg.hz = (float)epoch->hz;
+  cfg.snapshot_index = epoch->snapshot_index;
+  cudaStream_t st = c.stream;
+  const int S = (int)nsrc, T = (int)ntgt, kB = 256;
+  c.ls.launches = 0;
+  std::memset(&c.stats, 0, sizeof(c.stats));
+  Arena &ar = c.arena;
+  ar.reset();
+  ar.reserve(tree_arena_bytes(S, 1) + (int64_t)T * 96 + (1 << 20));
+  std::vector<int> tree_off{0, S}, warp_off{0, (T + 31) / 32};
+  Segment sg{};
+  sg.mode = tgt_vel ? kWalkBindingEnergy : kWalkPotential;
+  sg.tree_n = S;
+  sg.tgt_n = T;
+  std::vector<Segment> segs{sg};
+  Segment *d_segs = ar.alloc<Segment>(1);
+  int *d_tree_off = ar.alloc<int>(2), *d_warp_off = ar.alloc<int>(2);
+  HBT_CUDA(cudaMemcpyAsync(d_segs, segs.data(), sizeof(Segment), cudaMemcpyHostToDevice, st));
+  HBT_CUDA(cudaMemcpyAsync(d_tree_off, tree_off.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  HBT_CUDA(cudaMemcpyAsync(d_warp_off, warp_off.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+  TreeArrays tr;
+  tr.S = S;
+  tr.nseg = 1;
+  tr.tree_off = d_tree_off;
+  tr.tpos = ar.alloc<float4>(S);
+  tr.ts_seg = ar.alloc<int>(S);
+  tr.bbox = ar.alloc<uint32_t>(6);
+  HBT_CUDA(cudaMemcpyAsync(tr.tpos, src_pos_mass, sizeof(float4) * (size_t)S, cudaMemcpyHostToDevice, st));
+  fill_seg0_kernel<<<div_up(S, kB), kB, 0, st>>>(tr.ts_seg, S);
+  HBT_CHECK_LAUNCH();
+  HBT_CUDA(cudaEventRecord(c.ev[0], st));
+  launch_init_bbox(tr.bbox, 1, st, c.ls);
+  launch_bbox(tr.tpos, tr.ts_seg, S, tr.bbox, st, c.ls);
+  build_trees(tr, ar, cfg, st, c.ls);
+  HBT_CUDA(cudaEventRecord(c.ev[1], st));
+  if (T > 0)
+  {
+    float4 *d_tgt = ar.alloc<float4>(T), *d_vel = tgt_vel ? ar.alloc<float4>(T) : nullptr;
+    float *d_sm = tgt_self_mass ? ar.alloc<float>(T) : nullptr;
+    HBT_CUDA(cudaMemcpyAsync(d_tgt, tgt_pos, sizeof(float4) * (size_t)T, cudaMemcpyHostToDevice, st));
+    if (tgt_vel) HBT_CUDA(cudaMemcpyAsync(d_vel, tgt_vel, sizeof(float4) * (size_t)T, cudaMemcpyHostToDevice, st));
+    if (tgt_self_mass) HBT_CUDA(cudaMemcpyAsync(d_sm, tgt_self_mass, sizeof(float) * (size_t)T, cudaMemcpyHostToDevice, st));
+    // walk the targets in key order (spatially coherent warps), scatter the results back
+    uint64_t *ka = ar.alloc<uint64_t>(T), *kb = ar.alloc<uint64_t>(T);
+    int *va = ar.alloc<int>(T), *vb = ar.alloc<int>(T);
+    target_keys_kernel<<<div_up(T, kB), kB, 0, st>>>(d_tgt, T, tr.roots, ka, va);
+    HBT_CHECK_LAUNCH();
+    cub::DoubleBuffer<uint64_t> dk(ka, kb);
+    cub::DoubleBuffer<int> dv(va, vb);
+    size_t tb = 0;
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, T, 0, 63, st));
+    void *tmp = ar.alloc<char>((int64_t)tb);
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, T, 0, 63, st));
+    float4 *tgt_pm = ar.alloc<float4>(T), *tgt_v = tgt_vel ? ar.alloc<float4>(T) : nullptr;
+    target_gather_kernel<<<div_up(T, kB), kB, 0, st>>>(dv.Current(), d_tgt, d_sm, d_vel, T, tgt_pm, tgt_v);
+    HBT_CHECK_LAUNCH();
+    double *d_sorted = ar.alloc<double>(T), *d_out = ar.alloc<double>(T);
+    c.ls.launches += 12;
+    HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
+    WalkArgs wa{};
+    wa.node_xm = tr.node_xm;
+    wa.node_aux = tr.node_aux;
+    wa.cellcount = tr.cellcount;
+    wa.tree_off = d_tree_off;
+    wa.segs = d_segs;
+    wa.warp_off = d_warp_off;
+    wa.nseg = 1;
+    wa.nwarps = (T + 31) / 32;
+    wa.tgt_pm = tgt_pm;
+    wa.vel = tgt_v;
+    wa.out = d_sorted;
+    wa.counters = c.count_interactions ? c.d_counters : nullptr;
+    if (tgt_vel)
+      for (int j = 0; j < 3; j++)
+      {
+        wa.ref_pos[j] = (float)ref_pos[j];
+        wa.ref_vel[j] = (float)ref_vel[j];
+      }
+    HBT_CUDA(cudaEventRecord(c.ev[2], st));
+    launch_walk(wa, cfg, st, c.ls);
+    HBT_CUDA(cudaEventRecord(c.ev[3], st));
+    scatter_out_kernel<<<div_up(T, kB), kB, 0, st>>>(dv.Current(), d_sorted, T, d_out);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches++;
+    HBT_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)T, cudaMemcpyDeviceToHost, st));
+    HBT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
+    c.stats.walk_ms = ms;
+    if (c.count_interactions)
+    {
+      unsigned long long cnt[2];
+      HBT_CUDA(cudaMemcpy(cnt, c.d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+      c.stats.pair_interactions = (int64_t)cnt[0];
+      c.stats.nodes_visited = (int64_t)cnt[1];
+    }
+  }
+  HBT_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+  c.stats.build_ms = ms;
+  c.stats.tree_builds = 1;
+  c.stats.walk_targets = T;
+  c.stats.rounds = 1;
+  c.stats.kernel_launches = c.ls.launches;
+}
+} // namespace
+
+extern "C" {
+
+int hbtu_abi_version(void) { return HBTU_ABI_VERSION; }
+
+const char *hbtu_last_error(const hbtu_ctx *ctx) { return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str(); }
+
+int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
+{
+  if (out) *out = nullptr;
+  if (!p || !out || p->struct_size != (int32_t)sizeof(hbtu_params))
+  {
+    g_create_error = "hbtu_params is null or has the wrong struct_size (ABI mismatch)";
+    return HBTU_ERR_INVALID;
+  }
+  if (p->real_bytes != 4)
+  {
+    g_create_error = "only the HBTReal=float ABI variant is built";
+    return HBTU_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev)
+  {
+    g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal");
+    cudaGetLastError();
+    return HBTU_ERR_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, p->device);
+  if (prop.major != 10)
+  {
+    g_create_error = "device is not sm_100 (this library is built for sm_100a only)";
+    return HBTU_ERR_NODEVICE;
+  }
+  hbtu_ctx *ctx = new (std::nothrow) hbtu_ctx();
+  if (!ctx) return HBTU_ERR_NOMEM;
+  Context &c = ctx->c;
+  c.params = *p;
+  c.device = p->device;
+  c.cfg.box_size = (float)p->box_size;
+  c.cfg.box_half = (float)p->box_half;
+  c.cfg.softening = (float)p->softening_halo;
+  c.cfg.theta2 = (float)p->tree_node_open_angle_square;
+  c.cfg.resolution = (float)p->tree_node_resolution;
+  c.cfg.resolution_half = (float)p->tree_node_resolution_half;
+  c.cfg.G = (float)p->G;
+  c.cfg.bound_mass_precision = (float)p->bound_mass_precision;
+  c.cfg.relax_factor = (float)p->source_sub_relax_factor;
+  c.cfg.periodic = p->periodic_boundary_on != 0;
+  c.cfg.min_num_part = p->min_num_part_of_sub;
+  c.cfg.max_sample = p->max_sample_size;
+  c.cfg.scale_factor = 1.f;
+  int rc = guarded(ctx, [&](Context &cc) {
+    HBT_CUDA(cudaStreamCreateWithFlags(&cc.stream, cudaStreamNonBlocking));
+    for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
+    HBT_CUDA(cudaMalloc(&cc.d_counters, 2 * sizeof(unsigned long long)));
+  });
+  if (rc != HBTU_OK)
+  {
+    g_create_error = c.last_error;
+    hbtu_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return HBTU_OK;
+}
+
+void hbtu_destroy(hbtu_ctx *ctx)
+{
+  if (!ctx) return;
+  Context &c = ctx->c;
+  cudaSetDevice(c.device);
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  c.arena.release();
+  cudaFree(c.d_pos);
+  cudaFree(c.d_vel);
+  cudaFree(c.d_ids);
+  cudaFree(c.d_ids_orig);
+  cudaFree(c.d_E);
+  cudaFree(c.d_subs);
+  cudaFree(c.d_part_offset);
+  cudaFree(c.d_slot_base);
+  cudaFree(c.d_counters);
+  for (auto &ev : c.ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete ctx;
+}
+
+int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list)
+{
+  if (nsub < 0 || !part_offset) return HBTU_ERR_INVALID;
+  try
+  {
+    Context tmp;
+    build_forest(tmp, nsub, part_offset, nest_offset, nest_list);
+    return tmp.total_cap;
+  }
+  catch (...)
+  {
+    return HBTU_ERR_INVALID;
+  }
+}
+
+int hbtu_stage(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+               const float *vel, const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags)
+{
+  return guarded(ctx, [&](Context &c) { stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags); });
+}
+int hbtu_execute(hbtu_ctx *ctx)
+{
+  return guarded(ctx, [&](Context &c) { execute_batch(c); });
+}
+int hbtu_fetch(hbtu_ctx *ctx, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  return guarded(ctx, [&](Context &c) {
+    if (!io || !order_offset || (!order_out && order_capacity > 0)) throw CudaError{HBTU_ERR_INVALID, "null output"};
+    fetch_batch(c, io, order_capacity, order_offset, order_out, energy_out);
+  });
+}
+int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+                      const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_sub_io *io, int32_t flags,
+                      int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  int rc = hbtu_stage(ctx, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags);
+  if (rc != HBTU_OK) return rc;
+  rc = hbtu_execute(ctx);
+  if (rc != HBTU_OK) return rc;
+  return hbtu_fetch(ctx, io, order_capacity, order_offset, order_out, energy_out);
+}
+
+int hbtu_tree_potential(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsrc, const float *src_pos_mass, int64_t ntgt,
+                        const float *tgt_pos, const float *tgt_self_mass, const float *tgt_vel, const double *ref_pos,
+                        const double *ref_vel, double *out)
+{
+  return guarded(ctx, [&](Context &c) {
+    tree_potential(c, epoch, nsrc, src_pos_mass, ntgt, tgt_pos, tgt_self_mass, tgt_vel, ref_pos, ref_vel, out);
+  });
+}
+
+int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out)
+{
+  if (!ctx || !out) return HBTU_ERR_INVALID;
+  *out = ctx->c.stats;
+  return HBTU_OK;
+}
+
+/* diagnostics switch (not part of the reference seam): count accepted interactions and warp node visits
+ * in the walk kernels of subsequent calls; costs a few percent, so bench.py enables it for one untimed pass */
+int hbtu_set_counting(hbtu_ctx *ctx, int on)
+{
+  if (!ctx) return HBTU_ERR_INVALID;
+  ctx->c.count_interactions = on != 0;
+  return HBTU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,63 @@
+// context.cuh - the hbtu_ctx object: one CUDA device, one stream, one staged batch.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "device_tree.cuh"
+
+namespace hbt
+{
+
+struct SubHost
+{ // host mirror of a subhalo's place in the batch and of its iteration state
+  int64_t slot_base = 0, part_begin = 0, cap = 0;
+  int n_own = 0, n_src = 0, nbound = 0, nlast = 0, correction = 0, iterations = 0;
+  int depth = 0, parent = -1;
+  bool done = false, disrupted = false, is_orphan = false;
+  std::vector<int> children; // NestedSubhalos, in list order
+};
+
+struct Context
+{
+  hbtu_params params{};
+  DevConfig cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string last_error;
+
+  // staged batch -------------------------------------------------------------------------------
+  bool staged = false, executed = false;
+  int64_t nsub = 0, N = 0, total_cap = 0;
+  int32_t flags = 0;
+  int max_depth = 0;
+  std::vector<SubHost> subs;
+  std::vector<std::vector<int>> levels;
+  std::vector<hbtu_sub_io> io_in;
+
+  // persistent device buffers (grow-only)
+  float4 *d_pos = nullptr, *d_vel = nullptr;
+  int64_t cap_particles = 0, cap_vel = 0;
+  int *d_ids = nullptr, *d_ids_orig = nullptr;
+  float *d_E = nullptr;
+  int64_t cap_slots = 0;
+  SubState *d_subs = nullptr;
+  int64_t *d_part_offset = nullptr, *d_slot_base = nullptr;
+  int64_t cap_subs = 0;
+  unsigned long long *d_counters = nullptr;
+  bool count_interactions = false;
+
+  Arena arena;
+  LaunchStats ls;
+  hbtu_stats stats{};
+};
+
+void execute_batch(Context &c);
+void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out);
+
+} // namespace hbt
+
+struct hbtu_ctx
+{
+  hbt::Context c;
+};

@@ -1,0 +1,140 @@
+// device_tree.cuh - data layout in HBM of one unbinding round and the kernel launch API shared by
+// tree_build.cu / walk.cu / unbind_batch.cu.
+//
+// One ROUND processes every still-active subhalo of the current nesting level at once.  All per-round
+// arrays are concatenations over the active subhaloes ("segments"):
+//
+//   S-arrays (tree sources, length S = sum tree_n):  tpos  float4 (x,y,z,m) gathered source particles
+//                                                    key   uint64 63-bit octal key (tree_core.cuh)
+//                                                    spos  float4 sources in key order
+//                                                    cells (l,r,depth) per adjacent pair, depthmask, cellcount
+//                                                    msum  double4 segmented prefix sums of m, m*(x-centre)
+//   node arrays (length <= 2S-1):                    node_xm  float4 (x,y,z,m)  particle or cell CoM/mass
+//                                                    node_aux float2 (len^2/theta^2 [0 for particles], end index bits)
+//   T-arrays (walk targets, length T = sum tgt_n):   tgt_pm float4 (x,y,z,self mass), tgt_slot int64
+//
+// Algorithmic bytes per unit: a source particle costs 16 B (gather) + 16+12 B (key, sort
+// payload) + 16 B (sorted copy) + 32 B (moment scan) + 24 B (node) per build; a walk target reads 16 B and
+// writes 4 B; everything else is per-interaction fp32 issue work.
+#pragma once
+#include "common.cuh"
+
+namespace hbt
+{
+
+struct double4s
+{
+  double m, x, y, z;
+};
+
+// per active subhalo of a round; uploaded by the host planner every round
+struct Segment
+{
+  int64_t slot_base; // first slot of this subhalo in ids/E
+  int sub;           // subhalo index in the batch
+  int mode;          // 0 = full evaluation (tree == targets), 1 = correction (tree = removed, targets = bound)
+  int tree_first;    // first Elist index of the tree sources
+  int tree_n;
+  int tgt_n;
+  int tree_off; // offset in the S-concatenation
+  int tgt_off;  // offset in the T-concatenation
+  int warp_off; // first walk warp of this segment
+};
+
+enum WalkMode
+{
+  kWalkUnbindFull = 0,   // E = 0.5|dv|^2 + pot            (src/subhalo_unbind.cpp:341-354)
+  kWalkUnbindCorrect = 1, // E += v_old.dv + dK - pot_removed (src/subhalo_unbind.cpp:312-330)
+  kWalkPotential = 2,    // out = pot                      (GravityTree_t::EvaluatePotential)
+  kWalkBindingEnergy = 3 // out = 0.5|dv|^2 + pot          (GravityTree_t::BindingEnergy)
+};
+
+// Per-subhalo iteration state kept on the device for the whole batch.
+struct SubState
+{
+  int64_t slot_base;  // offset of this subhalo's Elist in ids/E
+  int64_t part_begin; // first input particle
+  int n_own;          // input particles
+  int n_src;          // Particles.size() seen by Unbind (own + children's unbound tails)
+  int nbound, nlast;
+  int status;     // SubStatus
+  int correction; // sticky CorrectionLoop flag
+  int iterations;
+  int death, sink;
+  int is_orphan;
+  int64_t sinktrack;
+  float ref_pos[3], ref_vel[3];         // ComovingAveragePosition / PhysicalAverageVelocity (RefPos/RefVel)
+  float old_ref_pos[3], old_ref_vel[3]; // OldRefPos / OldRefVel
+  float mb_pos[3], mb_vel[3];           // ComovingMostBoundPosition / PhysicalMostBoundVelocity
+  float mbound, spec_pot, spec_kin, am[3];
+  float ref_diff[3], dK; // RefVelDiff and dK of the current correction round
+  int count_bound;       // scratch: number of E<0 among this round's targets
+  int pad;
+  double sums[8]; // scratch: reduction accumulators
+};
+
+enum SubStatus
+{
+  kPending = 0,   // waiting for its nesting level
+  kActive = 1,    // iterating
+  kConverged = 2, // converged this round (final sort + kinematics pending)
+  kDisrupted = 3, // Nbound < MinNumPartOfSub
+  kDone = 4       // finished
+};
+
+struct TreeArrays
+{ // device pointers of one round (arena-owned)
+  int S = 0, nseg = 0;
+  float4 *tpos = nullptr;
+  int *ts_seg = nullptr;
+  uint64_t *skey = nullptr;
+  int *sperm = nullptr;
+  float4 *spos = nullptr;
+  int2 *cell_lr = nullptr;
+  int8_t *cell_depth = nullptr;
+  uint32_t *depthmask = nullptr;
+  int *cellcount = nullptr;
+  double4s *msum = nullptr;
+  float4 *node_xm = nullptr;
+  float2 *node_aux = nullptr;
+  SegRoot *roots = nullptr;
+  uint32_t *bbox = nullptr; // 6 ordered-uint per segment
+  const int *tree_off = nullptr; // [nseg+1] device
+};
+
+struct LaunchStats
+{
+  int64_t launches = 0;
+};
+
+// tree_build.cu -----------------------------------------------------------------------------------------
+// Build the pre-order node arrays for all segments from tpos/ts_seg (already filled, bbox accumulated).
+void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
+int64_t tree_arena_bytes(int64_t S, int64_t nseg);
+// accumulate per-segment bounding boxes of tpos into t.bbox (must be pre-initialised by init_bbox)
+void launch_init_bbox(uint32_t *bbox, int nseg, cudaStream_t stream, LaunchStats &ls);
+void launch_bbox(const float4 *tpos, const int *ts_seg, int S, uint32_t *bbox, cudaStream_t stream, LaunchStats &ls);
+
+// walk.cu -----------------------------------------------------------------------------------------------
+struct WalkArgs
+{
+  const float4 *node_xm;
+  const float2 *node_aux;
+  const int *cellcount;  // inclusive cell counts (node range of a segment derives from it)
+  const int *tree_off;   // [nseg+1]
+  const Segment *segs;   // [nseg]
+  const int *warp_off;   // [nseg+1]
+  int nseg, nwarps;
+  const float4 *tgt_pm;  // [T] x,y,z,self mass
+  const int64_t *tgt_slot; // [T] slot in ids/E (unbind modes)
+  const int *ids;        // Elist pid per slot
+  const float4 *vel;     // input velocities (by particle id) or per-target velocities (kWalkBindingEnergy)
+  float *E;              // per slot
+  const SubState *subs;
+  double *out;           // kWalkPotential / kWalkBindingEnergy
+  float ref_pos[3], ref_vel[3]; // kWalkBindingEnergy frame
+  unsigned long long *counters; // [2]: accepted interactions, warp node visits (nullptr = do not count)
+};
+void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
+
+} // namespace hbt

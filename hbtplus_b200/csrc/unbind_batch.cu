@@ -1,0 +1,946 @@
+// unbind_batch.cu - the batched, level-synchronous unbinding driver and its bookkeeping kernels (sm_100a).
+//
+// Replaces SubhaloSnapshot_t::RefineParticles / Subhalo_t::RecursiveUnbind / Subhalo_t::Unbind /
+// Subhalo_t::TruncateSource (src/subhalo_unbind.cpp:263-516).  The reference iterates one subhalo at a
+// time on one OpenMP thread; here ALL subhaloes of one nesting level iterate together, one "round" per
+// potential evaluation:
+//
+//   plan (host)  -> gather sources -> bbox -> build_trees (tree_build.cu) -> walk (walk.cu)
+//                -> count E<0 -> state1 (disruption / convergence / CorrectionLoop, :357-395)
+//                -> ONE radix sort that is at once the bound/unbound partition (:21-58), the E-sort of the
+//                   freshly removed tail (:382) and, for converged subhaloes, the final E-sort of the bound
+//                   part (:405)
+//                -> mass-weighted frame reductions in fp64 (:108-188) -> state2
+//                -> kinematics of converged subhaloes (:189-232) -> finalize
+//
+// The Elist of a subhalo (ParticleEnergy_t{pid,E}, :12-16) lives in two flat arrays ids[]/E[] at
+// [slot_base, slot_base+n_src); its layout after every round is the reference's: bound | removed this
+// round (E ascending) | removed earlier.  The host keeps a 16-byte mirror per active subhalo (status,
+// Nbound, Nlast, CorrectionLoop) read back once per round to plan the next one.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "context.cuh"
+
+namespace hbt
+{
+
+static constexpr int kBlock = 256;
+static inline int grid_for(int64_t n, int per_block = kBlock) { return n > 0 ? div_up(n, per_block) : 1; }
+
+// largest a in [0,n) with off[a] <= k
+__device__ __forceinline__ int find_seg(const int *__restrict__ off, int n, int k)
+{
+  int lo = 0, hi = n;
+  while (hi - lo > 1)
+  {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int find_seg64(const int64_t *__restrict__ off, int n, int64_t k)
+{
+  int lo = 0, hi = n;
+  while (hi - lo > 1)
+  {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batch set-up kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) init_ids_kernel(const int64_t *__restrict__ part_offset, const int64_t *__restrict__ slot_base,
+                                                           int nsub, int64_t N, int *__restrict__ ids)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int s = find_seg64(part_offset, nsub, i);
+  ids[slot_base[s] + (i - part_offset[s])] = (int)i;
+}
+
+struct CopyJob
+{
+  int64_t dst, src; // slot offsets
+};
+// generic segmented copy between slot arrays: job j copies count = job_off[j+1]-job_off[j] ints
+__global__ void __launch_bounds__(kBlock) seg_copy_kernel(const CopyJob *__restrict__ jobs, const int64_t *__restrict__ job_off, int njobs,
+                                                           int64_t total, const int *__restrict__ src, int *__restrict__ dst)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = find_seg64(job_off, njobs, i);
+  int64_t o = i - job_off[j];
+  dst[jobs[j].dst + o] = src[jobs[j].src + o];
+}
+
+struct LevelInit
+{
+  int sub, n_src, activate;
+};
+__global__ void level_init_kernel(const LevelInit *__restrict__ li, int n, SubState *__restrict__ subs)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SubState &st = subs[li[i].sub];
+  st.n_src = li[i].n_src;
+  if (li[i].activate) st.status = kActive;
+}
+
+// subhaloes whose source is too small to iterate (src/subhalo_unbind.cpp:269-293 and the disruption
+// branch :361-379, which every source with 2 <= n < MinNumPartOfSub necessarily takes)
+__global__ void trivial_kernel(const int *__restrict__ list, int n, SubState *__restrict__ subs, const int *__restrict__ ids,
+                               const float4 *__restrict__ pos, DevConfig cfg)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SubState &st = subs[list[i]];
+  const int nu = st.is_orphan ? st.n_own : st.n_src;
+  if (nu < cfg.min_num_part && st.death == -1) st.death = cfg.snapshot_index;
+  st.iterations = 0;
+  if (nu == 0)
+  {
+    st.nbound = 0;
+    st.mbound = 0.f;
+  }
+  else if (nu == 1)
+  {
+    st.nbound = 1;
+    st.mbound = pos[ids[st.slot_base]].w;
+  }
+  else
+  { // disruption without iterating
+    st.nbound = 1;
+    for (int j = 0; j < 3; j++) { st.ref_pos[j] = st.mb_pos[j]; st.ref_vel[j] = st.mb_vel[j]; }
+    st.mbound = pos[ids[st.slot_base]].w;
+    st.spec_pot = st.spec_kin = 0.f;
+    st.am[0] = st.am[1] = st.am[2] = 0.f;
+  }
+  st.nlast = st.nbound;
+  st.status = kDone;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// round kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) gather_src_kernel(const Segment *__restrict__ segs, const int *__restrict__ tree_off, int nseg, int S,
+                                                             const int *__restrict__ ids, const float4 *__restrict__ pos,
+                                                             float4 *__restrict__ tpos, int *__restrict__ ts_seg)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  int a = find_seg(tree_off, nseg, k);
+  const Segment sg = segs[a];
+  int64_t slot = sg.slot_base + sg.tree_first + (k - sg.tree_off);
+  tpos[k] = pos[ids[slot]];
+  ts_seg[k] = a;
+}
+
+// ids of the sorted sources (read phase), then written back in key order for full-evaluation segments:
+// the Elist order inside [0,Nlast) is free in exact mode, and key order makes walk targets coherent.
+__global__ void __launch_bounds__(kBlock) sorted_ids_read_kernel(const Segment *__restrict__ segs, const int *__restrict__ ts_seg,
+                                                                  const int *__restrict__ sperm, int S, const int *__restrict__ ids,
+                                                                  int *__restrict__ tmp)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const Segment sg = segs[ts_seg[k]];
+  int src = sperm[k]; // S-index before sorting (same segment)
+  tmp[k] = ids[sg.slot_base + sg.tree_first + (src - sg.tree_off)];
+}
+__global__ void __launch_bounds__(kBlock) sorted_ids_write_kernel(const Segment *__restrict__ segs, const int *__restrict__ ts_seg, int S,
+                                                                   const int *__restrict__ tmp, int *__restrict__ ids)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  const Segment sg = segs[ts_seg[k]];
+  if (sg.mode == kWalkUnbindFull) ids[sg.slot_base + sg.tree_first + (k - sg.tree_off)] = tmp[k];
+}
+
+__global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_off, int nseg, int T,
+                                                          const float4 *__restrict__ spos, const int *__restrict__ ids,
+                                                          const float4 *__restrict__ pos, float4 *__restrict__ tgt_pm,
+                                                          int64_t *__restrict__ tgt_slot, int *__restrict__ tgt_seg)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int a = find_seg(tgt_off, nseg, t);
+  const Segment sg = segs[a];
+  int j = t - sg.tgt_off;
+  int64_t slot = sg.slot_base + j;
+  float4 p;
+  if (sg.mode == kWalkUnbindFull)
+    p = spos[sg.tree_off + j]; // target j is sorted source j; w = its own mass (self term)
+  else
+  {
+    p = pos[ids[slot]];
+    p.w = 0.f; // not in the tree: no self term (src/subhalo_unbind.cpp:327)
+  }
+  tgt_pm[t] = p;
+  tgt_slot[t] = slot;
+  tgt_seg[t] = a;
+}
+
+__global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, DevConfig cfg)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nseg) return;
+  SubState &st = subs[segs[a].sub];
+  st.iterations++;
+  st.count_bound = 0;
+  for (int j = 0; j < 8; j++) st.sums[j] = 0.0;
+  if (segs[a].mode == kWalkUnbindCorrect)
+  { // RefVelDiff = RelativeVelocity(OldRef -> Ref), dK = 0.5*|RefVelDiff|^2  (src/subhalo_unbind.cpp:314-316)
+    float d[3];
+    for (int j = 0; j < 3; j++)
+    {
+      float dx = __fsub_rn(st.old_ref_pos[j], st.ref_pos[j]);
+      if (cfg.periodic) dx = nearest_f(dx, cfg.box_size, cfg.box_half);
+      float dv = __fsub_rn(st.old_ref_vel[j], st.ref_vel[j]);
+      d[j] = __fadd_rn(dv, __fmul_rn(__fmul_rn(cfg.hz, cfg.scale_factor), dx));
+      st.ref_diff[j] = d[j];
+    }
+    float vn = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+    st.dK = (float)(0.5 * (double)vn);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) count_bound_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
+                                                              const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
+                                                              SubState *__restrict__ subs)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = t < T;
+  int a = valid ? tgt_seg[t] : -1;
+  bool bound = valid && (E[tgt_slot[t]] < 0.f);
+  int a0 = __shfl_sync(0xffffffffu, a, 0);
+  if (__all_sync(0xffffffffu, a == a0))
+  {
+    unsigned m = __ballot_sync(0xffffffffu, bound);
+    if ((threadIdx.x & 31) == 0 && m && a0 >= 0) atomicAdd(&subs[segs[a0].sub].count_bound, __popc(m));
+  }
+  else if (bound)
+    atomicAdd(&subs[segs[a].sub].count_bound, 1);
+}
+
+// PartitionBindingEnergy result -> disruption / CorrectionLoop / convergence (src/subhalo_unbind.cpp:357-403)
+__global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids_orig,
+                              const float4 *__restrict__ pos, DevConfig cfg)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nseg) return;
+  SubState &st = subs[segs[a].sub];
+  const int Nlast = segs[a].tgt_n;
+  const int Nbound = st.count_bound;
+  st.nlast = Nlast;
+  if (Nbound < cfg.min_num_part)
+  {
+    st.nbound = 1;
+    st.nlast = 1;
+    if (st.death == -1) st.death = cfg.snapshot_index;
+    for (int j = 0; j < 3; j++) { st.ref_pos[j] = st.mb_pos[j]; st.ref_vel[j] = st.mb_vel[j]; }
+    st.mbound = pos[ids_orig[st.slot_base]].w; // Particles[0] is the old most-bound particle (exact mode: untouched order)
+    st.spec_pot = st.spec_kin = 0.f;
+    st.am[0] = st.am[1] = st.am[2] = 0.f;
+    st.status = kDisrupted;
+    return;
+  }
+  st.nbound = Nbound;
+  const int Ndiff = Nlast - Nbound;
+  if (Ndiff < Nbound && (cfg.max_sample <= 0 || Ndiff < cfg.max_sample))
+  {
+    st.correction = 1;
+    for (int j = 0; j < 3; j++) { st.old_ref_pos[j] = st.ref_pos[j]; st.old_ref_vel[j] = st.ref_vel[j]; }
+  }
+  if ((float)Nbound >= __fmul_rn((float)Nlast, cfg.bound_mass_precision))
+  {
+    st.status = kConverged;
+    if (st.death != -1) st.death = -1;
+    if (st.sinktrack != -1) { st.sink = -1; st.sinktrack = -1; }
+  }
+}
+
+// One key per target: (segment, bound|unbound) major, then E (where the reference sorts) or the current
+// position (where it does not): a single radix sort = partition + tail sort + final bound sort.
+__global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
+                                                            const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
+                                                            const SubState *__restrict__ subs, uint64_t *__restrict__ key, int *__restrict__ val)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int a = tgt_seg[t];
+  const Segment sg = segs[a];
+  int status = subs[sg.sub].status;
+  float e = E[tgt_slot[t]];
+  uint32_t j = (uint32_t)(t - sg.tgt_off);
+  uint64_t hi, low;
+  if (status == kDisrupted) { hi = 2ull * a; low = j; }
+  else if (!(e < 0.f)) { hi = 2ull * a + 1; low = float_to_ordered(e); }
+  else { hi = 2ull * a; low = (status == kConverged) ? float_to_ordered(e) : j; }
+  key[t] = (hi << 32) | low;
+  val[t] = t;
+}
+__global__ void __launch_bounds__(kBlock) permute_read_kernel(const int *__restrict__ order, const int64_t *__restrict__ tgt_slot, int T,
+                                                               const int *__restrict__ ids, const float *__restrict__ E,
+                                                               int *__restrict__ tmp_id, float *__restrict__ tmp_E)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= T) return;
+  int64_t slot = tgt_slot[order[p]];
+  tmp_id[p] = ids[slot];
+  tmp_E[p] = E[slot];
+}
+__global__ void __launch_bounds__(kBlock) permute_write_kernel(const int64_t *__restrict__ tgt_slot, int T, const int *__restrict__ tmp_id,
+                                                                const float *__restrict__ tmp_E, int *__restrict__ ids, float *__restrict__ E)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= T) return;
+  int64_t slot = tgt_slot[p];
+  ids[slot] = tmp_id[p];
+  E[slot] = tmp_E[p];
+}
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// accumulate NV doubles per target into subs[sub].sums with warp aggregation
+template <int NV>
+__device__ __forceinline__ void seg_accumulate(const double (&v)[NV], bool contributes, int a, int sub, SubState *subs)
+{
+  int a0 = __shfl_sync(0xffffffffu, a, 0);
+  int sub0 = __shfl_sync(0xffffffffu, sub, 0);
+  if (__all_sync(0xffffffffu, a == a0))
+  {
+    if (a0 < 0) return;
+    if (!__any_sync(0xffffffffu, contributes)) return;
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+    {
+      double s = warp_sum_d(contributes ? v[i] : 0.0);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&subs[sub0].sums[i], s);
+    }
+  }
+  else if (contributes)
+  {
+#pragma unroll
+    for (int i = 0; i < NV; i++) atomicAdd(&subs[sub].sums[i], v[i]);
+  }
+}
+
+// EnergySnapshot_t::AverageVelocity / AveragePosition over the first Nbound (src/subhalo_unbind.cpp:108-188)
+__global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+                                                               const int *__restrict__ ids, const float4 *__restrict__ pos,
+                                                               const float4 *__restrict__ vel, SubState *__restrict__ subs, DevConfig cfg)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = t < T;
+  int a = valid ? tgt_seg[t] : -1;
+  int sub = -1;
+  bool contributes = false;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (valid)
+  {
+    const Segment sg = segs[a];
+    sub = sg.sub;
+    const SubState &st = subs[sub];
+    int j = t - sg.tgt_off;
+    if (st.status != kDisrupted && j < st.nbound)
+    {
+      contributes = true;
+      int id = ids[sg.slot_base + j];
+      float4 x = pos[id], u = vel[id];
+      float m = x.w;
+      v[0] = (double)m;
+      v[1] = (double)__fmul_rn(u.x, m); // float product, double accumulate (:129-131)
+      v[2] = (double)__fmul_rn(u.y, m);
+      v[3] = (double)__fmul_rn(u.z, m);
+      if (cfg.periodic)
+      {
+        float4 o = pos[ids[sg.slot_base]]; // origin = first particle (:152-154)
+        v[4] = nearest_d((double)x.x - (double)o.x, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
+        v[5] = nearest_d((double)x.y - (double)o.y, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
+        v[6] = nearest_d((double)x.z - (double)o.z, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
+      }
+      else
+      {
+        v[4] = (double)__fmul_rn(x.x, m);
+        v[5] = (double)__fmul_rn(x.y, m);
+        v[6] = (double)__fmul_rn(x.z, m);
+      }
+    }
+  }
+  seg_accumulate<7>(v, contributes, a, sub, subs);
+}
+
+__global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
+                              const float4 *__restrict__ pos, const float4 *__restrict__ vel, DevConfig cfg)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nseg) return;
+  SubState &st = subs[segs[a].sub];
+  if (st.status == kDisrupted) return;
+  int id0 = ids[st.slot_base];
+  float4 x0 = pos[id0], v0 = vel[id0];
+  if (st.nbound == 1)
+  {
+    st.ref_vel[0] = v0.x; st.ref_vel[1] = v0.y; st.ref_vel[2] = v0.z;
+    st.ref_pos[0] = x0.x; st.ref_pos[1] = x0.y; st.ref_pos[2] = x0.z;
+    st.mbound = x0.w;
+  }
+  else
+  {
+    double msum = st.sums[0];
+    st.mbound = (float)msum;
+    for (int j = 0; j < 3; j++) st.ref_vel[j] = (float)(st.sums[1 + j] / msum);
+    double o[3] = {(double)x0.x, (double)x0.y, (double)x0.z};
+    for (int j = 0; j < 3; j++)
+    {
+      double s = st.sums[4 + j] / msum;
+      if (cfg.periodic) s += o[j];
+      st.ref_pos[j] = (float)s;
+    }
+  }
+  for (int j = 0; j < 8; j++) st.sums[j] = 0.0;
+}
+
+// EnergySnapshot_t::AverageKinematics (src/subhalo_unbind.cpp:189-232) for subhaloes that converged this round
+__global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+                                                             const int *__restrict__ ids, const float *__restrict__ E,
+                                                             const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                             SubState *__restrict__ subs, DevConfig cfg)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = t < T;
+  int a = valid ? tgt_seg[t] : -1;
+  int sub = -1;
+  bool contributes = false;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  if (valid)
+  {
+    const Segment sg = segs[a];
+    sub = sg.sub;
+    const SubState &st = subs[sub];
+    int j = t - sg.tgt_off;
+    if (st.status == kConverged && j < st.nbound)
+    {
+      contributes = true;
+      int64_t slot = sg.slot_base + j;
+      int id = ids[slot];
+      float4 x = pos[id], u = vel[id];
+      float m = x.w;
+      const float xs[3] = {x.x, x.y, x.z}, us[3] = {u.x, u.y, u.z};
+      double dx[3], dv[3], K = 0.0;
+      for (int c = 0; c < 3; c++)
+      {
+        dx[c] = (double)__fsub_rn(xs[c], st.ref_pos[c]);
+        if (cfg.periodic) dx[c] = nearest_d(dx[c], (double)cfg.box_size, (double)cfg.box_half);
+        dx[c] *= (double)cfg.scale_factor;
+        dv[c] = (double)__fsub_rn(us[c], st.ref_vel[c]) + (double)cfg.hz * dx[c];
+        K += dv[c] * dv[c] * (double)m;
+      }
+      v[0] = (double)__fmul_rn(E[slot], m);
+      v[1] = K;
+      v[2] = (dx[1] * dv[2] - dx[2] * dv[1]) * (double)m;
+      v[3] = (dx[2] * dv[0] - dx[0] * dv[2]) * (double)m;
+      v[4] = (dx[0] * dv[1] - dx[1] * dv[0]) * (double)m;
+      v[5] = (double)m;
+    }
+  }
+  seg_accumulate<6>(v, contributes, a, sub, subs);
+}
+
+struct RoundResult
+{
+  int status, nbound, nlast, correction;
+};
+
+__global__ void finalize_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
+                                const float4 *__restrict__ pos, const float4 *__restrict__ vel, RoundResult *__restrict__ res)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nseg) return;
+  SubState &st = subs[segs[a].sub];
+  if (st.status == kConverged)
+  {
+    if (st.nbound > 1)
+    {
+      double M = st.sums[5], Eav = st.sums[0] / M, K = st.sums[1] * (0.5 / M);
+      st.spec_pot = (float)(Eav - K);
+      st.spec_kin = (float)K;
+      st.am[0] = (float)(st.sums[2] / M);
+      st.am[1] = (float)(st.sums[3] / M);
+      st.am[2] = (float)(st.sums[4] / M);
+    }
+    else
+    {
+      st.spec_pot = st.spec_kin = 0.f;
+      st.am[0] = st.am[1] = st.am[2] = 0.f;
+    }
+    int id0 = ids[st.slot_base]; // Particles[0] after the final E-sort (:417-418)
+    float4 x0 = pos[id0], v0 = vel[id0];
+    st.mb_pos[0] = x0.x; st.mb_pos[1] = x0.y; st.mb_pos[2] = x0.z;
+    st.mb_vel[0] = v0.x; st.mb_vel[1] = v0.y; st.mb_vel[2] = v0.z;
+  }
+  res[a] = RoundResult{st.status, st.nbound, st.nlast, st.correction};
+  if (st.status == kConverged || st.status == kDisrupted) st.status = kDone;
+}
+
+// final packing of Subhalo_t::Particles (and SAVE_BINDING_ENERGY energies) into the caller's layout
+__global__ void __launch_bounds__(kBlock) pack_output_kernel(const int64_t *__restrict__ out_off, const int64_t *__restrict__ slot_base,
+                                                              const int *__restrict__ nbound, int nsub, int64_t total,
+                                                              const int *__restrict__ ids, const float *__restrict__ E,
+                                                              int *__restrict__ out_ids, float *__restrict__ out_E)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int s = find_seg64(out_off, nsub, i);
+  int64_t o = i - out_off[s];
+  out_ids[i] = ids[slot_base[s] + o];
+  if (out_E) out_E[i] = (o < nbound[s]) ? E[slot_base[s] + o] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------------
+template <class T>
+static T *upload(Arena &arena, const std::vector<T> &v, cudaStream_t stream)
+{
+  T *d = arena.alloc<T>((int64_t)v.size());
+  if (!v.empty()) HBT_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, stream));
+  return d;
+}
+
+static void run_seg_copy(Context &c, const std::vector<CopyJob> &jobs, const std::vector<int64_t> &job_off, const int *src, int *dst)
+{
+  if (jobs.empty() || job_off.back() == 0) return;
+  // small persistent side buffers: jobs are tiny compared with the arena arrays
+  CopyJob *d_jobs = nullptr;
+  int64_t *d_off = nullptr;
+  HBT_CUDA(cudaMalloc(&d_jobs, sizeof(CopyJob) * jobs.size()));
+  HBT_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * job_off.size()));
+  HBT_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CopyJob) * jobs.size(), cudaMemcpyHostToDevice, c.stream));
+  HBT_CUDA(cudaMemcpyAsync(d_off, job_off.data(), sizeof(int64_t) * job_off.size(), cudaMemcpyHostToDevice, c.stream));
+  int64_t total = job_off.back();
+  seg_copy_kernel<<<grid_for(total), kBlock, 0, c.stream>>>(d_jobs, d_off, (int)jobs.size(), total, src, dst);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches++;
+  HBT_CUDA(cudaStreamSynchronize(c.stream));
+  cudaFree(d_jobs);
+  cudaFree(d_off);
+}
+
+// one potential evaluation for every active subhalo of the level
+static void run_round(Context &c, std::vector<int> &active)
+{
+  const int nseg = (int)active.size();
+  std::vector<Segment> segs(nseg);
+  std::vector<int> tree_off(nseg + 1), tgt_off(nseg + 1), warp_off(nseg + 1);
+  int64_t S = 0, T = 0, W = 0;
+  for (int a = 0; a < nseg; a++)
+  {
+    SubHost &h = c.subs[active[a]];
+    Segment &sg = segs[a];
+    sg.slot_base = h.slot_base;
+    sg.sub = active[a];
+    sg.mode = h.correction ? kWalkUnbindCorrect : kWalkUnbindFull;
+    if (h.correction)
+    {
+      sg.tree_first = h.nbound;
+      sg.tree_n = h.nlast - h.nbound;
+    }
+    else
+    {
+      sg.tree_first = 0;
+      sg.tree_n = h.nbound;
+    }
+    sg.tgt_n = h.nbound;
+    sg.tree_off = (int)S;
+    sg.tgt_off = (int)T;
+    sg.warp_off = (int)W;
+    tree_off[a] = (int)S;
+    tgt_off[a] = (int)T;
+    warp_off[a] = (int)W;
+    S += sg.tree_n;
+    T += sg.tgt_n;
+    W += (sg.tgt_n + 31) / 32;
+    if (S > 0x3fffffff || T > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "round larger than 2^30 particles"};
+  }
+  tree_off[nseg] = (int)S;
+  tgt_off[nseg] = (int)T;
+  warp_off[nseg] = (int)W;
+
+  Arena &ar = c.arena;
+  ar.reset();
+  ar.reserve(tree_arena_bytes(S, nseg) + T * 64 + (int64_t)nseg * 128);
+  cudaStream_t st = c.stream;
+  Segment *d_segs = upload(ar, segs, st);
+  int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st), *d_warp_off = upload(ar, warp_off, st);
+
+  HBT_CUDA(cudaEventRecord(c.ev[0], st));
+  TreeArrays tr;
+  tr.S = (int)S;
+  tr.nseg = nseg;
+  tr.tree_off = d_tree_off;
+  tr.tpos = ar.alloc<float4>(S);
+  tr.ts_seg = ar.alloc<int>(S);
+  tr.bbox = ar.alloc<uint32_t>(6 * (int64_t)nseg);
+  gather_src_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, d_tree_off, nseg, (int)S, c.d_ids, c.d_pos, tr.tpos, tr.ts_seg);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches++;
+  launch_init_bbox(tr.bbox, nseg, st, c.ls);
+  launch_bbox(tr.tpos, tr.ts_seg, (int)S, tr.bbox, st, c.ls);
+  build_trees(tr, ar, c.cfg, st, c.ls);
+  int *tmp_ids = ar.alloc<int>(S);
+  sorted_ids_read_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, tr.sperm, (int)S, c.d_ids, tmp_ids);
+  HBT_CHECK_LAUNCH();
+  sorted_ids_write_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, (int)S, tmp_ids, c.d_ids);
+  HBT_CHECK_LAUNCH();
+  float4 *tgt_pm = ar.alloc<float4>(T);
+  int64_t *tgt_slot = ar.alloc<int64_t>(T);
+  int *tgt_seg = ar.alloc<int>(T);
+  targets_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, d_tgt_off, nseg, (int)T, tr.spos, c.d_ids, c.d_pos, tgt_pm, tgt_slot, tgt_seg);
+  HBT_CHECK_LAUNCH();
+  pre_walk_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.cfg);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches += 4;
+  HBT_CUDA(cudaEventRecord(c.ev[1], st));
+
+  WalkArgs wa{};
+  wa.node_xm = tr.node_xm;
+  wa.node_aux = tr.node_aux;
+  wa.cellcount = tr.cellcount;
+  wa.tree_off = d_tree_off;
+  wa.segs = d_segs;
+  wa.warp_off = d_warp_off;
+  wa.nseg = nseg;
+  wa.nwarps = (int)W;
+  wa.tgt_pm = tgt_pm;
+  wa.tgt_slot = tgt_slot;
+  wa.ids = c.d_ids;
+  wa.vel = c.d_vel;
+  wa.E = c.d_E;
+  wa.subs = c.d_subs;
+  wa.out = nullptr;
+  wa.counters = c.count_interactions ? c.d_counters : nullptr;
+  launch_walk(wa, c.cfg, st, c.ls);
+  HBT_CUDA(cudaEventRecord(c.ev[2], st));
+
+  count_bound_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);
+  HBT_CHECK_LAUNCH();
+  state1_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids_orig, c.d_pos, c.cfg);
+  HBT_CHECK_LAUNCH();
+  // partition + E-sorts in one radix sort
+  uint64_t *key_a = ar.alloc<uint64_t>(T), *key_b = ar.alloc<uint64_t>(T);
+  int *val_a = ar.alloc<int>(T), *val_b = ar.alloc<int>(T);
+  sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, key_a, val_a);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches += 3;
+  {
+    int bits = 33;
+    while ((1ll << (bits - 32)) < 2ll * nseg) bits++;
+    cub::DoubleBuffer<uint64_t> dk(key_a, key_b);
+    cub::DoubleBuffer<int> dv(val_a, val_b);
+    size_t tb = 0;
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)T, 0, bits, st));
+    void *tmp = ar.alloc<char>((int64_t)tb);
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)T, 0, bits, st));
+    c.ls.launches += 1 + (bits + 7) / 8;
+    int *tmp_id = ar.alloc<int>(T);
+    float *tmp_E = ar.alloc<float>(T);
+    permute_read_kernel<<<grid_for(T), kBlock, 0, st>>>(dv.Current(), tgt_slot, (int)T, c.d_ids, c.d_E, tmp_id, tmp_E);
+    HBT_CHECK_LAUNCH();
+    permute_write_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_slot, (int)T, tmp_id, tmp_E, c.d_ids, c.d_E);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches += 2;
+  }
+  frame_reduce_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_pos, c.d_vel, c.d_subs, c.cfg);
+  HBT_CHECK_LAUNCH();
+  state2_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, c.cfg);
+  HBT_CHECK_LAUNCH();
+  kinematics_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg);
+  HBT_CHECK_LAUNCH();
+  RoundResult *d_res = ar.alloc<RoundResult>(nseg);
+  finalize_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, d_res);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches += 4;
+  HBT_CUDA(cudaEventRecord(c.ev[3], st));
+  std::vector<RoundResult> res(nseg);
+  HBT_CUDA(cudaMemcpyAsync(res.data(), d_res, sizeof(RoundResult) * nseg, cudaMemcpyDeviceToHost, st));
+  HBT_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+  c.stats.build_ms += ms;
+  cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]);
+  c.stats.walk_ms += ms;
+  cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
+  c.stats.other_ms += ms;
+  c.stats.rounds++;
+  c.stats.tree_builds += nseg;
+  c.stats.walk_targets += T;
+
+  std::vector<int> next;
+  for (int a = 0; a < nseg; a++)
+  {
+    SubHost &h = c.subs[active[a]];
+    h.nbound = res[a].nbound;
+    h.nlast = res[a].nlast;
+    h.correction = res[a].correction;
+    h.iterations++;
+    if (res[a].status == kActive)
+      next.push_back(active[a]);
+    else
+    {
+      h.done = true;
+      h.disrupted = res[a].status == kDisrupted;
+    }
+  }
+  active.swap(next);
+}
+
+void execute_batch(Context &c)
+{
+  if (!c.staged) throw CudaError{HBTU_ERR_INVALID, "hbtu_execute before hbtu_stage"};
+  cudaStream_t st = c.stream;
+  const int nsub = (int)c.nsub;
+  c.ls.launches = 0;
+  std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms));
+  if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
+  if (c.cfg.max_sample > 0)
+    for (int s = 0; s < nsub; s++)
+      if (c.subs[s].cap > c.cfg.max_sample) throw CudaError{HBTU_ERR_UNSUPPORTED, "MaxSampleSizeOfPotentialEstimate>0 with a larger source is not built yet"};
+
+  // (re)initialise per-subhalo state from the staged inputs
+  std::vector<SubState> init(nsub);
+  for (int s = 0; s < nsub; s++)
+  {
+    SubHost &h = c.subs[s];
+    const hbtu_sub_io &io = c.io_in[s];
+    SubState z;
+    std::memset(&z, 0, sizeof(z));
+    z.slot_base = h.slot_base;
+    z.part_begin = h.part_begin;
+    z.n_own = h.n_own;
+    z.n_src = h.n_own;
+    z.status = kPending;
+    z.death = io.snapshot_index_of_death;
+    z.sink = io.snapshot_index_of_sink;
+    z.sinktrack = io.sink_track_id;
+    z.is_orphan = io.nbound <= 1;
+    for (int j = 0; j < 3; j++)
+    {
+      z.ref_pos[j] = (float)io.avg_pos[j];
+      z.ref_vel[j] = (float)io.avg_vel[j];
+      z.mb_pos[j] = (float)io.mostbound_pos[j];
+      z.mb_vel[j] = (float)io.mostbound_vel[j];
+      z.am[j] = io.specific_angular_momentum[j];
+    }
+    z.spec_pot = io.specific_self_potential_energy;
+    z.spec_kin = io.specific_self_kinetic_energy;
+    z.mbound = io.mbound;
+    z.nbound = (int)io.nbound;
+    init[s] = z;
+    h.n_src = h.n_own;
+    h.nbound = h.nlast = 0;
+    h.correction = 0;
+    h.done = h.disrupted = false;
+    h.iterations = 0;
+    h.is_orphan = io.nbound <= 1;
+  }
+  HBT_CUDA(cudaMemcpyAsync(c.d_subs, init.data(), sizeof(SubState) * nsub, cudaMemcpyHostToDevice, st));
+  if (c.N > 0)
+  {
+    init_ids_kernel<<<grid_for(c.N), kBlock, 0, st>>>(c.d_part_offset, c.d_slot_base, nsub, c.N, c.d_ids);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches++;
+  }
+  HBT_CUDA(cudaStreamSynchronize(st));
+
+  for (int level = c.max_depth; level >= 0; level--)
+  {
+    const std::vector<int> &lv = c.levels[level];
+    // 1. feed children's unbound tails into this level's sources (src/subhalo_unbind.cpp:437-443)
+    {
+      std::vector<CopyJob> jobs;
+      std::vector<int64_t> job_off{0};
+      for (int s : lv)
+      {
+        SubHost &h = c.subs[s];
+        int64_t n = h.n_own;
+        for (int ch : h.children)
+        {
+          SubHost &k = c.subs[ch];
+          int64_t tail = k.n_src - k.nbound;
+          if (tail > 0)
+          {
+            jobs.push_back(CopyJob{h.slot_base + n, k.slot_base + k.nbound});
+            job_off.push_back(job_off.back() + tail);
+            n += tail;
+          }
+        }
+        h.n_src = (int)n;
+      }
+      run_seg_copy(c, jobs, job_off, c.d_ids, c.d_ids);
+      // snapshot of the input order (needed for disrupted subhaloes and orphans)
+      std::vector<CopyJob> snap;
+      std::vector<int64_t> snap_off{0};
+      for (int s : lv)
+        if (c.subs[s].n_src > 0)
+        {
+          snap.push_back(CopyJob{c.subs[s].slot_base, c.subs[s].slot_base});
+          snap_off.push_back(snap_off.back() + c.subs[s].n_src);
+        }
+      run_seg_copy(c, snap, snap_off, c.d_ids, c.d_ids_orig);
+    }
+    // 2. classify
+    std::vector<int> active, trivial;
+    for (int s : lv)
+    {
+      SubHost &h = c.subs[s];
+      int nu = h.is_orphan ? h.n_own : h.n_src;
+      if (nu < 2 || nu < c.cfg.min_num_part)
+      {
+        trivial.push_back(s);
+        h.nbound = nu == 0 ? 0 : 1;
+        h.done = true;
+        h.disrupted = nu >= 2;
+      }
+      else
+      {
+        active.push_back(s);
+        h.nbound = h.nlast = nu;
+      }
+    }
+    { // n_src and the active flag on the device
+      std::vector<LevelInit> li(lv.size());
+      for (size_t i = 0; i < lv.size(); i++) li[i] = LevelInit{lv[i], c.subs[lv[i]].n_src, c.subs[lv[i]].done ? 0 : 1};
+      LevelInit *d_li = nullptr;
+      HBT_CUDA(cudaMalloc(&d_li, sizeof(LevelInit) * li.size()));
+      HBT_CUDA(cudaMemcpyAsync(d_li, li.data(), sizeof(LevelInit) * li.size(), cudaMemcpyHostToDevice, st));
+      level_init_kernel<<<grid_for((int64_t)li.size()), kBlock, 0, st>>>(d_li, (int)li.size(), c.d_subs);
+      HBT_CHECK_LAUNCH();
+      c.ls.launches++;
+      HBT_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_li);
+    }
+    if (!trivial.empty())
+    {
+      int *d_list = nullptr;
+      HBT_CUDA(cudaMalloc(&d_list, sizeof(int) * trivial.size()));
+      HBT_CUDA(cudaMemcpyAsync(d_list, trivial.data(), sizeof(int) * trivial.size(), cudaMemcpyHostToDevice, st));
+      trivial_kernel<<<grid_for((int64_t)trivial.size()), kBlock, 0, st>>>(d_list, (int)trivial.size(), c.d_subs, c.d_ids, c.d_pos, c.cfg);
+      HBT_CHECK_LAUNCH();
+      c.ls.launches++;
+      HBT_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_list);
+    }
+    // 3. iterate
+    while (!active.empty()) run_round(c, active);
+    // 4. restore the input order where the reference leaves Particles untouched: disrupted subhaloes
+    //    (no permutation copy, :361-379) and orphans (the unbound backup is discarded, :444-446)
+    {
+      std::vector<CopyJob> jobs;
+      std::vector<int64_t> job_off{0};
+      for (int s : lv)
+      {
+        SubHost &h = c.subs[s];
+        if ((h.disrupted || h.is_orphan) && h.n_src > 1)
+        {
+          jobs.push_back(CopyJob{h.slot_base, h.slot_base});
+          job_off.push_back(job_off.back() + h.n_src);
+        }
+      }
+      run_seg_copy(c, jobs, job_off, c.d_ids_orig, c.d_ids);
+    }
+  }
+  if (c.count_interactions)
+  {
+    unsigned long long cnt[2];
+    HBT_CUDA(cudaMemcpy(cnt, c.d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    c.stats.pair_interactions = (int64_t)cnt[0];
+    c.stats.nodes_visited = (int64_t)cnt[1];
+  }
+  c.stats.kernel_launches = c.ls.launches;
+  c.executed = true;
+}
+
+void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  if (!c.executed) throw CudaError{HBTU_ERR_INVALID, "hbtu_fetch before hbtu_execute"};
+  cudaStream_t st = c.stream;
+  const int nsub = (int)c.nsub;
+  cudaEvent_t e0 = c.ev[0], e1 = c.ev[1];
+  HBT_CUDA(cudaEventRecord(e0, st));
+  std::vector<SubState> fin(nsub);
+  HBT_CUDA(cudaMemcpyAsync(fin.data(), c.d_subs, sizeof(SubState) * nsub, cudaMemcpyDeviceToHost, st));
+  HBT_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> out_off(nsub + 1, 0), slot_base(nsub);
+  std::vector<int> nb(nsub);
+  for (int s = 0; s < nsub; s++)
+  {
+    const SubState &z = fin[s];
+    SubHost &h = c.subs[s];
+    int64_t full = h.n_src, ns = full;
+    if (c.flags & HBTU_FLAG_TRUNCATE_SOURCE)
+    { // Subhalo_t::TruncateSource, src/subhalo_unbind.cpp:449-458 (int*float -> float -> int)
+      int64_t nsrc = z.nbound <= 1 ? z.nbound : (int64_t)((float)z.nbound * c.cfg.relax_factor);
+      if (nsrc > full) nsrc = full;
+      ns = nsrc;
+    }
+    out_off[s + 1] = out_off[s] + ns;
+    slot_base[s] = h.slot_base;
+    nb[s] = z.nbound;
+    hbtu_sub_io &o = io[s];
+    for (int j = 0; j < 3; j++)
+    {
+      o.avg_pos[j] = z.ref_pos[j];
+      o.avg_vel[j] = z.ref_vel[j];
+      o.mostbound_pos[j] = z.mb_pos[j];
+      o.mostbound_vel[j] = z.mb_vel[j];
+      o.specific_angular_momentum[j] = z.am[j];
+    }
+    o.nbound = z.nbound;
+    o.sink_track_id = z.sinktrack;
+    o.snapshot_index_of_death = z.death;
+    o.snapshot_index_of_sink = z.sink;
+    o.mbound = z.mbound;
+    o.specific_self_potential_energy = z.spec_pot;
+    o.specific_self_kinetic_energy = z.spec_kin;
+    o.nsource_full = full;
+    o.nsource = ns;
+    o.iterations = z.iterations;
+    o.reserved = 0;
+  }
+  const int64_t total = out_off[nsub];
+  if (total > order_capacity) throw CudaError{HBTU_ERR_CAPACITY, "order_out too small"};
+  std::memcpy(order_offset, out_off.data(), sizeof(int64_t) * (nsub + 1));
+  if (total > 0)
+  {
+    c.arena.reset();
+    c.arena.reserve(total * 8 + (int64_t)nsub * 24 + (1 << 20));
+    int64_t *d_off = upload(c.arena, out_off, st), *d_sb = upload(c.arena, slot_base, st);
+    int *d_nb = upload(c.arena, nb, st);
+    int *d_out = c.arena.alloc<int>(total);
+    float *d_oe = energy_out ? c.arena.alloc<float>(total) : nullptr;
+    pack_output_kernel<<<grid_for(total), kBlock, 0, st>>>(d_off, d_sb, d_nb, nsub, total, c.d_ids, c.d_E, d_out, d_oe);
+    HBT_CHECK_LAUNCH();
+    HBT_CUDA(cudaMemcpyAsync(order_out, d_out, sizeof(int) * total, cudaMemcpyDeviceToHost, st));
+    if (energy_out) HBT_CUDA(cudaMemcpyAsync(energy_out, d_oe, sizeof(float) * total, cudaMemcpyDeviceToHost, st));
+    c.stats.d2h_bytes = total * (energy_out ? 8 : 4) + (int64_t)nsub * sizeof(SubState);
+  }
+  HBT_CUDA(cudaEventRecord(e1, st));
+  HBT_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  c.stats.d2h_ms = ms;
+}
+
+} // namespace hbt

@@ -1,0 +1,125 @@
+"""Host-side mirror of the reference's unbinding interface on top of the C-ABI.
+
+``UnbindContext`` plays the role of ``SubhaloSnapshot_t::RefineParticles`` /
+``Subhalo_t::Unbind`` (reference: src/subhalo_unbind.cpp:263-516) and of
+``GravityTree_t::EvaluatePotential/BindingEnergy`` (src/gravity_tree.cpp:79-175) for callers
+written in Python (tests, bench.py).  It only marshals arrays into ``hbtu_*`` calls of
+``libhbtunbind.so``; there is no Python or CPU implementation of the path behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class UnbindError(RuntimeError):
+    """The reference path cannot fail; the C-ABI reports errors as negative codes, which become this."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"hbtu error {code}: {msg}")
+        self.code = code
+
+
+class BatchResult:
+    """Outputs of one batch: per-subhalo records + the new ``Subhalo_t::Particles`` orders."""
+
+    def __init__(self, io, order_offset, order, energy):
+        self.io, self.order_offset, self.order, self.energy = io, order_offset, order, energy
+
+    def particles(self, s: int) -> np.ndarray:
+        b = self.order_offset[s]
+        return self.order[b : b + self.io["nsource"][s]]
+
+    def bound(self, s: int) -> np.ndarray:
+        b = self.order_offset[s]
+        return self.order[b : b + self.io["nbound"][s]]
+
+
+class UnbindContext:
+    def __init__(self, params: capi.Params, lib_path: str | None = None):
+        self._lib = capi.load_library(lib_path)
+        self._lib.hbtu_set_counting.argtypes = [C.c_void_p, C.c_int]
+        self._ctx = C.c_void_p()
+        self.params = params
+        rc = self._lib.hbtu_create(C.byref(params), C.byref(self._ctx))
+        if rc != capi.HBTU_OK:
+            raise UnbindError(rc, (self._lib.hbtu_last_error(None) or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.hbtu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != capi.HBTU_OK:
+            raise UnbindError(rc, (self._lib.hbtu_last_error(self._ctx) or b"").decode())
+
+    def set_counting(self, on: bool):
+        self._check(self._lib.hbtu_set_counting(self._ctx, int(on)))
+
+    def stats(self) -> capi.Stats:
+        st = capi.Stats()
+        self._check(self._lib.hbtu_get_stats(self._ctx, C.byref(st)))
+        return st
+
+    # -- RefineParticles / RecursiveUnbind / Unbind / TruncateSource ---------------------------------
+    def unbind_batch(self, epoch, snap, flags: int = 0, want_energy: bool = True) -> BatchResult:
+        cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
+        io = snap.io.copy()
+        order_offset = np.zeros(snap.nsub + 1, np.int64)
+        order = np.full(max(cap, 1), -1, np.int32)
+        energy = np.zeros(max(cap, 1), np.float32) if want_energy else None
+        pm = np.ascontiguousarray(snap.pos_mass, np.float32)
+        vv = np.ascontiguousarray(snap.vel, np.float32)
+        rc = self._lib.hbtu_unbind_batch(
+            self._ctx, *capi.batch_args(epoch, snap.part_offset, pm, vv, snap.nest_offset, snap.nest_list, io, flags, cap, order_offset, order, energy)
+        )
+        self._check(rc)
+        return BatchResult(io, order_offset, order, energy)
+
+    def stage(self, epoch, snap, flags: int = 0):
+        pm = np.ascontiguousarray(snap.pos_mass, np.float32)
+        vv = np.ascontiguousarray(snap.vel, np.float32)
+        args = capi.batch_args(epoch, snap.part_offset, pm, vv, snap.nest_offset, snap.nest_list, snap.io, flags, 0, None, None, None)
+        self._check(self._lib.hbtu_stage(self._ctx, *args[:9]))
+        self._staged = snap
+
+    def execute(self):
+        self._check(self._lib.hbtu_execute(self._ctx))
+
+    def fetch(self, want_energy: bool = True) -> BatchResult:
+        snap = self._staged
+        cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
+        io = snap.io.copy()
+        order_offset = np.zeros(snap.nsub + 1, np.int64)
+        order = np.full(max(cap, 1), -1, np.int32)
+        energy = np.zeros(max(cap, 1), np.float32) if want_energy else None
+        P = capi._ptr
+        rc = self._lib.hbtu_fetch(self._ctx, io.ctypes.data_as(C.POINTER(capi.SubIO)), cap, P(order_offset, C.c_int64), P(order, C.c_int32), P(energy, C.c_float))
+        self._check(rc)
+        return BatchResult(io, order_offset, order, energy)
+
+    # -- GravityTree_t::Build + EvaluatePotential / BindingEnergy -------------------------------------
+    def tree_potential(self, epoch, src_pos_mass, tgt_pos, self_mass=None, tgt_vel=None, ref_pos=None, ref_vel=None) -> np.ndarray:
+        src = np.ascontiguousarray(src_pos_mass, np.float32)
+        tgt = np.ascontiguousarray(tgt_pos, np.float32)
+        out = np.zeros(len(tgt), np.float64)
+        sm = None if self_mass is None else np.ascontiguousarray(self_mass, np.float32)
+        tv = None if tgt_vel is None else np.ascontiguousarray(tgt_vel, np.float32)
+        rp = None if ref_pos is None else np.ascontiguousarray(ref_pos, np.float64)
+        rv = None if ref_vel is None else np.ascontiguousarray(ref_vel, np.float64)
+        P = capi._ptr
+        rc = self._lib.hbtu_tree_potential(
+            self._ctx, C.byref(epoch), len(src), P(src, C.c_float), len(tgt), P(tgt, C.c_float), P(sm, C.c_float), P(tv, C.c_float),
+            P(rp, C.c_double), P(rv, C.c_double), P(out, C.c_double))
+        self._check(rc)
+        return out

@@ -1,0 +1,192 @@
+/* hbt_unbind.h - C-ABI of the B200-native HBT+ unbinding path.
+ *
+ * This is the drop-in boundary.  The reference has no
+ * FFI for this path; its seam is three C++ member functions, which a host
+ * shim (integration/subhalo_unbind_b200.cpp) re-implements by pack -> call ->
+ * unpack on top of the entry points declared here:
+ *
+ *   void SubhaloSnapshot_t::RefineParticles()        src/subhalo.h:245, src/subhalo_unbind.cpp:460-516
+ *   void Subhalo_t::Unbind(const Snapshot_t&)        src/subhalo.h:111, src/subhalo_unbind.cpp:263-431
+ *   void Subhalo_t::RecursiveUnbind(...)             src/subhalo.h:112, src/subhalo_unbind.cpp:432-447
+ *   void Subhalo_t::TruncateSource()                 src/subhalo.h:114, src/subhalo_unbind.cpp:449-458
+ *   double GravityTree_t::EvaluatePotential(...)     src/gravity_tree.h:14,  src/gravity_tree.cpp:79-164
+ *   double GravityTree_t::BindingEnergy(...)         src/gravity_tree.h:15,  src/gravity_tree.cpp:166-175
+ *
+ * Plain C, POD only: no STL, no torch types, caller owns every host buffer.
+ * Every function returns HBTU_OK (0) or a negative HBTU_ERR_* code; the text of
+ * the last error of a context is available from hbtu_last_error().  There is
+ * NO CPU fallback: without a CUDA device hbtu_create() fails.
+ *
+ * The same structs and the same batch signature are implemented by the two
+ * CPU checkers used only by tests/bench baselines:
+ *   oracle/_ref/libhbtref_v32.so   (the unmodified reference sources, hbtref_*)
+ *   oracle/libhbtoracle.so         (plain-C restatement, hbto_*)
+ */
+#ifndef HBT_UNBIND_H
+#define HBT_UNBIND_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBTU_ABI_VERSION 1
+
+#define HBTU_OK 0
+#define HBTU_ERR_INVALID (-1)     /* bad argument / malformed nest forest            */
+#define HBTU_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed            */
+#define HBTU_ERR_NOMEM (-3)       /* device or pinned-host allocation failed         */
+#define HBTU_ERR_NODEVICE (-4)    /* no usable sm_100 device: there is no fallback   */
+#define HBTU_ERR_UNSUPPORTED (-5) /* ABI variant not built (e.g. HBT_REAL8)          */
+#define HBTU_ERR_CAPACITY (-6)    /* caller-provided output buffer too small         */
+
+/* POD copy of the Parameter_t fields the path reads (src/config_parser.h:22-123,
+ * derived ones from src/config_parser.cpp:95-103) plus PhysicalConst::G.
+ * Values are passed as double but must hold the HBTReal-rounded value of the
+ * caller's build (float when real_bytes==4), because the reference evaluates
+ * e.g. Nlast*BoundMassPrecision in HBTReal arithmetic (src/subhalo_unbind.cpp:395). */
+typedef struct hbtu_params
+{
+  int32_t struct_size;                 /* = sizeof(hbtu_params), ABI check                  */
+  int32_t real_bytes;                  /* sizeof(HBTReal) of the caller: 4 (8 unsupported)  */
+  int32_t min_num_part_of_sub;         /* MinNumPartOfSub                                   */
+  int32_t periodic_boundary_on;        /* PeriodicBoundaryOn                                */
+  int32_t refine_mostbound_particle;   /* RefineMostboundParticle                           */
+  int32_t device;                      /* CUDA device ordinal this context drives           */
+  int64_t max_sample_size;             /* MaxSampleSizeOfPotentialEstimate (0 = exact)      */
+  double bound_mass_precision;         /* BoundMassPrecision                                */
+  double source_sub_relax_factor;      /* SourceSubRelaxFactor                              */
+  double box_size;                     /* BoxSize                                           */
+  double box_half;                     /* BoxHalf                                           */
+  double softening_halo;               /* SofteningHalo                                     */
+  double tree_node_open_angle_square;  /* TreeNodeOpenAngleSquare                           */
+  double tree_node_resolution;         /* TreeNodeResolution                                */
+  double tree_node_resolution_half;    /* TreeNodeResolutionHalf                            */
+  double tree_alloc_factor;            /* TreeAllocFactor   (accepted; device tree self-sizes) */
+  int64_t tree_min_num_of_cells;       /* TreeMinNumOfCells (accepted; unused)              */
+  double G;                            /* PhysicalConst::G                                  */
+  int64_t direct_sum_max;              /* subhaloes with <= this many source particles use the
+                                          fused direct-sum kernel; <0 = library default, 0 = tree only */
+} hbtu_params;
+
+/* What Unbind reads from `epoch` (src/snapshot.h:17-39, src/snapshot_number.h). */
+typedef struct hbtu_epoch
+{
+  double scale_factor; /* Cosmology.ScaleFactor */
+  double hz;           /* Cosmology.Hz          */
+  int32_t snapshot_index;
+  int32_t reserved;
+} hbtu_epoch;
+
+/* Per-subhalo scalar state: the Subhalo_t fields Unbind reads and writes
+ * (src/subhalo.h:24-146).  [io] = read on entry, written on exit. */
+typedef struct hbtu_sub_io
+{
+  double avg_pos[3];       /* [io] ComovingAveragePosition (initial frame must be set)  */
+  double avg_vel[3];       /* [io] PhysicalAverageVelocity                              */
+  double mostbound_pos[3]; /* [io] ComovingMostBoundPosition                            */
+  double mostbound_vel[3]; /* [io] PhysicalMostBoundVelocity                            */
+  int64_t nbound;          /* [io] Nbound (entry value drives the orphan rule, :434)    */
+  int64_t sink_track_id;   /* [io] SinkTrackId                                          */
+  int32_t snapshot_index_of_death; /* [io] */
+  int32_t snapshot_index_of_sink;  /* [io] */
+  float mbound;                         /* [out] Mbound                                 */
+  float specific_self_potential_energy; /* [out] */
+  float specific_self_kinetic_energy;   /* [out] */
+  float specific_angular_momentum[3];   /* [out] */
+  int64_t nsource_full;    /* [out] Particles.size() after unbinding, before TruncateSource */
+  int64_t nsource;         /* [out] entries written to order_out for this subhalo        */
+  int32_t iterations;      /* [out] potential evaluations performed (diagnostic)         */
+  int32_t reserved;
+} hbtu_sub_io;
+
+/* flags for hbtu_unbind_batch */
+#define HBTU_FLAG_TRUNCATE_SOURCE 1 /* apply Subhalo_t::TruncateSource to every subhalo at the end
+                                       (what RefineParticles does, src/subhalo_unbind.cpp:511-513) */
+
+typedef struct hbtu_ctx hbtu_ctx;
+
+/* Create / destroy a context bound to one CUDA device.  One context per host
+ * thread / MPI rank / GPU; a context is not re-entrant. */
+int hbtu_create(const hbtu_params *params, hbtu_ctx **out);
+void hbtu_destroy(hbtu_ctx *ctx);
+const char *hbtu_last_error(const hbtu_ctx *ctx); /* ctx may be NULL: error of the failed create */
+int hbtu_abi_version(void);
+
+/* Upper bound of the number of entries hbtu_unbind_batch writes to order_out
+ * for this forest (every subhalo can receive all particles of its descendants). */
+int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset,
+                            const int32_t *nest_list);
+
+/* Unbind a batch of subhaloes (replaces RefineParticles / RecursiveUnbind / Unbind).
+ *
+ *  part_offset[nsub+1]  subhalo s owns input particles [part_offset[s], part_offset[s+1])
+ *  pos_mass[4*N]        x,y,z (comoving), mass      per input particle (HOST memory)
+ *  vel[4*N]             vx,vy,vz (physical), unused per input particle (HOST memory)
+ *  nest_offset/nest_list CSR of NestedSubhalos (batch-local subhalo indices), may be NULL (no nesting).
+ *                       Subhaloes that appear in nobody's list are roots.  Each root is processed
+ *                       like Subhalo_t::RecursiveUnbind: children first, each child's unbound tail
+ *                       Particles[Nbound..] is appended to its parent's source in list order.
+ *  io[nsub]             per-subhalo scalars, updated in place
+ *  order_offset[nsub+1] [out] subhalo s's final particle list is
+ *                       order_out[order_offset[s] .. order_offset[s]+io[s].nsource)
+ *  order_out            [out] indices into the batch's input particle arrays: the new
+ *                       Subhalo_t::Particles order (bound by E ascending, then removal batches)
+ *  energy_out           [out, optional] binding energy aligned with order_out (valid for the first
+ *                       io[s].nbound entries of each subhalo; SAVE_BINDING_ENERGY), else NULL
+ */
+int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                      const float *pos_mass, const float *vel, const int64_t *nest_offset,
+                      const int32_t *nest_list, hbtu_sub_io *io, int32_t flags, int64_t order_capacity,
+                      int64_t *order_offset, int32_t *order_out, float *energy_out);
+
+/* The same call split so that a caller can keep a snapshot resident in HBM:
+ *   hbtu_stage   : validate + host->device copies of the batch
+ *   hbtu_execute : all kernels (may be called repeatedly on the staged batch; inputs are not modified)
+ *   hbtu_fetch   : device->host copies of io / order / energies
+ * hbtu_unbind_batch == stage + execute + fetch. */
+int hbtu_stage(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+               const float *pos_mass, const float *vel, const int64_t *nest_offset,
+               const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags);
+int hbtu_execute(hbtu_ctx *ctx);
+int hbtu_fetch(hbtu_ctx *ctx, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset,
+               int32_t *order_out, float *energy_out);
+
+/* GravityTree_t::Build + EvaluatePotential / BindingEnergy for one particle set
+ * (src/gravity_tree.cpp:79-175): tree over the nsrc source particles, potential at ntgt targets.
+ *  src_pos_mass / tgt_pos / tgt_vel are float4-strided (x,y,z,mass|unused) HOST arrays
+ *  tgt_self_mass  NULL, or per-target mass whose self term m/eps is cancelled (a target that is
+ *                 itself a tree source), 0 for foreign targets
+ *  tgt_vel/ref_*  if tgt_vel != NULL the result is the binding energy 0.5|dv|^2 + pot w.r.t.
+ *                 the frame (ref_pos, ref_vel), else the potential
+ *  out[ntgt]      double results (the device sums in fp32 tiles + fp64 carries)              */
+int hbtu_tree_potential(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsrc, const float *src_pos_mass,
+                        int64_t ntgt, const float *tgt_pos, const float *tgt_self_mass,
+                        const float *tgt_vel, const double *ref_pos, const double *ref_vel, double *out);
+
+/* Counters of the last hbtu_execute / hbtu_tree_potential (for bench.py's roofline and
+ * gpu_launches fields). */
+typedef struct hbtu_stats
+{
+  int64_t kernel_launches;     /* kernels launched by this library (incl. CUB passes)  */
+  int64_t tree_builds;         /* subhalo trees built                                  */
+  int64_t walk_targets;        /* target particles walked / direct-summed              */
+  int64_t pair_interactions;   /* accepted target x source interactions evaluated      */
+  int64_t nodes_visited;       /* warp-level node visits of the tree walk              */
+  int64_t rounds;              /* batched unbinding rounds                             */
+  double walk_ms;              /* CUDA-event time of walk / direct-sum kernels         */
+  double build_ms;             /* CUDA-event time of tree build kernels                */
+  double other_ms;             /* partition / sort / reductions                        */
+  double h2d_ms, d2h_ms;       /* copies in hbtu_stage / hbtu_fetch                    */
+  int64_t h2d_bytes, d2h_bytes;
+} hbtu_stats;
+int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
+/* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted
+ * interactions and warp node visits into hbtu_stats (costs a few percent; off by default). */
+int hbtu_set_counting(hbtu_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBT_UNBIND_H */

@@ -1,0 +1,98 @@
+"""ctypes loaders for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; nothing under hbtplus_b200/ does (the product path has no CPU fallback).
+
+  load_ref()     oracle/_ref/libhbtref_v32.so  - the unmodified reference sources (hbtref_*)
+  load_oracle()  oracle/libhbtoracle.so        - the plain-C restatement (hbto_*)
+Both export ``*_unbind_batch`` / ``*_tree_potential`` with the argument list of the product's
+hbtu_* entry points (include/hbt_unbind.h), the context pointer replaced by ``const hbtu_params*``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from hbtplus_b200 import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_PATH = os.path.join(_HERE, "_ref", "libhbtref_v32.so")
+ORACLE_PATH = os.path.join(_HERE, "libhbtoracle.so")
+
+
+def _bind(lib, prefix):
+    ub = getattr(lib, prefix + "_unbind_batch")
+    ub.argtypes = [C.POINTER(capi.Params)] + capi.BATCH_ARGTYPES
+    ub.restype = C.c_int
+    tp = getattr(lib, prefix + "_tree_potential")
+    tp.argtypes = [C.POINTER(capi.Params)] + capi.POTENTIAL_ARGTYPES
+    tp.restype = C.c_int
+    getattr(lib, prefix + "_set_num_threads").argtypes = [C.c_int]
+    getattr(lib, prefix + "_get_max_threads").restype = C.c_int
+    return lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_PATH)
+
+
+def load_ref():
+    return _bind(C.CDLL(REF_PATH), "hbtref")
+
+
+def load_oracle():
+    lib = _bind(C.CDLL(ORACLE_PATH), "hbto")
+    lib.hbto_walk_counts.argtypes = [C.POINTER(capi.Params), C.POINTER(capi.Epoch), C.c_int64, C.POINTER(C.c_float),
+                                     C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.hbto_walk_counts.restype = C.c_int
+    lib.hbto_last_interactions.restype = C.c_int64
+    return lib
+
+
+class Result:
+    def __init__(self, io, order_offset, order, energy):
+        self.io, self.order_offset, self.order, self.energy = io, order_offset, order, energy
+
+    def particles(self, s):
+        b = self.order_offset[s]
+        return self.order[b : b + self.io["nsource"][s]]
+
+    def bound(self, s):
+        b = self.order_offset[s]
+        return self.order[b : b + self.io["nbound"][s]]
+
+
+def run_batch(lib, prefix, params, epoch, snap, flags=0, want_energy=True):
+    """Call ``<prefix>_unbind_batch`` on a hbtplus_b200.synth.Snapshot; returns a Result."""
+    cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
+    io = snap.io.copy()
+    order_offset = np.zeros(snap.nsub + 1, np.int64)
+    order = np.full(max(cap, 1), -1, np.int32)
+    energy = np.zeros(max(cap, 1), np.float32) if want_energy else None
+    pm = np.ascontiguousarray(snap.pos_mass, np.float32)
+    vv = np.ascontiguousarray(snap.vel, np.float32)
+    rc = getattr(lib, prefix + "_unbind_batch")(
+        C.byref(params), *capi.batch_args(epoch, snap.part_offset, pm, vv, snap.nest_offset, snap.nest_list, io, flags, cap, order_offset, order, energy)
+    )
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_unbind_batch failed: {rc}")
+    return Result(io, order_offset, order, energy)
+
+
+def tree_potential(lib, prefix, params, epoch, src_pos_mass, tgt_pos, self_mass=None, tgt_vel=None, ref_pos=None, ref_vel=None):
+    src = np.ascontiguousarray(src_pos_mass, np.float32)
+    tgt = np.ascontiguousarray(tgt_pos, np.float32)
+    out = np.zeros(len(tgt), np.float64)
+    sm = None if self_mass is None else np.ascontiguousarray(self_mass, np.float32)
+    tv = None if tgt_vel is None else np.ascontiguousarray(tgt_vel, np.float32)
+    rp = None if ref_pos is None else np.ascontiguousarray(ref_pos, np.float64)
+    rv = None if ref_vel is None else np.ascontiguousarray(ref_vel, np.float64)
+    P = capi._ptr
+    rc = getattr(lib, prefix + "_tree_potential")(
+        C.byref(params), C.byref(epoch), len(src), P(src, C.c_float), len(tgt), P(tgt, C.c_float), P(sm, C.c_float), P(tv, C.c_float),
+        P(rp, C.c_double), P(rv, C.c_double), P(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_tree_potential failed: {rc}")
+    return out

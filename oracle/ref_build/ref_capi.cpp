@@ -1,0 +1,283 @@
+/* ref_capi.cpp - C entry points around the UNMODIFIED reference sources.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This translation unit is compiled together with
+ * /root/reference/src/{subhalo_unbind,gravity_tree,...}.cpp (see ../Makefile)
+ * into oracle/_ref/libhbtref_<variant>.so.  It contains no algorithm: it fills
+ * the reference's own data structures (HBTConfig, Subhalo_t, Particle_t) from
+ * the POD arguments of include/hbt_unbind.h, calls the reference's own
+ *   Subhalo_t::RecursiveUnbind / Unbind / TruncateSource   (src/subhalo_unbind.cpp:263-458)
+ *   SubhaloSnapshot_t::RefineParticles                      (src/subhalo_unbind.cpp:460-516)
+ *   GravityTree_t::Build / EvaluatePotential / BindingEnergy (src/gravity_tree.cpp:79-175)
+ * and copies the results back.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load the resulting library.
+ */
+#include <omp.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "datatypes.h"
+#include "config_parser.h"
+#include "snapshot.h"
+#include "subhalo.h"
+#include "gravity_tree.h"
+
+#include "hbt_unbind.h"
+
+/* the real body lives in src/io/subhalo_io.cpp, which needs libhdf5 (absent) */
+void SubhaloSnapshot_t::BuildHDFDataType()
+{
+  H5T_SubhaloInMem = 0;
+  H5T_SubhaloInDisk = 0;
+}
+
+namespace
+{
+class Epoch_t : public Snapshot_t
+{ /* the minimum Unbind needs from `epoch`: Cosmology + snapshot index */
+  HBTxyz dummy;
+
+public:
+  Epoch_t() : dummy{{0, 0, 0}} {}
+  HBTInt size() const { return 0; }
+  const HBTxyz &GetComovingPosition(const HBTInt) const { return dummy; }
+  const HBTxyz &GetPhysicalVelocity(const HBTInt) const { return dummy; }
+  HBTReal GetMass(const HBTInt) const { return 0; }
+};
+
+class ParticleView_t : public Snapshot_t
+{ /* a Snapshot_t over a vector<Particle_t>, as src/halo.h / subhalo_unbind.cpp's views do */
+public:
+  const std::vector<Particle_t> &P;
+  ParticleView_t(const std::vector<Particle_t> &p, const Snapshot_t &epoch) : P(p) { Cosmology = epoch.Cosmology; }
+  HBTInt size() const { return P.size(); }
+  const HBTxyz &GetComovingPosition(const HBTInt i) const { return P[i].ComovingPosition; }
+  const HBTxyz &GetPhysicalVelocity(const HBTInt i) const { return P[i].PhysicalVelocity; }
+  HBTReal GetMass(const HBTInt i) const { return P[i].Mass; }
+};
+
+void apply_params(const hbtu_params *p)
+{
+  HBTConfig.MinNumPartOfSub = p->min_num_part_of_sub;
+  HBTConfig.PeriodicBoundaryOn = p->periodic_boundary_on != 0;
+  HBTConfig.RefineMostboundParticle = p->refine_mostbound_particle != 0;
+  HBTConfig.MaxSampleSizeOfPotentialEstimate = p->max_sample_size;
+  HBTConfig.BoundMassPrecision = p->bound_mass_precision;
+  HBTConfig.SourceSubRelaxFactor = p->source_sub_relax_factor;
+  HBTConfig.BoxSize = p->box_size;
+  HBTConfig.BoxHalf = p->box_half;
+  HBTConfig.SofteningHalo = p->softening_halo;
+  HBTConfig.TreeNodeOpenAngleSquare = p->tree_node_open_angle_square;
+  HBTConfig.TreeNodeResolution = p->tree_node_resolution;
+  HBTConfig.TreeNodeResolutionHalf = p->tree_node_resolution_half;
+  HBTConfig.TreeAllocFactor = p->tree_alloc_factor > 0 ? p->tree_alloc_factor : 0.8;
+  HBTConfig.TreeMinNumOfCells = p->tree_min_num_of_cells > 0 ? p->tree_min_num_of_cells : 10;
+  HBTConfig.MinSnapshotIndex = 0;
+  HBTConfig.MaxSnapshotIndex = 1 << 30;
+  PhysicalConst::G = p->G;
+  PhysicalConst::H0 = 100.;
+}
+
+void set_epoch(Snapshot_t &snap, const hbtu_epoch *e)
+{
+  snap.Cosmology.OmegaM0 = 0.3;
+  snap.Cosmology.OmegaLambda0 = 0.7;
+  snap.Cosmology.ScaleFactor = e->scale_factor;
+  snap.Cosmology.Hz = e->hz;
+  snap.Cosmology.OmegaZ = 0.3;
+  snap.SetSnapshotIndex(e->snapshot_index);
+}
+
+void fill_subhalo(Subhalo_t &sub, int64_t s, const int64_t *part_offset, const float *pos_mass, const float *vel,
+                  const hbtu_sub_io &io)
+{
+  int64_t b = part_offset[s], n = part_offset[s + 1] - b;
+  sub.Particles.resize(n);
+  for (int64_t i = 0; i < n; i++)
+  {
+    Particle_t &p = sub.Particles[i];
+    p.Id = (HBTInt)(b + i); /* the input index travels as the particle Id */
+    for (int j = 0; j < 3; j++)
+    {
+      p.ComovingPosition[j] = pos_mass[4 * (b + i) + j];
+      p.PhysicalVelocity[j] = vel[4 * (b + i) + j];
+    }
+    p.Mass = pos_mass[4 * (b + i) + 3];
+#ifndef DM_ONLY
+    p.Type = TypeDM;
+#endif
+  }
+  for (int j = 0; j < 3; j++)
+  {
+    sub.ComovingAveragePosition[j] = io.avg_pos[j];
+    sub.PhysicalAverageVelocity[j] = io.avg_vel[j];
+    sub.ComovingMostBoundPosition[j] = io.mostbound_pos[j];
+    sub.PhysicalMostBoundVelocity[j] = io.mostbound_vel[j];
+  }
+  sub.Nbound = (HBTInt)io.nbound;
+  sub.SinkTrackId = (HBTInt)io.sink_track_id;
+  sub.SnapshotIndexOfDeath = io.snapshot_index_of_death;
+  sub.SnapshotIndexOfSink = io.snapshot_index_of_sink;
+  sub.TrackId = (HBTInt)s;
+}
+
+void read_subhalo(const Subhalo_t &sub, hbtu_sub_io &io)
+{
+  for (int j = 0; j < 3; j++)
+  {
+    io.avg_pos[j] = sub.ComovingAveragePosition[j];
+    io.avg_vel[j] = sub.PhysicalAverageVelocity[j];
+    io.mostbound_pos[j] = sub.ComovingMostBoundPosition[j];
+    io.mostbound_vel[j] = sub.PhysicalMostBoundVelocity[j];
+    io.specific_angular_momentum[j] = sub.SpecificAngularMomentum[j];
+  }
+  io.nbound = sub.Nbound;
+  io.sink_track_id = sub.SinkTrackId;
+  io.snapshot_index_of_death = sub.SnapshotIndexOfDeath;
+  io.snapshot_index_of_sink = sub.SnapshotIndexOfSink;
+  io.mbound = sub.Mbound;
+  io.specific_self_potential_energy = sub.SpecificSelfPotentialEnergy;
+  io.specific_self_kinetic_energy = sub.SpecificSelfKineticEnergy;
+}
+
+int write_orders(const std::vector<Subhalo_t> &subs, const std::vector<int64_t> &full, hbtu_sub_io *io,
+                 int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  int64_t pos = 0, nsub = subs.size();
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    const Subhalo_t &sub = subs[s];
+    int64_t n = sub.Particles.size();
+    if (pos + n > order_capacity) return HBTU_ERR_CAPACITY;
+    order_offset[s] = pos;
+    for (int64_t i = 0; i < n; i++) order_out[pos + i] = (int32_t)sub.Particles[i].Id;
+    if (energy_out)
+    {
+      for (int64_t i = 0; i < n; i++) energy_out[pos + i] = 0.f;
+#ifdef SAVE_BINDING_ENERGY
+      int64_t ne = sub.Energies.size();
+      for (int64_t i = 0; i < n && i < ne; i++) energy_out[pos + i] = sub.Energies[i];
+#endif
+    }
+    io[s].nsource = n;
+    io[s].nsource_full = full[s];
+    io[s].iterations = 0;
+    pos += n;
+  }
+  order_offset[nsub] = pos;
+  return HBTU_OK;
+}
+} // namespace
+
+extern "C" {
+
+int hbtref_sizeof_particle(void) { return (int)sizeof(Particle_t); }
+int hbtref_sizeof_subhalo(void) { return (int)sizeof(Subhalo_t); }
+int hbtref_sizeof_hbtint(void) { return (int)sizeof(HBTInt); }
+int hbtref_sizeof_hbtreal(void) { return (int)sizeof(HBTReal); }
+
+void hbtref_set_num_threads(int n)
+{
+  omp_set_num_threads(n);
+  omp_set_max_active_levels(1); /* HBT.cpp:22 */
+}
+int hbtref_get_max_threads(void) { return omp_get_max_threads(); }
+void hbtref_seed(unsigned s)
+{
+  srand(s);
+  srand48(s);
+}
+
+/* Same contract as hbtu_unbind_batch (include/hbt_unbind.h); roots are driven with the
+ * reference's RecursiveUnbind, then TruncateSource when asked - the schedule of
+ * RefineParticles (src/subhalo_unbind.cpp:479-513) with one OpenMP loop over roots. */
+int hbtref_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                        const float *pos_mass, const float *vel, const int64_t *nest_offset, const int32_t *nest_list,
+                        hbtu_sub_io *io, int32_t flags, int64_t order_capacity, int64_t *order_offset,
+                        int32_t *order_out, float *energy_out)
+{
+  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  apply_params(params);
+  Epoch_t snap;
+  set_epoch(snap, epoch);
+  omp_set_max_active_levels(1);
+
+  std::vector<Subhalo_t> subs(nsub);
+  std::vector<char> is_child(nsub, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t s = 0; s < nsub; s++) fill_subhalo(subs[s], s, part_offset, pos_mass, vel, io[s]);
+  if (nest_offset)
+    for (int64_t s = 0; s < nsub; s++)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++)
+      {
+        int32_t c = nest_list[k];
+        if (c < 0 || c >= nsub || is_child[c] || c == s) return HBTU_ERR_INVALID;
+        is_child[c] = 1;
+        subs[s].NestedSubhalos.push_back(c);
+      }
+  /* largest roots first so that dynamic scheduling balances, as the reference's
+   * mass-sorted member lists effectively do */
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t s = 0; s < nsub; s++)
+    if (!is_child[s]) subs[s].RecursiveUnbind(subs, snap);
+
+  std::vector<int64_t> full(nsub);
+  for (int64_t s = 0; s < nsub; s++) full[s] = subs[s].Particles.size();
+  if (flags & HBTU_FLAG_TRUNCATE_SOURCE)
+  {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t s = 0; s < nsub; s++) subs[s].TruncateSource();
+  }
+  for (int64_t s = 0; s < nsub; s++) read_subhalo(subs[s], io[s]);
+  return write_orders(subs, full, io, order_capacity, order_offset, order_out, energy_out);
+}
+
+/* GravityTree_t::Build + EvaluatePotential/BindingEnergy; same contract as hbtu_tree_potential. */
+int hbtref_tree_potential(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsrc, const float *src_pos_mass,
+                          int64_t ntgt, const float *tgt_pos, const float *tgt_self_mass, const float *tgt_vel,
+                          const double *ref_pos, const double *ref_vel, double *out)
+{
+  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  apply_params(params);
+  Epoch_t snap;
+  set_epoch(snap, epoch);
+  std::vector<Particle_t> P(nsrc);
+  for (int64_t i = 0; i < nsrc; i++)
+  {
+    P[i].Id = i;
+    for (int j = 0; j < 3; j++)
+    {
+      P[i].ComovingPosition[j] = src_pos_mass[4 * i + j];
+      P[i].PhysicalVelocity[j] = 0;
+    }
+    P[i].Mass = src_pos_mass[4 * i + 3];
+  }
+  ParticleView_t view(P, snap);
+  GravityTree_t tree;
+  tree.Reserve(nsrc);
+  tree.Build(view);
+  HBTxyz rp, rv;
+  if (tgt_vel)
+    for (int j = 0; j < 3; j++)
+    {
+      rp[j] = ref_pos[j];
+      rv[j] = ref_vel[j];
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < ntgt; i++)
+  {
+    HBTxyz x{{(HBTReal)tgt_pos[4 * i], (HBTReal)tgt_pos[4 * i + 1], (HBTReal)tgt_pos[4 * i + 2]}};
+    HBTReal m = tgt_self_mass ? tgt_self_mass[i] : 0;
+    if (tgt_vel)
+    {
+      HBTxyz v{{(HBTReal)tgt_vel[4 * i], (HBTReal)tgt_vel[4 * i + 1], (HBTReal)tgt_vel[4 * i + 2]}};
+      out[i] = tree.BindingEnergy(x, v, rp, rv, m);
+    }
+    else
+      out[i] = tree.EvaluatePotential(x, m);
+  }
+  return HBTU_OK;
+}
+
+} // extern "C"
