@@ -219,7 +219,8 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
   Arena &ar = c.arena;
   ar.reset();
   ar.reserve(tree_arena_bytes(S, 1) + (int64_t)T * 96 + (1 << 20));
-  std::vector<int> tree_off{0, S}, warp_off{0, (T + 31) / 32};
+  const int tpl = walk_targets_per_lane(T);
+  std::vector<int> tree_off{0, S}, warp_off{0, (T + 32 * tpl - 1) / (32 * tpl)};
   Segment sg{};
   sg.mode = tgt_vel ? kWalkBindingEnergy : kWalkPotential;
   sg.tree_n = S;
@@ -277,7 +278,8 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
     wa.segs = d_segs;
     wa.warp_off = d_warp_off;
     wa.nseg = 1;
-    wa.nwarps = (T + 31) / 32;
+    wa.nwarps = warp_off[1];
+    wa.targets_per_lane = tpl;
     wa.tgt_pm = tgt_pm;
     wa.vel = tgt_v;
     wa.out = d_sorted;

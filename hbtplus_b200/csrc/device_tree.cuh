@@ -125,6 +125,7 @@ struct WalkArgs
   const Segment *segs;   // [nseg]
   const int *warp_off;   // [nseg+1]
   int nseg, nwarps;
+  int targets_per_lane;  // 1, 2 or 4: warps own 32*T consecutive targets; warp_off is per class
   const float4 *tgt_pm;  // [T] x,y,z,self mass
   const int64_t *tgt_slot; // [T] slot in ids/E (unbind modes)
   const int *ids;        // Elist pid per slot
@@ -136,5 +137,7 @@ struct WalkArgs
   unsigned long long *counters; // [2]: accepted interactions, warp node visits (nullptr = do not count)
 };
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
+// targets per lane the walk uses for a segment with tgt_n targets (env HBTU_WALK_TPL / HBTU_WALK_BIG override)
+int walk_targets_per_lane(int tgt_n);
 
 } // namespace hbt

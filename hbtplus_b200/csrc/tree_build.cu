@@ -362,8 +362,8 @@ void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t
     ls.launches += 2;
   }
   // nodes ---------------------------------------------------------------------------------------------
-  t.node_xm = arena.alloc<float4>(2 * (int64_t)S);
-  t.node_aux = arena.alloc<float2>(2 * (int64_t)S);
+  t.node_xm = arena.alloc<float4>(2 * (int64_t)S + 64); // +pad: the walk stages 32 nodes without a bounds check
+  t.node_aux = arena.alloc<float2>(2 * (int64_t)S + 64);
   emit_particles_kernel<<<grid_for(S), kBlock, 0, stream>>>(t.spos, t.cellcount, S, t.node_xm, t.node_aux);
   HBT_CHECK_LAUNCH();
   emit_cells_kernel<<<grid_for(S), kBlock, 0, stream>>>(t.cell_lr, t.cell_depth, t.depthmask, t.cellcount, t.msum, t.ts_seg, t.tree_off,

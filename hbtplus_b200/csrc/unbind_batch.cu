@@ -543,8 +543,10 @@ static void run_round(Context &c, std::vector<int> &active)
 {
   const int nseg = (int)active.size();
   std::vector<Segment> segs(nseg);
-  std::vector<int> tree_off(nseg + 1), tgt_off(nseg + 1), warp_off(nseg + 1);
-  int64_t S = 0, T = 0, W = 0;
+  std::vector<int> tree_off(nseg + 1), tgt_off(nseg + 1);
+  // walk warps per class of targets-per-lane (index 0: T=1, 1: T=2, 2: T=4); a segment belongs to one class
+  std::vector<int> warp_off[3] = {std::vector<int>(nseg + 1), std::vector<int>(nseg + 1), std::vector<int>(nseg + 1)};
+  int64_t S = 0, T = 0, W[3] = {0, 0, 0};
   for (int a = 0; a < nseg; a++)
   {
     SubHost &h = c.subs[active[a]];
@@ -565,25 +567,27 @@ static void run_round(Context &c, std::vector<int> &active)
     sg.tgt_n = h.nbound;
     sg.tree_off = (int)S;
     sg.tgt_off = (int)T;
-    sg.warp_off = (int)W;
+    const int tpl = walk_targets_per_lane(sg.tgt_n), cls = tpl == 4 ? 2 : (tpl == 2 ? 1 : 0);
+    sg.warp_off = (int)W[cls];
     tree_off[a] = (int)S;
     tgt_off[a] = (int)T;
-    warp_off[a] = (int)W;
+    for (int q = 0; q < 3; q++) warp_off[q][a] = (int)W[q];
     S += sg.tree_n;
     T += sg.tgt_n;
-    W += (sg.tgt_n + 31) / 32;
+    W[cls] += (sg.tgt_n + 32 * tpl - 1) / (32 * tpl);
     if (S > 0x3fffffff || T > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "round larger than 2^30 particles"};
   }
   tree_off[nseg] = (int)S;
   tgt_off[nseg] = (int)T;
-  warp_off[nseg] = (int)W;
+  for (int q = 0; q < 3; q++) warp_off[q][nseg] = (int)W[q];
 
   Arena &ar = c.arena;
   ar.reset();
   ar.reserve(tree_arena_bytes(S, nseg) + T * 64 + (int64_t)nseg * 128);
   cudaStream_t st = c.stream;
   Segment *d_segs = upload(ar, segs, st);
-  int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st), *d_warp_off = upload(ar, warp_off, st);
+  int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st);
+  int *d_warp_off[3] = {upload(ar, warp_off[0], st), upload(ar, warp_off[1], st), upload(ar, warp_off[2], st)};
 
   HBT_CUDA(cudaEventRecord(c.ev[0], st));
   TreeArrays tr;
@@ -620,9 +624,7 @@ static void run_round(Context &c, std::vector<int> &active)
   wa.cellcount = tr.cellcount;
   wa.tree_off = d_tree_off;
   wa.segs = d_segs;
-  wa.warp_off = d_warp_off;
   wa.nseg = nseg;
-  wa.nwarps = (int)W;
   wa.tgt_pm = tgt_pm;
   wa.tgt_slot = tgt_slot;
   wa.ids = c.d_ids;
@@ -631,7 +633,13 @@ static void run_round(Context &c, std::vector<int> &active)
   wa.subs = c.d_subs;
   wa.out = nullptr;
   wa.counters = c.count_interactions ? c.d_counters : nullptr;
-  launch_walk(wa, c.cfg, st, c.ls);
+  for (int q = 0; q < 3; q++)
+  {
+    wa.warp_off = d_warp_off[q];
+    wa.nwarps = (int)W[q];
+    wa.targets_per_lane = 1 << q;
+    launch_walk(wa, c.cfg, st, c.ls);
+  }
   HBT_CUDA(cudaEventRecord(c.ev[2], st));
 
   count_bound_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);

@@ -20,6 +20,8 @@
 //     src/gravity_tree.cpp:146-160) is taken only when some lane needs it (warp vote).
 //
 // Roofline: FP32 issue.  Tensor cores are deliberately not used.
+#include <cstdlib>
+
 #include "device_tree.cuh"
 
 namespace hbt
@@ -45,15 +47,99 @@ __device__ __forceinline__ float dot3_rn(const float a[3], const float b[3])
   return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
 }
 
-template <bool PERIODIC, bool COUNT>
+struct __align__(16) TileNode
+{ // one staged node: 32 B so that a warp's tile is 1 KB and both loads are broadcasts
+  float4 xm;  // x, y, z, mass
+  float lenq; // len^2/theta^2 (0 for particles)
+  int end;    // index of the first node after this node's subtree
+  int pad0, pad1;
+};
+
+__device__ __forceinline__ float rsqrt_raw(float x)
+{ // single MUFU.RSQ; r2 == 0 (self / co-located pair) gives +inf and is replaced by the spline branch
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One pass over the staged tile [tile_base, tile_lim) starting at node `no`, for the T targets of every lane.
+//   CAREFUL=false: every accepted source is added as -m/r and the smallest accepted r^2 is tracked; the caller
+//                  redoes the tile with CAREFUL=true if any lane met r < 2.8 eps (spline-softened pair, or r = 0).
+//   CAREFUL=true : the reference's full kernel (src/gravity_tree.cpp:141-161), branch taken on a warp vote.
+// Returns the node index at which the warp left the tile.
+template <int T, bool PERIODIC, bool COUNT, bool CAREFUL>
+__device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int tile_base, int tile_lim, int no, const float (&px)[T],
+                                         const float (&py)[T], const float (&pz)[T], int (&skip)[T], float (&accf)[T], float &minr2,
+                                         const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis)
+{
+  do
+  {
+    const TileNode *nd = &tile[no - tile_base];
+    const float4 n = nd->xm;
+    const float lenq = nd->lenq;
+    const int nend = nd->end;
+    bool any_open = false;
+#pragma unroll
+    for (int k = 0; k < T; k++)
+    {
+      float dx = n.x - px[k], dy = n.y - py[k], dz = n.z - pz[k];
+      if (PERIODIC)
+      {
+        dx = nearest_f(dx, cfg.box_size, cfg.box_half);
+        dy = nearest_f(dy, cfg.box_size, cfg.box_half);
+        dz = nearest_f(dz, cfg.box_size, cfg.box_half);
+      }
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      const bool active = no >= skip[k];
+      const bool open = active && (lenq > r2); // reference criterion, per target (src/gravity_tree.cpp:135)
+      const bool acc = active && !(lenq > r2);
+      const float rinv = rsqrt_raw(r2);
+      any_open |= open;
+      if (CAREFUL)
+      {
+        float contrib = -n.w * rinv;
+        if (__any_sync(kFull, acc && (r2 < h2)))
+        {
+          if (r2 < h2)
+          { // Gadget spline kernel, src/gravity_tree.cpp:146-160
+            float u = sqrtf(r2) * hinv, wp;
+            if (u < 0.5f)
+              wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
+            else
+              wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
+            contrib = n.w * hinv * wp;
+          }
+        }
+        if (acc) accf[k] += contrib;
+      }
+      else if (acc)
+      {
+        accf[k] = fmaf(-n.w, rinv, accf[k]);
+        minr2 = fminf(minr2, r2);
+      }
+      if (acc)
+      {
+        skip[k] = nend; // resume after this subtree (a particle's end is no+1)
+        if (COUNT) n_acc++;
+      }
+    }
+    if (COUNT) n_vis++;
+    no = __any_sync(kFull, any_open) ? no + 1 : nend;
+  } while (no < tile_lim);
+  return no;
+}
+
+// T targets per lane: a warp owns 32*T consecutive targets (lane l holds targets l, l+32, ...).  T=1 for small
+// subhaloes; T=4 for large ones, where it quarters the dependent tile loads and the control instructions per
+// interaction at the price of a ~1.3x larger node union.
+template <int T, bool PERIODIC, bool COUNT>
 __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a, const DevConfig cfg)
 {
-  __shared__ float4 s_xm[kWalkWarps][32];
-  __shared__ float2 s_aux[kWalkWarps][32];
+  __shared__ TileNode s_tile[kWalkWarps][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kWalkWarps + w;
   if (warp >= a.nwarps) return;
-  // segment of this warp: largest s with warp_off[s] <= warp
+  // segment of this warp: largest s with warp_off[s] <= warp (segments of the other class have no warps)
   int lo = 0, hi = a.nseg;
   while (hi - lo > 1)
   {
@@ -61,149 +147,161 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
     if (a.warp_off[mid] <= warp) lo = mid; else hi = mid;
   }
   const Segment sg = a.segs[lo];
-  const int j = (warp - a.warp_off[lo]) * 32 + lane;
-  const bool valid = j < sg.tgt_n;
-  const int t = sg.tgt_off + (valid ? j : 0);
-  const float4 tp = a.tgt_pm[t];
+  const int j0 = (warp - a.warp_off[lo]) * (32 * T) + lane;
+  float px[T], py[T], pz[T], pm[T];
+  int skip[T];
+  bool valid[T];
+#pragma unroll
+  for (int k = 0; k < T; k++)
+  {
+    const int j = j0 + 32 * k;
+    valid[k] = j < sg.tgt_n;
+    const float4 tp = a.tgt_pm[sg.tgt_off + (valid[k] ? j : 0)];
+    px[k] = tp.x; py[k] = tp.y; pz[k] = tp.z; pm[k] = tp.w;
+    skip[k] = valid[k] ? 0 : 0x7fffffff; // resume index of this target
+  }
   const int t0 = a.tree_off[lo], t1 = a.tree_off[lo + 1];
   const int node_begin = t0 + (t0 > 0 ? a.cellcount[t0 - 1] : 0);
   const int node_end = t1 + a.cellcount[t1 - 1];
 
   const float h = 2.8f * cfg.softening, h2 = h * h, hinv = 1.0f / h;
-  int skip = valid ? 0 : 0x7fffffff; // resume index of this lane
-  int no = node_begin, tile_base = -0x40000000;
-  float accf = 0.f;
-  double accd = 0.0;
-  unsigned it = 0;
-  unsigned long long n_acc = 0, n_vis = 0;
+  int no = node_begin;
+  double accd[T];
+#pragma unroll
+  for (int k = 0; k < T; k++) accd[k] = 0.0;
+  unsigned n_acc = 0, n_vis = 0;
+  TileNode *const tile = s_tile[w];
 
   while (no < node_end)
   {
-    int jj = no - tile_base;
-    if ((unsigned)jj >= 32u)
+    // stage nodes [no, no+32): one coalesced 16 B + 8 B load per lane (arrays are padded by 32 nodes)
+    const int tile_base = no;
+    const int tile_lim = min(no + 32, node_end);
     {
-      tile_base = no;
-      jj = 0;
-      int idx = no + lane;
-      float4 xm = make_float4(0.f, 0.f, 0.f, 0.f);
-      float2 ax = make_float2(0.f, 0.f);
-      if (idx < node_end)
-      {
-        xm = __ldg(&a.node_xm[idx]);
-        ax = __ldg(&a.node_aux[idx]);
-      }
+      const float4 xm = __ldg(&a.node_xm[no + lane]);
+      const float2 ax = __ldg(&a.node_aux[no + lane]);
       __syncwarp();
-      s_xm[w][lane] = xm;
-      s_aux[w][lane] = ax;
+      tile[lane].xm = xm;
+      *reinterpret_cast<float2 *>(&tile[lane].lenq) = ax;
       __syncwarp();
     }
-    const float4 n = s_xm[w][jj];
-    const float2 ax = s_aux[w][jj];
-    float dx = n.x - tp.x, dy = n.y - tp.y, dz = n.z - tp.z;
-    if (PERIODIC)
-    {
-      dx = nearest_f(dx, cfg.box_size, cfg.box_half);
-      dy = nearest_f(dy, cfg.box_size, cfg.box_half);
-      dz = nearest_f(dz, cfg.box_size, cfg.box_half);
+    int skip0[T];
+    float accf[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) { skip0[k] = skip[k]; accf[k] = 0.f; }
+    float minr2 = INFINITY;
+    const unsigned c0 = n_acc, c1 = n_vis;
+    int nx = walk_tile<T, PERIODIC, COUNT, false>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, cfg, h2, hinv, n_acc, n_vis);
+    if (__any_sync(kFull, minr2 < h2))
+    { // some lane met a softened pair in this tile: redo the tile exactly
+#pragma unroll
+      for (int k = 0; k < T; k++) { skip[k] = skip0[k]; accf[k] = 0.f; }
+      n_acc = c0;
+      n_vis = c1;
+      nx = walk_tile<T, PERIODIC, COUNT, true>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, cfg, h2, hinv, n_acc, n_vis);
     }
-    const float r2 = dx * dx + dy * dy + dz * dz;
-    const bool active = no >= skip;
-    const bool open = active && (ax.x > r2);
-    const bool acc = active && !open;
-    const int nend = __float_as_int(ax.y);
-    float contrib = -n.w * rsqrtf(r2);
-    if (__any_sync(kFull, acc && (r2 < h2)))
-    {
-      if (r2 < h2)
-      { // Gadget spline kernel, src/gravity_tree.cpp:146-160
-        float u = sqrtf(r2) * hinv, wp;
-        if (u < 0.5f)
-          wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
-        else
-          wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
-        contrib = n.w * hinv * wp;
-      }
-    }
-    if (acc)
-    {
-      accf += contrib;
-      skip = nend;
-      if (COUNT) n_acc++;
-    }
-    if (COUNT) n_vis++;
-    no = __any_sync(kFull, open) ? no + 1 : nend;
-    if (((++it) & 63u) == 0u)
-    {
-      accd += (double)accf;
-      accf = 0.f;
-    }
+    no = nx;
+#pragma unroll
+    for (int k = 0; k < T; k++) accd[k] += (double)accf[k]; // <= 32 fp32 terms per flush
   }
   if (COUNT)
   {
-    for (int o = 16; o > 0; o >>= 1) n_acc += __shfl_xor_sync(kFull, n_acc, o);
+    unsigned long long na = n_acc;
+    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(kFull, na, o);
     if (lane == 0)
     {
-      atomicAdd(&a.counters[0], n_acc);
-      atomicAdd(&a.counters[1], n_vis);
+      atomicAdd(&a.counters[0], na);
+      atomicAdd(&a.counters[1], (unsigned long long)n_vis);
     }
   }
-  if (!valid) return;
-  // pot = targetMass/eps + sum ; return pot*G/a   (src/gravity_tree.cpp:98,163)
-  double pot = accd + (double)accf + (double)__fdiv_rn(tp.w, cfg.softening);
-  pot = pot * (double)cfg.G / (double)cfg.scale_factor;
-
   const int MODE = sg.mode; // warp-uniform: one segment per warp
-  if (MODE == kWalkPotential)
+#pragma unroll
+  for (int k = 0; k < T; k++)
   {
-    a.out[t] = pot;
-    return;
-  }
-  const float x[3] = {tp.x, tp.y, tp.z};
-  if (MODE == kWalkBindingEnergy)
-  {
-    float4 v4 = a.vel[t];
+    if (!valid[k]) continue;
+    const int t = sg.tgt_off + j0 + 32 * k;
+    // pot = targetMass/eps + sum ; return pot*G/a   (src/gravity_tree.cpp:98,163)
+    double pot = accd[k] + (double)__fdiv_rn(pm[k], cfg.softening);
+    pot = pot * (double)cfg.G / (double)cfg.scale_factor;
+    if (MODE == kWalkPotential)
+    {
+      a.out[t] = pot;
+      continue;
+    }
+    const float x[3] = {px[k], py[k], pz[k]};
+    if (MODE == kWalkBindingEnergy)
+    {
+      float4 v4 = a.vel[t];
+      const float v[3] = {v4.x, v4.y, v4.z};
+      float dv[3];
+      relative_velocity(x, v, a.ref_pos, a.ref_vel, cfg, dv);
+      a.out[t] = (double)dot3_rn(dv, dv) * 0.5 + pot;
+      continue;
+    }
+    const int64_t slot = a.tgt_slot[t];
+    const SubState &st = a.subs[sg.sub];
+    float4 v4 = a.vel[a.ids[slot]];
     const float v[3] = {v4.x, v4.y, v4.z};
-    float dv[3];
-    relative_velocity(x, v, a.ref_pos, a.ref_vel, cfg, dv);
-    a.out[t] = (double)dot3_rn(dv, dv) * 0.5 + pot;
-    return;
+    if (MODE == kWalkUnbindFull)
+    { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
+      float dv[3];
+      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
+      a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+    }
+    else
+    { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
+      float ov[3];
+      relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
+      float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
+      a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
+    }
   }
-  const int64_t slot = a.tgt_slot[t];
-  const SubState &st = a.subs[sg.sub];
-  float4 v4 = a.vel[a.ids[slot]];
-  const float v[3] = {v4.x, v4.y, v4.z};
-  if (MODE == kWalkUnbindFull)
-  { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
-    float dv[3];
-    relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-    a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+}
+
+template <int T>
+static void launch_t(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream)
+{
+  const int grid = div_up(a.nwarps, kWalkWarps);
+  const bool count = a.counters != nullptr;
+  if (cfg.periodic)
+  {
+    if (count) walk_kernel<T, true, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+    else walk_kernel<T, true, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
   }
   else
-  { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
-    float ov[3];
-    relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
-    float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
-    a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
+  {
+    if (count) walk_kernel<T, false, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+    else walk_kernel<T, false, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
   }
 }
 
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls)
 {
   if (a.nwarps <= 0) return;
-  const int grid = div_up(a.nwarps, kWalkWarps);
-  const bool count = a.counters != nullptr;
-  if (cfg.periodic)
-  {
-    if (count) walk_kernel<true, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
-    else walk_kernel<true, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
-  }
-  else
-  {
-    if (count) walk_kernel<false, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
-    else walk_kernel<false, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
-  }
+  if (a.targets_per_lane == 4) launch_t<4>(a, cfg, stream);
+  else if (a.targets_per_lane == 2) launch_t<2>(a, cfg, stream);
+  else launch_t<1>(a, cfg, stream);
   HBT_CHECK_LAUNCH();
   ls.launches++;
 }
 
+} // namespace hbt
+
+namespace hbt
+{
+int walk_targets_per_lane(int tgt_n)
+{ // measured on B200 (profiles/r01_walk_notes.md): T=4 wins once a segment alone fills the GPU (~1e6 targets),
+  // T=1 wins below ~5e5 where the warp count, not the instruction count, limits throughput
+  static int forced = -1, big4 = 0, big2 = 0;
+  if (forced < 0)
+  {
+    const char *e = getenv("HBTU_WALK_TPL");
+    forced = e ? atoi(e) : 0;
+    const char *b4 = getenv("HBTU_WALK_BIG4"), *b2 = getenv("HBTU_WALK_BIG2");
+    big4 = b4 ? atoi(b4) : (1 << 20);
+    big2 = b2 ? atoi(b2) : (1 << 19);
+  }
+  if (forced == 1 || forced == 2 || forced == 4) return tgt_n >= 32 * forced ? forced : 1;
+  return tgt_n >= big4 ? 4 : (tgt_n >= big2 ? 2 : 1);
+}
 } // namespace hbt
