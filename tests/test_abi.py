@@ -1,0 +1,107 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol include/hbt_unbind.h declares,
+the ctypes mirror matches the C structs, and there is NO fallback when no device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from hbtplus_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hbt_unbind.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hbtu_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/hbt_unbind.h but not exported"
+    assert set(capi.EXPORTS) <= set(syms)
+    assert lib.hbtu_abi_version() == 1
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    prog = tmp_path / "sz.c"
+    prog.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "hbt_unbind.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hbtu_params), sizeof(hbtu_epoch), sizeof(hbtu_sub_io),'
+        " sizeof(hbtu_stats), offsetof(hbtu_sub_io, mbound), offsetof(hbtu_sub_io, nsource_full), offsetof(hbtu_params, G));return 0;}\n"
+    )
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(capi.Params), C.sizeof(capi.Epoch), C.sizeof(capi.SubIO), C.sizeof(capi.Stats),
+            capi.SubIO.mbound.offset, capi.SubIO.nsource_full.offset, capi.Params.G.offset]
+    assert got == want
+    assert capi.SUBIO_DTYPE.itemsize == C.sizeof(capi.SubIO)
+    for name in capi.SUBIO_DTYPE.names:
+        assert capi.SUBIO_DTYPE.fields[name][1] == getattr(capi.SubIO, name).offset, name
+
+
+def test_order_capacity_matches_host_mirror():
+    lib = capi.load_library()
+    part_offset = np.array([0, 10, 15, 40, 41, 60], np.int64)
+    nest_offset = np.array([0, 2, 3, 3, 3, 3], np.int64)
+    nest_list = np.array([1, 2, 3], np.int32)  # 0 -> {1,2}, 1 -> {3}
+    P = capi._ptr
+    got = lib.hbtu_order_capacity(5, P(part_offset, C.c_int64), P(nest_offset, C.c_int64), P(nest_list, C.c_int32))
+    assert got == capi.order_capacity(part_offset, nest_offset, nest_list) == (10 + 5 + 25 + 1) + (5 + 1) + 25 + 1 + 19
+    bad = np.array([1, 1, 3], np.int32)  # 1 nested twice
+    assert lib.hbtu_order_capacity(5, P(part_offset, C.c_int64), P(nest_offset, C.c_int64), P(bad, C.c_int32)) == capi.HBTU_ERR_INVALID
+    cyc_off = np.array([0, 1, 2, 2, 2, 2], np.int64)
+    cyc = np.array([1, 0], np.int32)
+    assert lib.hbtu_order_capacity(5, P(part_offset, C.c_int64), P(cyc_off, C.c_int64), P(cyc, C.c_int32)) == capi.HBTU_ERR_INVALID
+
+
+def test_create_rejects_bad_abi_and_has_no_cpu_fallback():
+    lib = capi.load_library()
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    ctx = C.c_void_p()
+    p.struct_size = 8
+    assert lib.hbtu_create(C.byref(p), C.byref(ctx)) == capi.HBTU_ERR_INVALID
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    p.real_bytes = 8
+    assert lib.hbtu_create(C.byref(p), C.byref(ctx)) == capi.HBTU_ERR_UNSUPPORTED
+    if not torch.cuda.is_available():
+        p = capi.make_params(box_size=62.5, softening=5e-3)
+        rc = lib.hbtu_create(C.byref(p), C.byref(ctx))
+        assert rc == capi.HBTU_ERR_NODEVICE and not ctx.value
+        assert b"no CPU fallback" in lib.hbtu_last_error(None)
+        from hbtplus_b200.unbind import UnbindContext, UnbindError
+
+        with pytest.raises(UnbindError):
+            UnbindContext(p)
+
+
+def test_product_package_never_touches_the_oracle():
+    """hbtplus_b200/ must not import, load or link anything under oracle/."""
+    pkg = os.path.join(ROOT, "hbtplus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "libhbtoracle" not in txt and "libhbtref" not in txt and "hbto_" not in txt, (dirpath, f)
+    out = subprocess.check_output(["ldd", capi.LIB_PATH]).decode()
+    assert "hbtoracle" not in out and "hbtref" not in out
+
+
+def test_params_follow_the_reference_derivations():
+    p = capi.make_params(box_size=62.5, softening=5e-3, open_angle=0.45)
+    f = np.float32
+    assert p.box_half == float(f(62.5) / f(2))
+    assert p.tree_node_open_angle_square == float(f(0.45) * f(0.45))
+    assert p.tree_node_resolution == float(f(float(f(5e-3)) * 0.1))
+    assert p.G == float(f(43.0071))
+    e = capi.make_epoch(1.0)
+    assert e.hz == 100.0 and e.scale_factor == 1.0

@@ -1,0 +1,153 @@
+"""CPU tests of the oracle itself: the plain-C restatement against the golden fixtures (generated from the
+unmodified reference), against the reference library where it is present, and against analytic answers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import load_golden, orders_equal_modulo_ties
+from hbtplus_b200 import capi, synth
+from oracle import pyoracle as po
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+@pytest.mark.parametrize("tag,flags", [("full", 0), ("trunc", capi.HBTU_FLAG_TRUNCATE_SOURCE)])
+def test_oracle_matches_golden(oracle_lib, name, tag, flags):
+    p, e, _ = cases.CASES[name]()
+    snap, z = load_golden(name)
+    r = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=flags)
+    g = z[f"{tag}_io"]
+    skip = cases.unbound_inputs(snap)
+    for f in cases.IO_EXACT:
+        assert np.array_equal(r.io[f], g[f]), f
+    for f in cases.IO_FLOAT:  # bit-exact: same arithmetic widths, serial summation order
+        assert np.array_equal(r.io[f][~skip], g[f][~skip]), f
+    assert np.array_equal(r.order_offset, z[f"{tag}_order_offset"])
+    go, ge = z[f"{tag}_order"], z[f"{tag}_energy"]
+    for s in range(snap.nsub):
+        b = r.order_offset[s]
+        n = r.io["nsource"][s]
+        assert orders_equal_modulo_ties(r.order[b:b + n], go[b:b + n], ge[b:b + n], int(g["nbound"][s])), (name, s)
+    ntot = int(r.order_offset[-1])
+    assert np.array_equal(np.sort(r.energy[:ntot]), np.sort(ge))
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_potential_matches_golden(oracle_lib, name):
+    p, e, _ = cases.CASES[name]()
+    snap, z = load_golden(name)
+    b, en = z["pot_src_range"]
+    src, tgt = snap.pos_mass[b:en], z["pot_tgt"]
+    got = po.tree_potential(oracle_lib, "hbto", p, e, src, tgt, self_mass=tgt[:, 3].copy())
+    assert np.array_equal(got, z["pot_self"])
+    got = po.tree_potential(oracle_lib, "hbto", p, e, src, tgt + np.float32([0.01, 0.0, -0.02, 0.0]))
+    assert np.array_equal(got, z["pot_foreign"])
+    s = int(np.argmax(np.diff(snap.part_offset)))
+    got = po.tree_potential(oracle_lib, "hbto", p, e, src, tgt, self_mass=tgt[:, 3].copy(), tgt_vel=z["be_vel"],
+                            ref_pos=snap.io["avg_pos"][s], ref_vel=snap.io["avg_vel"][s])
+    assert np.array_equal(got, z["be"])
+
+
+def test_oracle_matches_reference_random(oracle_lib, ref_lib):
+    """Fresh random batches (nested + periodic) through both CPU libraries."""
+    oracle_lib.hbto_set_num_threads(1)
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        nsub = 12
+        sizes = synth.subhalo_sizes(rng, nsub, 15, 1500)
+        parent = np.full(nsub, -1)
+        for s in range(1, nsub):
+            if rng.random() < 0.5:
+                parent[s] = rng.integers(0, s)
+        periodic = bool(trial % 2)
+        p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
+        e = capi.make_epoch(0.9)
+        snap = synth.make_snapshot(sizes, seed=100 + trial, parent=parent, wrap=periodic, f_contam=0.3)
+        a = po.run_batch(ref_lib, "hbtref", p, e, snap, flags=trial % 2)
+        b = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=trial % 2)
+        skip = cases.unbound_inputs(snap)
+        for f in cases.IO_EXACT:
+            assert np.array_equal(a.io[f], b.io[f]), f
+        for f in cases.IO_FLOAT:
+            assert np.array_equal(a.io[f][~skip], b.io[f][~skip]), f
+        for s in range(nsub):
+            assert orders_equal_modulo_ties(b.particles(s), a.particles(s), a.energy[a.order_offset[s]:], int(a.io["nbound"][s]))
+    oracle_lib.hbto_set_num_threads(8)
+
+
+def _spline(r, eps):
+    h = 2.8 * eps
+    u = r / h
+    if r >= h:
+        return -1.0 / r
+    if u < 0.5:
+        wp = -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6))
+    else:
+        wp = -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)))
+    return wp / h
+
+
+def test_two_particle_potential_is_the_spline_kernel(oracle_lib):
+    """Analytic KAT: one source, targets at r in and out of the softened range (src/gravity_tree.cpp:141-163)."""
+    eps = 5e-3
+    p = capi.make_params(box_size=62.5, softening=eps, periodic=False)
+    e = capi.make_epoch(0.5)
+    src = np.array([[1.0, 2.0, 3.0, 0.7]], np.float32)
+    rs = np.array([1e-4, 2e-3, 6e-3, 7.1e-3, 1.3e-2, 1.5e-2, 0.3, 5.0])
+    tgt = np.zeros((len(rs), 4), np.float32)
+    tgt[:, :3] = src[0, :3]
+    tgt[:, 0] += rs
+    got = po.tree_potential(oracle_lib, "hbto", p, e, src, tgt)
+    rr = (tgt[:, 0].astype(np.float64) - np.float64(src[0, 0]))
+    want = np.array([_spline(r, p.softening_halo) for r in rr]) * np.float64(src[0, 3]) * p.G / e.scale_factor
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_uniform_sphere_potential(oracle_lib):
+    """Analytic sanity: centre potential of a uniform sphere = -3GM/2R within tree + sampling error."""
+    rng = np.random.default_rng(3)
+    n = 20000
+    x = rng.standard_normal((n, 3))
+    x *= (rng.random(n) ** (1 / 3) / np.linalg.norm(x, axis=1))[:, None]
+    src = np.zeros((n, 4), np.float32)
+    src[:, :3] = x + 10.0
+    src[:, 3] = 1.0 / n
+    p = capi.make_params(box_size=62.5, softening=1e-3, periodic=False)
+    e = capi.make_epoch(1.0)
+    got = po.tree_potential(oracle_lib, "hbto", p, e, src, np.array([[10, 10, 10, 0]], np.float32))
+    assert abs(got[0] / (-1.5 * p.G) - 1) < 0.02
+
+
+def test_tree_invariants_and_counts(oracle_lib):
+    """Root-level invariants via the instrumented walk: a far target accepts exactly the root (1 interaction),
+    a member opens it; cells ~ 0.48 N."""
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=False)
+    e = capi.make_epoch(1.0)
+    snap = synth.make_snapshot([5000], seed=2, wrap=False)
+    pm = np.ascontiguousarray(snap.pos_mass)
+    far = np.array([[1e4, 1e4, 1e4, 0]], np.float32)
+    tg = np.concatenate([far, pm[:8]]).astype(np.float32)
+    acc = np.zeros(len(tg), np.int64)
+    opened = np.zeros(len(tg), np.int64)
+    P = capi._ptr
+    ncell = oracle_lib.hbto_walk_counts(C.byref(p), C.byref(e), len(pm), P(pm, C.c_float), len(tg), P(tg, C.c_float), P(acc, C.c_int64), P(opened, C.c_int64))
+    assert 0.35 * len(pm) < ncell < 0.65 * len(pm)
+    assert acc[0] == 1 and opened[0] == 0
+    assert (acc[1:] > 50).all() and (opened[1:] > 10).all()
+    pot = po.tree_potential(oracle_lib, "hbto", p, e, pm, far)
+    r = np.linalg.norm(far[0, :3].astype(np.float64) - (pm[:, :3].astype(np.float64) * pm[:, 3:4]).sum(0) / pm[:, 3].sum())
+    assert abs(pot[0] / (-p.G * pm[:, 3].astype(np.float64).sum() / r) - 1) < 1e-6
+
+
+def test_partition_edge_cases(oracle_lib):
+    """n = 0, 1, 2, MinNumPartOfSub-1, MinNumPartOfSub: guards of src/subhalo_unbind.cpp:269-293,361-379."""
+    p, e, snap = cases.case_flat()
+    r = po.run_batch(oracle_lib, "hbto", p, e, snap)
+    n = np.diff(snap.part_offset)
+    nb = r.io["nbound"]
+    assert nb[n == 0].tolist() == [0] and (nb[(n >= 1) & (n < 20)] == 1).all()
+    assert (r.io["snapshot_index_of_death"][n < 20] == e.snapshot_index).all()
+    for s in np.nonzero(nb > 1)[0]:
+        en = r.energy[r.order_offset[s]: r.order_offset[s] + nb[s]]
+        assert (en < 0).all() and (np.diff(en) >= 0).all()
