@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py - bound-particle unbinding throughput (particles/s) of the B200-native path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles P]
+
+Workload (BASELINE.json configs[1]): AqA2-shaped single Milky-Way halo, synthetic, one central source of 0.72*P
+particles + 4e4 subhaloes (dN/dn ~ n^-1.9 on [20, 5e6], nesting depth <= 4) totalling P = 1.8e8 particles per GPU,
+BoxSize 100, softening 4.8e-5, periodic off, exact potential (MaxSampleSizeOfPotentialEstimate 0), theta 0.45.
+A "step" is one RefineParticles-equivalent pass (all nesting levels, all iterations, TruncateSource) over the batch.
+
+  value : whole-job particles/s with the batch resident in HBM (hbtu_execute only), CUDA-event timed on the
+          library's stream, max over ranks.
+  e2e   : the same through the C-ABI call a host shim makes (hbtu_unbind_batch) from pinned HOST buffers:
+          H2D of positions/velocities and D2H of the new particle orders + records inside the timed region.
+  N > 1 : one process per GPU (torchrun), each rank owns one such halo (weak scaling; hierarchies never span
+          ranks); the only collective is the NCCL all-gather of the per-subhalo result records.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref: the unmodified HBT+ sources, else the
+oracle port) on a bounded sample of the same workload with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from hbtplus_b200 import capi, synth  # noqa: E402
+
+METRIC = "bound-particle unbinding throughput"
+UNIT = "particles/s"
+BOX, EPS = 100.0, 4.8e-5
+SEED = 20240002
+FLOP_PER_INTERACTION = 12  # 3 FADD + FMUL + 2 FFMA + FSETP + FFMA (+MUFU) = 8 issue slots = 12 flop
+
+
+def params_for(device: int = 0) -> capi.Params:
+    return capi.make_params(box_size=BOX, softening=EPS, periodic=False, max_sample_size=0, device=device)
+
+
+def workload_sizes(particles: float, seed: int):
+    rng = np.random.default_rng(seed)
+    nsub = max(50, int(40000 * min(1.0, particles / 1.8e8)))
+    n_max = 5e6 * min(1.0, particles / 1.8e8)
+    sizes = synth.aqa2_sizes(rng, n_total=particles, central_frac=0.72, nsub=nsub, n_max=max(n_max, 2000))
+    parent = synth.nest_forest(rng, sizes, max_depth=4, p_nest=0.5, root=0)
+    return sizes, parent
+
+
+def cpu_sample(particles: float, seed: int, target: int):
+    """Bounded sample of the workload for the CPU legs: whole sub-hierarchies (depth-1 subhaloes of the central with
+    everything nested in them), taken in index order with a stride until ~`target` particles are collected."""
+    sizes, parent = workload_sizes(particles, seed)
+    nsub = len(sizes)
+    root = np.arange(nsub)
+    for s in np.argsort(-sizes, kind="stable"):  # parents are larger, so they come first
+        if parent[s] > 0:
+            root[s] = root[parent[s]]
+    tops = np.nonzero(parent == 0)[0]
+    rng = np.random.default_rng(seed + 1)
+    rng.shuffle(tops)
+    chosen, tot = [], 0
+    for t in tops:
+        members = np.nonzero(root == t)[0]
+        n = int(sizes[members].sum())
+        if n > target // 3:
+            continue  # keep the sample bounded: one giant sub-hierarchy would be most of the CPU time
+        chosen.extend(members.tolist())
+        tot += n
+        if tot >= target:
+            break
+    chosen = np.array(sorted(chosen))
+    local = {int(g): i for i, g in enumerate(chosen)}
+    par = np.array([local.get(int(parent[g]), -1) for g in chosen])
+    snap = synth.make_snapshot(sizes[chosen], seed=seed + 2, box_size=BOX, particle_mass=1e-6, parent=par, wrap=False,
+                               centre=[BOX / 2] * 3, f_contam=0.2)
+    desc = (f"{len(chosen)} subhaloes in {int((par < 0).sum())} whole sub-hierarchies of the central (sizes {int(sizes[chosen].min())}.."
+            f"{int(sizes[chosen].max())}, {snap.npart} particles), same generator/seed family as the GPU batch; the 0.72*P central is excluded")
+    return snap, desc
+
+
+def run_cpu(snap, threads: int | None = None):
+    """One RefineParticles-equivalent pass on the host cores; returns (seconds, kind, threads)."""
+    from oracle import pyoracle as po
+
+    p = params_for()
+    e = capi.make_epoch(1.0)
+    ncpu = threads or os.cpu_count() or 1
+    if po.have_ref():
+        lib, prefix, kind = po.load_ref(), "hbtref", "reference"
+    else:
+        if not os.path.exists(po.ORACLE_PATH):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        lib, prefix, kind = po.load_oracle(), "hbto", "port"
+    getattr(lib, prefix + "_set_num_threads")(ncpu)
+    t0 = time.perf_counter()
+    r = po.run_batch(lib, prefix, p, e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE, want_energy=False)
+    dt = time.perf_counter() - t0
+    return dt, kind, ncpu, int(r.io["nbound"].sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=float, default=1.8e8, help="particles per GPU (BASELINE configs[1]: 1.8e8)")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="particles in the bounded CPU sample (~15-20 s on 16 cores)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"AqA2-shaped synthetic Milky-Way halo per GPU: central source 0.72*P + subhaloes dN/dn~n^-1.9 on [20,5e6], nest depth<=4, "
+                f"P={args.particles:.3g} particles, BoxSize {BOX}, eps {EPS}, periodic off, exact potential (MaxSample 0), theta 0.45")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        snap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
+        times, kind, ncpu, nb = [], None, None, 0
+        for i in range(args.warmup + args.steps):
+            dt, kind, ncpu, nb = run_cpu(snap)
+            if i >= args.warmup:
+                times.append(dt)
+        dt = float(np.mean(times))
+        val = snap.npart / dt
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": desc, "cpu_threads": ncpu, "sum_nbound": nb},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from hbtplus_b200.unbind import UnbindContext
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the unbinding path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    sizes, parent = workload_sizes(args.particles, SEED + rank)
+    snap = synth.make_snapshot_torch(sizes, device=dev, seed=SEED + rank, box_size=BOX, particle_mass=1e-6, parent=parent,
+                                     centre=[BOX / 2] * 3, wrap=False, pin=True)
+    torch.cuda.empty_cache()
+    n_local = snap.npart
+    ctx = UnbindContext(params_for(local_rank))
+    e = capi.make_epoch(1.0)
+    flags = capi.HBTU_FLAG_TRUNCATE_SOURCE
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # one counted pass: exact number of accepted pair interactions of a step (roofline numerator); also warm-up 0
+    ctx.stage(e, snap, flags)
+    ctx.set_counting(True)
+    ctx.execute()
+    st0 = ctx.stats()
+    ctx.set_counting(False)
+    for _ in range(args.warmup):
+        ctx.execute()
+    barrier()
+    exec_ms, walk_ms, build_ms, other_ms, wall = [], [], [], [], []
+    with ClockSampler(local_rank) as clk:
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            ctx.execute()
+            wall.append(time.perf_counter() - t0)
+            st = ctx.stats()
+            exec_ms.append(st.execute_ms)
+            walk_ms.append(st.walk_ms)
+            build_ms.append(st.build_ms)
+            other_ms.append(st.other_ms)
+        barrier()
+        # end to end through the ABI call, pinned host buffers in, host arrays out
+        e2e_wall, e2e_h2d, e2e_d2h = [], 0, 0
+        res = None
+        for i in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            res = ctx.unbind_batch(e, snap, flags=flags, want_energy=False)
+            dt = time.perf_counter() - t0
+            if i > 0:
+                e2e_wall.append(dt)
+            st = ctx.stats()
+            e2e_h2d, e2e_d2h = st.h2d_bytes, st.d2h_bytes
+    clocks = clk.summary()
+    launches = ctx.stats().kernel_launches
+
+    t_dev = torch.tensor([sum(exec_ms) * 1e-3, sum(e2e_wall), sum(walk_ms) * 1e-3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_local), float(res.io["nbound"].sum()), float(st0.pair_interactions)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        # the path's only collective: gather the per-subhalo result records (~150 B each) of all ranks
+        from hbtplus_b200 import sched
+
+        nsub_all = torch.tensor([snap.nsub], device=dev)
+        counts = [torch.zeros_like(nsub_all) for _ in range(world)]
+        dist.all_gather(counts, nsub_all)
+        offs = np.concatenate([[0], np.cumsum([int(c) for c in counts])])
+        table = sched.gather_records(res.io, offs[rank] + np.arange(snap.nsub), int(offs[-1]), device=dev)
+        assert table is not None and len(table) == offs[-1]
+    t_exec, t_e2e, t_walk = (float(x) for x in t_dev.cpu())
+    n_all, nb_all, inter_all = (float(x) for x in tot.cpu())
+    value = n_all * args.steps / t_exec
+    e2e_value = n_all * len(e2e_wall) / t_e2e
+
+    out = None
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_inter = nsm * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 8
+        inter_rate = st0.pair_interactions * args.steps / (sum(walk_ms) * 1e-3)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_exec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "particles_per_gpu": n_local, "subhaloes_per_gpu": snap.nsub, "sum_nbound": nb_all,
+                       "l2_policy": "inputs (5.8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
+                       "timing": "CUDA events on the library stream around hbtu_execute, max over ranks", "wall_ms_per_step": float(np.mean(wall)) * 1e3,
+                       "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
+                       "rounds": int(st0.rounds), "pair_interactions_per_step": inter_all},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
+                    "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "api": "hbtu_unbind_batch from pinned host buffers"},
+            "gpu_launches": int(launches * args.steps),
+            "roofline": {"bound": "fp32_issue", "achieved": inter_rate * FLOP_PER_INTERACTION / 1e12, "peak": peak_inter * FLOP_PER_INTERACTION / 1e12,
+                         "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "kernel": "walk_kernel",
+                         "interactions_per_s": inter_rate, "peak_interactions_per_s": peak_inter,
+                         "peak_source": f"{nsm} SM x 128 fp32 lanes x sm_max_mhz ({peak_src}) / 8 issue slots per interaction (SURVEY.md 8(d)); 12 flop per interaction",
+                         "note": "tensor cores deliberately unused (not a dense contraction); kernel share of the step = walk/total in config.phase_ms"},
+        }
+        if world == 1:
+            csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
+            dt, kind, ncpu, _ = run_cpu(csnap)
+            out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

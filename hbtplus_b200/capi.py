@@ -95,6 +95,7 @@ class Stats(C.Structure):
         ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("execute_ms", C.c_double),
     ]
 
 

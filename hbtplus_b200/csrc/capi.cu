@@ -375,6 +375,7 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
   int rc = guarded(ctx, [&](Context &cc) {
     HBT_CUDA(cudaStreamCreateWithFlags(&cc.stream, cudaStreamNonBlocking));
     for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : cc.ev_exec) HBT_CUDA(cudaEventCreate(&ev));
     HBT_CUDA(cudaMalloc(&cc.d_counters, 2 * sizeof(unsigned long long)));
   });
   if (rc != HBTU_OK)
@@ -404,6 +405,8 @@ void hbtu_destroy(hbtu_ctx *ctx)
   cudaFree(c.d_slot_base);
   cudaFree(c.d_counters);
   for (auto &ev : c.ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c.ev_exec)
     if (ev) cudaEventDestroy(ev);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;

@@ -24,6 +24,7 @@ struct Context
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_exec[2] = {nullptr, nullptr};
   std::string last_error;
 
   // staged batch -------------------------------------------------------------------------------

@@ -721,6 +721,7 @@ void execute_batch(Context &c)
   const int nsub = (int)c.nsub;
   c.ls.launches = 0;
   std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms));
+  HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
   if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
   if (c.cfg.max_sample > 0)
     for (int s = 0; s < nsub; s++)
@@ -875,6 +876,13 @@ void execute_batch(Context &c)
     HBT_CUDA(cudaMemcpy(cnt, c.d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
     c.stats.pair_interactions = (int64_t)cnt[0];
     c.stats.nodes_visited = (int64_t)cnt[1];
+  }
+  HBT_CUDA(cudaEventRecord(c.ev_exec[1], st));
+  HBT_CUDA(cudaEventSynchronize(c.ev_exec[1]));
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
+    c.stats.execute_ms = ms;
   }
   c.stats.kernel_launches = c.ls.launches;
   c.executed = true;

@@ -168,3 +168,149 @@ def make_snapshot(
         nest_offset[1:] = np.cumsum([len(l) for l in lists])
         nest_list = np.array([c for l in lists for c in l], np.int32)
     return Snapshot(part_offset, pos_mass, vel4, nest_offset, nest_list, io)
+
+
+def nest_forest(rng: np.random.Generator, sizes: np.ndarray, max_depth: int = 4, p_nest: float = 0.5, root: int | None = 0) -> np.ndarray:
+    """Random nesting: every subhalo is nested in a LARGER one (or in `root`), depth <= max_depth.
+
+    Mirrors what NestSubhalos produces (src/subhalo_tracking.cpp:669): satellites hang off more massive hosts."""
+    nsub = len(sizes)
+    order = np.argsort(-np.asarray(sizes), kind="stable")
+    parent = np.full(nsub, -1, np.int64)
+    depth = np.zeros(nsub, np.int64)
+    placed = []
+    for s in order:
+        if root is not None and s == root:
+            placed.append(s)
+            continue
+        cand = -1
+        if placed and rng.random() < p_nest:
+            c = placed[int(rng.integers(0, len(placed)))]
+            if depth[c] + 1 <= max_depth and sizes[c] > sizes[s]:
+                cand = c
+        if cand < 0 and root is not None:
+            cand = root
+        parent[s] = cand
+        depth[s] = depth[cand] + 1 if cand >= 0 else 0
+        placed.append(s)
+    return parent
+
+
+def make_snapshot_torch(sizes, *, device, seed: int = 20240002, box_size: float = 100.0, particle_mass: float = 1e-6,
+                        f_contam: float = 0.2, contam_scale: float = 2.0, contam_hot: float = 4.0, parent=None, centre=None,
+                        wrap: bool = False, frame_noise: float = 0.05, pin: bool = True) -> Snapshot:
+    """Same construction as make_snapshot, with the per-particle work done by torch on `device`
+    (a 1.8e8-particle AqA2-shaped batch takes seconds instead of minutes).  Returns HOST arrays
+    (pinned when pin=True) - torch is used here only as an array library / allocator."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    sizes = np.asarray(sizes, np.int64)
+    nsub = len(sizes)
+    part_offset = np.zeros(nsub + 1, np.int64)
+    np.cumsum(sizes, out=part_offset[1:])
+    n_tot = int(part_offset[-1])
+    mtot = np.maximum(sizes, 1) * particle_mass
+    rvir = (G_INTERNAL * mtot / 1e6) ** (1.0 / 3.0)
+    a_of = rvir / 4.0
+    centres = rng.random((nsub, 3)) * box_size if centre is None else np.broadcast_to(np.asarray(centre, float), (nsub, 3)).copy()
+    bulk = rng.standard_normal((nsub, 3)) * 200.0
+    if parent is not None:
+        parent = np.asarray(parent, np.int64)
+        depth = np.zeros(nsub, np.int64)
+        for s in range(nsub):
+            q, d = s, 0
+            while parent[q] >= 0:
+                q, d = parent[q], d + 1
+            depth[s] = d
+        dirs = rng.standard_normal((nsub, 3))
+        dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+        tang = np.cross(dirs, rng.standard_normal((nsub, 3)))
+        tang /= np.linalg.norm(tang, axis=1)[:, None]
+        frac = rng.uniform(0.3, 1.5, nsub)
+        for s in np.argsort(depth, kind="stable"):
+            p = parent[s]
+            if p < 0:
+                continue
+            rad = a_of[p] * frac[s]
+            centres[s] = centres[p] + dirs[s] * rad
+            vc = np.sqrt(G_INTERNAL * mtot[p] * (rad / (rad + a_of[p])) ** 2 / rad)
+            bulk[s] = bulk[p] + tang[s] * vc * 0.8
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = lambda x, dt=torch.float32: torch.as_tensor(x, dtype=dt, device=device)
+    sizes_t = torch.as_tensor(sizes, device=device)
+    sub_of = torch.repeat_interleave(torch.arange(nsub, device=device), sizes_t)
+    a = t(a_of)[sub_of]
+    umax = (10.0 / 11.0) ** 2
+    su = torch.sqrt(torch.rand(n_tot, generator=g, device=device) * umax)
+    r = a * su / (1.0 - su)
+    del su
+    is_c = torch.rand(n_tot, generator=g, device=device) < f_contam
+    r = torch.where(is_c, r * contam_scale, r)
+    cost = torch.rand(n_tot, generator=g, device=device) * 2 - 1
+    sint = torch.sqrt(1 - cost * cost)
+    phi = torch.rand(n_tot, generator=g, device=device) * (2 * np.pi)
+    pos_mass = torch.empty((n_tot, 4), dtype=torch.float32, device=device)
+    c_t = t(centres)[sub_of]
+    pos_mass[:, 0] = r * sint * torch.cos(phi) + c_t[:, 0]
+    pos_mass[:, 1] = r * sint * torch.sin(phi) + c_t[:, 1]
+    pos_mass[:, 2] = r * cost + c_t[:, 2]
+    del c_t, cost, sint, phi
+    if wrap:
+        pos_mass[:, :3] = torch.remainder(pos_mass[:, :3], box_size)
+    pos_mass[:, 3] = particle_mass
+    menc = t(mtot)[sub_of] * (r / (r + a)) ** 2
+    sigma = torch.sqrt(G_INTERNAL * menc / (3.0 * torch.maximum(r, 1e-3 * a)))
+    del menc, r, a
+    sigma = torch.where(is_c, sigma * contam_hot, sigma)
+    del is_c
+    vel = torch.zeros((n_tot, 4), dtype=torch.float32, device=device)
+    b_t = t(bulk)[sub_of]
+    for j in range(3):
+        vel[:, j] = torch.randn(n_tot, generator=g, device=device) * sigma + b_t[:, j]
+    del b_t, sigma, sub_of
+
+    def to_host(x):
+        h = torch.empty(x.shape, dtype=x.dtype, pin_memory=pin and torch.cuda.is_available())
+        h.copy_(x)
+        return h.numpy()
+
+    first = torch.as_tensor(np.minimum(part_offset[:-1], max(n_tot - 1, 0)), device=device)
+    mb_pos = pos_mass[first, :3].cpu().numpy() if n_tot else np.zeros((nsub, 3), np.float32)
+    mb_vel = vel[first, :3].cpu().numpy() if n_tot else np.zeros((nsub, 3), np.float32)
+    pm_h, vel_h = to_host(pos_mass), to_host(vel)
+    del pos_mass, vel
+    io = np.zeros(nsub, SUBIO_DTYPE)
+    noise = rng.standard_normal((nsub, 3)) * frame_noise
+    ref_pos = centres + noise * a_of[:, None]
+    if wrap:
+        ref_pos = np.mod(ref_pos, box_size)
+    io["avg_pos"] = ref_pos.astype(np.float32)
+    io["avg_vel"] = (bulk + noise[:, ::-1] * 20.0).astype(np.float32)
+    io["mostbound_pos"] = mb_pos
+    io["mostbound_vel"] = mb_vel
+    io["nbound"] = sizes
+    io["sink_track_id"] = -1
+    io["snapshot_index_of_death"] = -1
+    io["snapshot_index_of_sink"] = -1
+    nest_offset = nest_list = None
+    if parent is not None:
+        order = np.argsort(parent, kind="stable")
+        order = order[parent[order] >= 0]
+        counts = np.bincount(parent[order], minlength=nsub)
+        nest_offset = np.zeros(nsub + 1, np.int64)
+        np.cumsum(counts, out=nest_offset[1:])
+        nest_list = order.astype(np.int32)
+    return Snapshot(part_offset, pm_h, vel_h, nest_offset, nest_list, io)
+
+
+def aqa2_sizes(rng: np.random.Generator, n_total: float = 1.8e8, central_frac: float = 0.72, nsub: int = 40000, n_max: float = 5e6):
+    """AqA2-shaped size list (SURVEY.md section 8(d) cfg 2): one central source + `nsub` subhaloes with
+    dN/dn ~ n^-1.9 on [20, n_max], rescaled so that the batch holds ~n_total particles."""
+    n_central = int(n_total * central_frac)
+    sub = subhalo_sizes(rng, nsub, 20, int(n_max))
+    want = n_total - n_central
+    for _ in range(4):  # rescale the draw to the wanted particle total, keeping 20 <= n <= n_max
+        sub = np.clip((sub * (want / sub.sum())).astype(np.int64), 20, int(n_max))
+    return np.concatenate([[n_central], sub]).astype(np.int64)

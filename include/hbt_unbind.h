@@ -180,6 +180,7 @@ typedef struct hbtu_stats
   double other_ms;             /* partition / sort / reductions                        */
   double h2d_ms, d2h_ms;       /* copies in hbtu_stage / hbtu_fetch                    */
   int64_t h2d_bytes, d2h_bytes;
+  double execute_ms;           /* CUDA-event time of the whole hbtu_execute (host planning gaps included) */
 } hbtu_stats;
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted
