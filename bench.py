@@ -71,7 +71,7 @@ def cpu_sample(particles: float, seed: int, target: int):
     for t in tops:
         members = np.nonzero(root == t)[0]
         n = int(sizes[members].sum())
-        if n > target // 3:
+        if n > target // 10:
             continue  # keep the sample bounded: one giant sub-hierarchy would be most of the CPU time
         chosen.extend(members.tolist())
         tot += n
@@ -168,8 +168,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=float, default=1.8e8, help="particles per GPU (BASELINE configs[1]: 1.8e8)")
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="particles in the bounded CPU sample (~15-20 s on 16 cores)")
+    ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="particles in the bounded CPU sample (10-30 s on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--profile", action="store_true", help="for ncu: no counting pass, no e2e, no CPU leg (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +226,8 @@ def main():
 
     # one counted pass: exact number of accepted pair interactions of a step (roofline numerator); also warm-up 0
     ctx.stage(e, snap, flags)
-    ctx.set_counting(True)
+    if not args.profile:
+        ctx.set_counting(True)
     ctx.execute()
     st0 = ctx.stats()
     ctx.set_counting(False)
@@ -247,7 +249,7 @@ def main():
         # end to end through the ABI call, pinned host buffers in, host arrays out
         e2e_wall, e2e_h2d, e2e_d2h = [], 0, 0
         res = None
-        for i in range(args.e2e_steps + 1):
+        for i in range(0 if args.profile else args.e2e_steps + 1):
             barrier()
             t0 = time.perf_counter()
             res = ctx.unbind_batch(e, snap, flags=flags, want_energy=False)
@@ -260,6 +262,9 @@ def main():
     launches = ctx.stats().kernel_launches
 
     t_dev = torch.tensor([sum(exec_ms) * 1e-3, sum(e2e_wall), sum(walk_ms) * 1e-3], dtype=torch.float64, device=dev)
+    if res is None:
+        res = ctx.fetch(want_energy=False)
+        e2e_wall = []
     tot = torch.tensor([float(n_local), float(res.io["nbound"].sum()), float(st0.pair_interactions)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -276,7 +281,7 @@ def main():
     t_exec, t_e2e, t_walk = (float(x) for x in t_dev.cpu())
     n_all, nb_all, inter_all = (float(x) for x in tot.cpu())
     value = n_all * args.steps / t_exec
-    e2e_value = n_all * len(e2e_wall) / t_e2e
+    e2e_value = n_all * len(e2e_wall) / t_e2e if t_e2e > 0 else None
 
     out = None
     if rank == 0:
@@ -307,7 +312,7 @@ def main():
                          "peak_source": f"{nsm} SM x 128 fp32 lanes x sm_max_mhz ({peak_src}) / 8 issue slots per interaction (SURVEY.md 8(d)); 12 flop per interaction",
                          "note": "tensor cores deliberately unused (not a dense contraction); kernel share of the step = walk/total in config.phase_ms"},
         }
-        if world == 1:
+        if world == 1 and not args.profile:
             csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
             dt, kind, ncpu, _ = run_cpu(csnap)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}

@@ -312,10 +312,33 @@ __device__ __forceinline__ double warp_sum_d(double v)
   return v;
 }
 
-// accumulate NV doubles per target into subs[sub].sums with warp aggregation
+// accumulate NV doubles per target into subs[sub].sums.  tgt_seg is non-decreasing, so a block whose first and
+// last target share a segment reduces in shared memory and issues NV atomics per BLOCK (the 1e8-particle
+// central would otherwise serialise millions of same-address fp64 atomics); mixed blocks fall back to
+// warp-level aggregation, mixed warps to per-lane atomics.
 template <int NV>
-__device__ __forceinline__ void seg_accumulate(const double (&v)[NV], bool contributes, int a, int sub, SubState *subs)
+__device__ __forceinline__ void seg_accumulate(const double (&v)[NV], bool contributes, int a, int sub, SubState *subs, bool block_uniform)
 {
+  __shared__ double red[NV][kBlock / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (block_uniform)
+  {
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+    {
+      double s = warp_sum_d(contributes ? v[i] : 0.0);
+      if (lane == 0) red[i][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+      double s = 0.0;
+      for (int k = 0; k < kBlock / 32; k++) s += red[threadIdx.x][k];
+      int sub0 = __shfl_sync((1u << NV) - 1u, sub, 0);
+      if (sub0 >= 0 && s != 0.0) atomicAdd(&subs[sub0].sums[threadIdx.x], s);
+    }
+    return;
+  }
   int a0 = __shfl_sync(0xffffffffu, a, 0);
   int sub0 = __shfl_sync(0xffffffffu, sub, 0);
   if (__all_sync(0xffffffffu, a == a0))
@@ -326,7 +349,7 @@ __device__ __forceinline__ void seg_accumulate(const double (&v)[NV], bool contr
     for (int i = 0; i < NV; i++)
     {
       double s = warp_sum_d(contributes ? v[i] : 0.0);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&subs[sub0].sums[i], s);
+      if (lane == 0) atomicAdd(&subs[sub0].sums[i], s);
     }
   }
   else if (contributes)
@@ -344,6 +367,8 @@ __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__r
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < T;
   int a = valid ? tgt_seg[t] : -1;
+  const int tb0 = blockIdx.x * blockDim.x, tb1 = min(tb0 + (int)blockDim.x, T) - 1;
+  const bool block_uniform = (tb1 == tb0 + (int)blockDim.x - 1) && tgt_seg[tb0] == tgt_seg[tb1];
   int sub = -1;
   bool contributes = false;
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__r
       }
     }
   }
-  seg_accumulate<7>(v, contributes, a, sub, subs);
+  seg_accumulate<7>(v, contributes, a, sub, subs, block_uniform);
 }
 
 __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
@@ -421,6 +446,8 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < T;
   int a = valid ? tgt_seg[t] : -1;
+  const int tb0 = blockIdx.x * blockDim.x, tb1 = min(tb0 + (int)blockDim.x, T) - 1;
+  const bool block_uniform = (tb1 == tb0 + (int)blockDim.x - 1) && tgt_seg[tb0] == tgt_seg[tb1];
   int sub = -1;
   bool contributes = false;
   double v[6] = {0, 0, 0, 0, 0, 0};
@@ -455,7 +482,7 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
       v[5] = (double)m;
     }
   }
-  seg_accumulate<6>(v, contributes, a, sub, subs);
+  seg_accumulate<6>(v, contributes, a, sub, subs, block_uniform);
 }
 
 struct RoundResult
