@@ -1,0 +1,276 @@
+// subhalo_unbind_b200.cpp - drop-in replacement object for the reference's src/subhalo_unbind.cpp.
+//
+// It defines exactly the four member functions that file defines
+//     void SubhaloSnapshot_t::RefineParticles()                         (src/subhalo.h:245)
+//     void Subhalo_t::Unbind(const Snapshot_t &epoch)                   (src/subhalo.h:111)
+//     void Subhalo_t::RecursiveUnbind(SubhaloList_t&, const Snapshot_t&) (src/subhalo.h:112)
+//     void Subhalo_t::TruncateSource()                                  (src/subhalo.h:114)
+// with unchanged signatures, so HBT.cpp:75, subhalo_merge.cpp:210 and every other caller link against it
+// unmodified.  Each one packs the reference's own data structures (vector<Particle_t>, Subhalo_t scalars,
+// HBTConfig, Cosmology) into the POD arguments of include/hbt_unbind.h, calls the CUDA library and unpacks.
+// There is no algorithm and no CPU fallback here: a failing call throws std::runtime_error (the reference's own
+// error style, src/config_parser.cpp:70).  Compile with the same -D flags as the rest of HBT+ (V32: -DDM_ONLY).
+//
+// Build:  g++ -std=c++11 -O2 -fopenmp $(HBT_DEFS) -I$(HBT)/src -I<repo>/include -c subhalo_unbind_b200.cpp
+// Link :  replace subhalo_unbind.o by subhalo_unbind_b200.o and add -L<repo>/hbtplus_b200/csrc -lhbtunbind
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "datatypes.h"
+#include "snapshot_number.h"
+#include "subhalo.h"
+
+#include "hbt_unbind.h"
+
+static_assert(sizeof(HBTReal) == 4, "only the HBTReal=float ABI variant of libhbtunbind is built");
+
+namespace
+{
+hbtu_ctx *g_ctx = nullptr;
+hbtu_params g_params;
+
+void fill_params(hbtu_params &p)
+{
+  std::memset(&p, 0, sizeof(p));
+  p.struct_size = sizeof(hbtu_params);
+  p.real_bytes = sizeof(HBTReal);
+  p.min_num_part_of_sub = HBTConfig.MinNumPartOfSub;
+  p.periodic_boundary_on = HBTConfig.PeriodicBoundaryOn;
+  p.refine_mostbound_particle = HBTConfig.RefineMostboundParticle;
+  const char *dev = getenv("HBT_UNBIND_DEVICE"); // one MPI rank <-> one GPU; default: local rank modulo device count is the launcher's job
+  p.device = dev ? atoi(dev) : 0;
+  p.max_sample_size = HBTConfig.MaxSampleSizeOfPotentialEstimate;
+  p.bound_mass_precision = HBTConfig.BoundMassPrecision;
+  p.source_sub_relax_factor = HBTConfig.SourceSubRelaxFactor;
+  p.box_size = HBTConfig.BoxSize;
+  p.box_half = HBTConfig.BoxHalf;
+  p.softening_halo = HBTConfig.SofteningHalo;
+  p.tree_node_open_angle_square = HBTConfig.TreeNodeOpenAngleSquare;
+  p.tree_node_resolution = HBTConfig.TreeNodeResolution;
+  p.tree_node_resolution_half = HBTConfig.TreeNodeResolutionHalf;
+  p.tree_alloc_factor = HBTConfig.TreeAllocFactor;
+  p.tree_min_num_of_cells = HBTConfig.TreeMinNumOfCells;
+  p.G = PhysicalConst::G;
+  p.direct_sum_max = 0;
+}
+
+hbtu_ctx *context()
+{ // one context per process (= per MPI rank); re-created if the configuration changed
+  hbtu_params p;
+  fill_params(p);
+  if (g_ctx && std::memcmp(&p, &g_params, sizeof(p)) == 0) return g_ctx;
+  if (g_ctx) hbtu_destroy(g_ctx);
+  g_ctx = nullptr;
+  int rc = hbtu_create(&p, &g_ctx);
+  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_create failed: ") + hbtu_last_error(nullptr));
+  g_params = p;
+  static bool registered = false;
+  if (!registered)
+  {
+    atexit([] { if (g_ctx) hbtu_destroy(g_ctx); g_ctx = nullptr; });
+    registered = true;
+  }
+  return g_ctx;
+}
+
+struct Batch
+{ // pack -> call -> unpack of a set of subhaloes given by index into `Subhalos`
+  std::vector<Subhalo_t *> subs;
+  std::vector<int64_t> part_offset, nest_offset;
+  std::vector<int32_t> nest_list;
+
+  void run(const Snapshot_t &epoch, int32_t flags)
+  {
+    const int64_t nsub = subs.size();
+    if (nsub == 0) return;
+    part_offset.assign(nsub + 1, 0);
+    for (int64_t s = 0; s < nsub; s++) part_offset[s + 1] = part_offset[s] + (int64_t)subs[s]->Particles.size();
+    const int64_t N = part_offset[nsub];
+    std::vector<Particle_t> all(N); // the reference's Unbind also makes one full copy (subhalo_unbind.cpp:409-415)
+    std::vector<float> pos_mass(4 * (size_t)N), vel(4 * (size_t)N);
+    std::vector<hbtu_sub_io> io(nsub);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t s = 0; s < nsub; s++)
+    {
+      const Subhalo_t &sub = *subs[s];
+      int64_t b = part_offset[s];
+      for (size_t i = 0; i < sub.Particles.size(); i++)
+      {
+        const Particle_t &p = sub.Particles[i];
+        all[b + i] = p;
+        float *x = &pos_mass[4 * (b + i)], *v = &vel[4 * (b + i)];
+        x[0] = p.ComovingPosition[0]; x[1] = p.ComovingPosition[1]; x[2] = p.ComovingPosition[2]; x[3] = p.Mass;
+        v[0] = p.PhysicalVelocity[0]; v[1] = p.PhysicalVelocity[1]; v[2] = p.PhysicalVelocity[2]; v[3] = 0.f;
+      }
+      hbtu_sub_io &o = io[s];
+      std::memset(&o, 0, sizeof(o));
+      for (int j = 0; j < 3; j++)
+      {
+        o.avg_pos[j] = sub.ComovingAveragePosition[j];
+        o.avg_vel[j] = sub.PhysicalAverageVelocity[j];
+        o.mostbound_pos[j] = sub.ComovingMostBoundPosition[j];
+        o.mostbound_vel[j] = sub.PhysicalMostBoundVelocity[j];
+        o.specific_angular_momentum[j] = sub.SpecificAngularMomentum[j];
+      }
+      o.nbound = sub.Nbound;
+      o.sink_track_id = sub.SinkTrackId;
+      o.snapshot_index_of_death = sub.SnapshotIndexOfDeath;
+      o.snapshot_index_of_sink = sub.SnapshotIndexOfSink;
+      o.mbound = sub.Mbound;
+      o.specific_self_potential_energy = sub.SpecificSelfPotentialEnergy;
+      o.specific_self_kinetic_energy = sub.SpecificSelfKineticEnergy;
+    }
+    hbtu_epoch e;
+    e.scale_factor = epoch.Cosmology.ScaleFactor;
+    e.hz = epoch.Cosmology.Hz;
+    e.snapshot_index = epoch.GetSnapshotIndex();
+    e.reserved = 0;
+    const int64_t *no = nest_offset.empty() ? nullptr : nest_offset.data();
+    const int32_t *nl = nest_offset.empty() ? nullptr : nest_list.data();
+    int64_t cap = hbtu_order_capacity(nsub, part_offset.data(), no, nl);
+    if (cap < 0) throw std::runtime_error("hbtu_order_capacity: malformed nesting");
+    std::vector<int64_t> order_offset(nsub + 1);
+    std::vector<int32_t> order(cap > 0 ? cap : 1);
+#ifdef SAVE_BINDING_ENERGY
+    std::vector<float> energy(cap > 0 ? cap : 1);
+    float *pe = energy.data();
+#else
+    float *pe = nullptr;
+#endif
+    hbtu_ctx *ctx = context();
+    int rc = hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), no, nl, io.data(), flags, cap,
+                               order_offset.data(), order.data(), pe);
+    if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_unbind_batch failed: ") + hbtu_last_error(ctx));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t s = 0; s < nsub; s++)
+    {
+      Subhalo_t &sub = *subs[s];
+      const hbtu_sub_io &o = io[s];
+      sub.Particles.resize(o.nsource);
+      const int32_t *ord = &order[order_offset[s]];
+      for (int64_t i = 0; i < o.nsource; i++) sub.Particles[i] = all[ord[i]];
+      for (int j = 0; j < 3; j++)
+      {
+        sub.ComovingAveragePosition[j] = o.avg_pos[j];
+        sub.PhysicalAverageVelocity[j] = o.avg_vel[j];
+        sub.ComovingMostBoundPosition[j] = o.mostbound_pos[j];
+        sub.PhysicalMostBoundVelocity[j] = o.mostbound_vel[j];
+        sub.SpecificAngularMomentum[j] = o.specific_angular_momentum[j];
+      }
+      sub.Nbound = (HBTInt)o.nbound;
+      sub.Mbound = o.mbound;
+      sub.SinkTrackId = (HBTInt)o.sink_track_id;
+      sub.SnapshotIndexOfDeath = o.snapshot_index_of_death;
+      sub.SnapshotIndexOfSink = o.snapshot_index_of_sink;
+      sub.SpecificSelfPotentialEnergy = o.specific_self_potential_energy;
+      sub.SpecificSelfKineticEnergy = o.specific_self_kinetic_energy;
+#ifdef SAVE_BINDING_ENERGY
+      sub.Energies.assign(&energy[order_offset[s]], &energy[order_offset[s]] + (o.nbound < o.nsource ? o.nbound : o.nsource));
+#endif
+#ifndef DM_ONLY
+      if (sub.Particles.size() >= 2) sub.CountParticleTypes(); else sub.CountParticles(); // host bookkeeping stays on the host
+#endif
+    }
+  }
+};
+
+// append `sub` and, depth first, everything nested in it; returns its batch index
+int64_t add_hierarchy(Batch &b, std::vector<std::vector<int32_t>> &lists, SubhaloList_t &Subhalos, Subhalo_t &sub)
+{
+  int64_t me = b.subs.size();
+  b.subs.push_back(&sub);
+  lists.emplace_back();
+  for (HBTInt i = 0; i < (HBTInt)sub.NestedSubhalos.size(); i++)
+  {
+    int64_t ch = add_hierarchy(b, lists, Subhalos, Subhalos[sub.NestedSubhalos[i]]);
+    lists[me].push_back((int32_t)ch);
+  }
+  return me;
+}
+void close_nests(Batch &b, const std::vector<std::vector<int32_t>> &lists)
+{
+  b.nest_offset.assign(lists.size() + 1, 0);
+  b.nest_list.clear();
+  for (size_t s = 0; s < lists.size(); s++)
+  {
+    b.nest_list.insert(b.nest_list.end(), lists[s].begin(), lists[s].end());
+    b.nest_offset[s + 1] = b.nest_list.size();
+  }
+}
+} // namespace
+
+void Subhalo_t::Unbind(const Snapshot_t &epoch)
+{ // second caller: subhalo_merge.cpp:207-210 (merged hosts), one subhalo per call
+  Batch b;
+  b.subs.push_back(this);
+  b.run(epoch, 0);
+}
+
+void Subhalo_t::RecursiveUnbind(SubhaloList_t &Subhalos, const Snapshot_t &snap)
+{
+  Batch b;
+  std::vector<std::vector<int32_t>> lists;
+  add_hierarchy(b, lists, Subhalos, *this);
+  close_nests(b, lists);
+  b.run(snap, 0);
+}
+
+void Subhalo_t::TruncateSource()
+{ // pure host bookkeeping (8 lines in the reference, src/subhalo_unbind.cpp:449-458); RefineParticles below lets the
+  // library truncate, this is for the merge path that calls it separately (subhalo_merge.cpp:211-214)
+  HBTInt n = Nbound <= 1 ? Nbound : (HBTInt)(Nbound * HBTConfig.SourceSubRelaxFactor);
+  if (n > (HBTInt)Particles.size()) n = Particles.size();
+  Particles.resize(n);
+}
+
+void SubhaloSnapshot_t::RefineParticles()
+{ // ONE batch for the whole rank: every host halo's hierarchy, the field subhaloes and the new-born ones
+  Batch b;
+  std::vector<std::vector<int32_t>> lists;
+  std::vector<char> done(Subhalos.size(), 0);
+#ifdef INCLUSIVE_MASS
+  for (auto &sub : Subhalos) { b.subs.push_back(&sub); lists.emplace_back(); }
+#else
+  HBTInt NumHalos = MemberTable.SubGroups.size();
+  for (HBTInt haloid = 0; haloid < NumHalos; haloid++)
+  {
+    auto &subgroup = MemberTable.SubGroups[haloid];
+    if (subgroup.size() == 0) continue;
+    auto &central = Subhalos[subgroup[0]];
+    // the other heads of this host feed the central like nested subhaloes (subhalo_unbind.cpp:485-492)
+    auto &heads = MemberTable.SubGroupsOfHeads[haloid];
+    int64_t me = add_hierarchy(b, lists, Subhalos, central);
+    for (size_t i = 1; i < heads.size(); i++)
+    {
+      int64_t ch = add_hierarchy(b, lists, Subhalos, Subhalos[heads[i]]);
+      lists[me].push_back((int32_t)ch);
+    }
+  }
+  for (auto *s : b.subs) done[s - Subhalos.data()] = 1;
+  HBTInt NumField = MemberTable.SubGroups[-1].size();
+  for (HBTInt i = 0; i < NumField; i++)
+  { // field subhaloes: plain Unbind, no recursion (subhalo_unbind.cpp:498-503)
+    HBTInt subid = MemberTable.SubGroups[-1][i];
+    if (done[subid]) continue;
+    b.subs.push_back(&Subhalos[subid]);
+    lists.emplace_back();
+    done[subid] = 1;
+  }
+  for (HBTInt i = MemberTable.AllMembers.size(); i < (HBTInt)Subhalos.size(); i++)
+  { // new-born subhaloes (subhalo_unbind.cpp:505-510)
+    if (done[i]) continue;
+    b.subs.push_back(&Subhalos[i]);
+    lists.emplace_back();
+    done[i] = 1;
+  }
+#endif
+  close_nests(b, lists);
+  b.run(*this, HBTU_FLAG_TRUNCATE_SOURCE);
+  // subhaloes the reference's loops never unbind (members of a host whose nest is not reachable from a head) are
+  // still truncated by its last loop (subhalo_unbind.cpp:511-513)
+  for (size_t i = 0; i < Subhalos.size(); i++)
+    if (!done[i]) Subhalos[i].TruncateSource();
+}

@@ -96,3 +96,40 @@ def tree_potential(lib, prefix, params, epoch, src_pos_mass, tgt_pos, self_mass=
     if rc != 0:
         raise RuntimeError(f"{prefix}_tree_potential failed: {rc}")
     return out
+
+
+DROPIN_PATH = os.path.join(_HERE, "_ref", "libhbtdropin_v32.so")
+
+
+def have_dropin() -> bool:
+    return os.path.exists(DROPIN_PATH)
+
+
+def load_dropin():
+    """The reference harness linked against integration/subhalo_unbind_b200.o + libhbtunbind.so (GPU backend)."""
+    return _bind(C.CDLL(DROPIN_PATH), "hbtref")
+
+
+def refine_particles(lib, params, epoch, snap, host_halo_id, n_old, nhalos, mbound_in):
+    """``SubhaloSnapshot_t::RefineParticles()`` through the harness in ref_build/ref_capi.cpp."""
+    f = lib.hbtref_refine_particles
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(capi.Params), C.POINTER(capi.Epoch), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                  C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.POINTER(C.c_float),
+                  C.POINTER(capi.SubIO), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list) + snap.npart
+    io = snap.io.copy()
+    order_offset = np.zeros(snap.nsub + 1, np.int64)
+    order = np.full(max(cap, 1), -1, np.int32)
+    energy = np.zeros(max(cap, 1), np.float32)
+    pm = np.ascontiguousarray(snap.pos_mass, np.float32)
+    vv = np.ascontiguousarray(snap.vel, np.float32)
+    hh = np.ascontiguousarray(host_halo_id, np.int32)
+    mb = np.ascontiguousarray(mbound_in, np.float32)
+    P = capi._ptr
+    rc = f(C.byref(params), C.byref(epoch), snap.nsub, P(snap.part_offset, C.c_int64), P(pm, C.c_float), P(vv, C.c_float),
+           P(snap.nest_offset, C.c_int64), P(snap.nest_list, C.c_int32), P(hh, C.c_int32), n_old, nhalos, P(mb, C.c_float),
+           io.ctypes.data_as(C.POINTER(capi.SubIO)), cap, P(order_offset, C.c_int64), P(order, C.c_int32), P(energy, C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"hbtref_refine_particles failed: {rc}")
+    return Result(io, order_offset, order, energy)

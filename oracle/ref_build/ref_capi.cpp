@@ -280,4 +280,57 @@ int hbtref_tree_potential(const hbtu_params *params, const hbtu_epoch *epoch, in
   return HBTU_OK;
 }
 
+
+/* SubhaloSnapshot_t::RefineParticles() itself (src/subhalo_unbind.cpp:460-516) on an in-memory snapshot:
+ * host haloes with a central + heads + nests, field subhaloes (host_halo_id = -1) and new-born subhaloes
+ * (index >= n_old, unknown to the MemberTable).  The central of a host is its member with the largest mbound_in.
+ * The same translation unit is linked a second time against integration/subhalo_unbind_b200.o instead of the
+ * reference's subhalo_unbind.o (libhbtdropin_v32.so): same driver, two backends. */
+int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                            const float *pos_mass, const float *vel, const int64_t *nest_offset, const int32_t *nest_list,
+                            const int32_t *host_halo_id, int64_t n_old, int32_t nhalos, const float *mbound_in, hbtu_sub_io *io,
+                            int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  apply_params(params);
+  omp_set_max_active_levels(1);
+  SubhaloSnapshot_t snap;
+  set_epoch(snap, epoch);
+  std::vector<char> is_child(nsub, 0);
+  snap.Subhalos.resize(n_old);
+  auto fill = [&](Subhalo_t &sub, int64_t s) {
+    fill_subhalo(sub, s, part_offset, pos_mass, vel, io[s]);
+    sub.HostHaloId = host_halo_id[s];
+    sub.Mbound = mbound_in[s];
+    sub.Rank = 0;
+    if (nest_offset)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++) sub.NestedSubhalos.push_back(nest_list[k]);
+  };
+  for (int64_t s = 0; s < n_old; s++) fill(snap.Subhalos[s], s);
+  if (nest_offset)
+    for (int64_t k = 0; k < nest_offset[nsub]; k++) is_child[nest_list[k]] = 1;
+#pragma omp parallel
+  snap.MemberTable.Build(nhalos, snap.Subhalos, true); /* orphaned worksharing inside: must be called in parallel */
+  snap.MemberTable.SubGroupsOfHeads.assign(nhalos, std::vector<HBTInt>());
+  for (HBTInt h = 0; h < nhalos; h++)
+  {
+    auto &grp = snap.MemberTable.SubGroups[h];
+    for (HBTInt i = 0; i < grp.size(); i++)
+      if (!is_child[grp[i]]) snap.MemberTable.SubGroupsOfHeads[h].push_back(grp[i]); /* mass-sorted: central first */
+  }
+  for (int64_t s = n_old; s < nsub; s++)
+  {
+    snap.Subhalos.emplace_back();
+    fill(snap.Subhalos.back(), s);
+  }
+  snap.RefineParticles();
+  std::vector<int64_t> full(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    full[s] = snap.Subhalos[s].Particles.size();
+    read_subhalo(snap.Subhalos[s], io[s]);
+  }
+  return write_orders(snap.Subhalos, full, io, order_capacity, order_offset, order_out, energy_out);
+}
+
 } // extern "C"

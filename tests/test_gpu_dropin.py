@@ -1,0 +1,49 @@
+"""Drop-in test at the reference's own seam: the SAME harness (oracle/ref_build/ref_capi.cpp) drives
+``SubhaloSnapshot_t::RefineParticles()`` on an in-memory snapshot once with the reference's subhalo_unbind.o
+(libhbtref_v32.so, CPU) and once with integration/subhalo_unbind_b200.o + libhbtunbind.so (libhbtdropin_v32.so, GPU).
+Host haloes with central + heads + old nests, field subhaloes and new-born subhaloes are all present."""
+import numpy as np
+import pytest
+
+import cases
+from hbtplus_b200 import capi, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def snapshot_with_hosts(seed, periodic):
+    #        halo 0: 0 central, 1 & 2 heads, 3 in 1, 4 in 3 | halo 1: 5 central (old nest 7), 6 head | field 8, 9, 10 | new-born 11 (halo 1), 12 (field), 13 (halo 0)
+    sizes = [6000, 900, 400, 120, 45, 2500, 300, 150, 700, 30, 18, 260, 90, 55]
+    parent = [-1, -1, -1, 1, 3, -1, -1, 5, -1, -1, -1, -1, -1, -1]
+    host = [0, 0, 0, 0, 0, 1, 1, 1, -1, -1, -1, 1, -1, 0]
+    n_old = 11
+    snap = synth.make_snapshot(sizes, seed=seed, parent=parent, wrap=periodic, f_contam=0.3)
+    # satellites of a host sit inside its central (their unbound tails are what the central collects)
+    mb = np.asarray(sizes, np.float32)
+    return snap, np.asarray(host, np.int32), n_old, 2, mb
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_refine_particles_drop_in(periodic):
+    if not (po.have_ref() and po.have_dropin()):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    ref, drop = po.load_ref(), po.load_dropin()
+    ref.hbtref_set_num_threads(4)
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
+    e = capi.make_epoch(0.9, snapshot_index=15)
+    snap, host, n_old, nhalos, mb = snapshot_with_hosts(31 + periodic, periodic)
+    want = po.refine_particles(ref, p, e, snap, host, n_old, nhalos, mb)
+    got = po.refine_particles(drop, p, e, snap, host, n_old, nhalos, mb)
+    skip = cases.unbound_inputs(snap)
+    for f in ("nbound", "snapshot_index_of_death", "snapshot_index_of_sink", "sink_track_id", "nsource"):
+        assert np.array_equal(got.io[f], want.io[f]), f
+    assert np.allclose(got.io["mbound"][~skip], want.io["mbound"][~skip], rtol=1e-3)
+    for f in ("avg_pos", "avg_vel", "mostbound_pos", "mostbound_vel"):
+        assert np.allclose(got.io[f][~skip], want.io[f][~skip], rtol=2e-6, atol=1e-6), f
+    for s in range(snap.nsub):
+        assert cases.jaccard(got.bound(s), want.bound(s)) >= 0.999, s
+        assert sorted(got.particles(s).tolist()) == sorted(want.particles(s).tolist()), s
+    # the central of halo 0 was fed by its heads (1, 2) and, through them, by 3 and 4
+    assert want.io["nsource_full"][0] == 0 or want.io["nsource"][0] >= want.io["nbound"][0]
+    assert (want.io["nbound"][[0, 5]] > 1000).all()
