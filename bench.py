@@ -210,7 +210,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    sizes, parent = workload_sizes(args.particles, SEED + rank)
+    sizes, parent = workload_sizes(args.particles, SEED)  # same halo shape on every rank (weak scaling), own particle realisation
     snap = synth.make_snapshot_torch(sizes, device=dev, seed=SEED + rank, box_size=BOX, particle_mass=1e-6, parent=parent,
                                      centre=[BOX / 2] * 3, wrap=False, pin=True)
     torch.cuda.empty_cache()
@@ -278,6 +278,11 @@ def main():
         offs = np.concatenate([[0], np.cumsum([int(c) for c in counts])])
         table = sched.gather_records(res.io, offs[rank] + np.arange(snap.nsub), int(offs[-1]), device=dev)
         assert table is not None and len(table) == offs[-1]
+    per_rank = [sum(exec_ms) / args.steps]
+    if world > 1:
+        allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allt, torch.tensor([per_rank[0]], dtype=torch.float64, device=dev))
+        per_rank = [float(x) for x in allt]
     t_exec, t_e2e, t_walk = (float(x) for x in t_dev.cpu())
     n_all, nb_all, inter_all = (float(x) for x in tot.cpu())
     value = n_all * args.steps / t_exec
@@ -301,7 +306,7 @@ def main():
                        "l2_policy": "inputs (5.8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the library stream around hbtu_execute, max over ranks", "wall_ms_per_step": float(np.mean(wall)) * 1e3,
                        "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
-                       "rounds": int(st0.rounds), "pair_interactions_per_step": inter_all},
+                       "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
                     "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "api": "hbtu_unbind_batch from pinned host buffers"},
