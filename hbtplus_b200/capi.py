@@ -47,6 +47,7 @@ class Params(C.Structure):
         ("tree_min_num_of_cells", C.c_int64),
         ("G", C.c_double),
         ("direct_sum_max", C.c_int64),
+        ("shuffle_seed", C.c_int64),
     ]
 
 
@@ -144,7 +145,8 @@ def make_params(
     length_in_mpch: float = 1.0,
     vel_in_kms: float = 1.0,
     device: int = 0,
-    direct_sum_max: int = -1,
+    direct_sum_max: int = 0,
+    shuffle_seed: int = 0,
 ) -> Params:
     """Derive the path's 14 config fields exactly as ``Parameter_t::ParseConfigFile`` does
     (reference: src/config_parser.cpp:95-103), in HBTReal=float arithmetic."""
@@ -173,6 +175,7 @@ def make_params(
     # G=43.0071*(MassInMsunh/1e10)/VelInKmS/VelInKmS/LengthInMpch (double expr, stored to float)
     p.G = f32(43.0071 * (float(f(mass_in_msunh)) / 1e10) / float(f(vel_in_kms)) / float(f(vel_in_kms)) / float(f(length_in_mpch)))
     p.direct_sum_max = direct_sum_max
+    p.shuffle_seed = shuffle_seed
     return p
 
 

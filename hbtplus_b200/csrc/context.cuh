@@ -35,6 +35,7 @@ struct Context
   std::vector<SubHost> subs;
   std::vector<std::vector<int>> levels;
   std::vector<hbtu_sub_io> io_in;
+  std::vector<int> refine_list; // converged subhaloes of the current level that need RefineBindingEnergyOrder
 
   // persistent device buffers (grow-only)
   float4 *d_pos = nullptr, *d_vel = nullptr;

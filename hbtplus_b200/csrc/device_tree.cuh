@@ -39,6 +39,8 @@ struct Segment
   int tree_off; // offset in the S-concatenation
   int tgt_off;  // offset in the T-concatenation
   int warp_off; // first walk warp of this segment
+  int keep_order;    // sampled mode with Nlast > MaxSampleSize: the Elist order is the sample, do not re-order it
+  float mass_factor; // MassFactor of the sampled tree: Nlast/MaxSampleSize (src/subhalo_unbind.cpp:335-339), else 1
 };
 
 enum WalkMode
@@ -46,7 +48,8 @@ enum WalkMode
   kWalkUnbindFull = 0,   // E = 0.5|dv|^2 + pot            (src/subhalo_unbind.cpp:341-354)
   kWalkUnbindCorrect = 1, // E += v_old.dv + dK - pot_removed (src/subhalo_unbind.cpp:312-330)
   kWalkPotential = 2,    // out = pot                      (GravityTree_t::EvaluatePotential)
-  kWalkBindingEnergy = 3 // out = 0.5|dv|^2 + pot          (GravityTree_t::BindingEnergy)
+  kWalkBindingEnergy = 3, // out = 0.5|dv|^2 + pot          (GravityTree_t::BindingEnergy)
+  kWalkRefine = 4         // out_f = self-binding energy among the MaxSampleSize most bound (RefineBindingEnergyOrder, :234-262)
 };
 
 // Per-subhalo iteration state kept on the device for the whole batch.
@@ -62,6 +65,8 @@ struct SubState
   int iterations;
   int death, sink;
   int is_orphan;
+  int first_id; // input index of Particles[0] on entry (OldMostboundParticle, src/subhalo_unbind.cpp:298)
+  int shuffled; // the source was permuted for sampling
   int64_t sinktrack;
   float ref_pos[3], ref_vel[3];         // ComovingAveragePosition / PhysicalAverageVelocity (RefPos/RefVel)
   float old_ref_pos[3], old_ref_vel[3]; // OldRefPos / OldRefVel
@@ -133,6 +138,7 @@ struct WalkArgs
   float *E;              // per slot
   const SubState *subs;
   double *out;           // kWalkPotential / kWalkBindingEnergy
+  float *out_f;          // kWalkRefine: per target
   float ref_pos[3], ref_vel[3]; // kWalkBindingEnergy frame
   unsigned long long *counters; // [2]: accepted interactions, warp node visits (nullptr = do not count)
 };

@@ -147,6 +147,18 @@ HBT_HD int64_t cell_node_pos(const CellRange &c, const int *__restrict__ cellcou
 }
 HBT_HD int64_t cell_node_end(const CellRange &c, const int *__restrict__ cellcount_incl) { return (int64_t)c.r + 1 + cellcount_incl[c.r]; }
 
+// Counter-based sampling permutation (sampled mode): positions j of subhalo `sub` are ordered by this 40-bit key
+// (ties by j).  Replaces std::random_shuffle on libc rand() (src/subhalo_unbind.cpp:302); oracle/hbt_oracle.c
+// restates the same formula for its shuffle mode 1.
+HBT_HD uint64_t shuffle_key(uint64_t seed, uint64_t sub, uint64_t j)
+{
+  uint64_t z = seed ^ (0x9E3779B97F4A7C15ULL * (sub + 1)) ^ (j * 0xBF58476D1CE4E5B9ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return z >> 24;
+}
+
 // order-preserving float <-> uint32 maps (for atomic min/max and radix sorting by energy)
 HBT_HD uint32_t float_to_ordered(float f)
 {

@@ -82,15 +82,70 @@ __global__ void __launch_bounds__(kBlock) seg_copy_kernel(const CopyJob *__restr
 
 struct LevelInit
 {
-  int sub, n_src, activate;
+  int sub, n_src, activate, shuffled;
 };
-__global__ void level_init_kernel(const LevelInit *__restrict__ li, int n, SubState *__restrict__ subs)
+// runs BEFORE the sampling shuffle: Particles[0] on entry is the old most-bound particle (src/subhalo_unbind.cpp:298)
+__global__ void level_init_kernel(const LevelInit *__restrict__ li, int n, SubState *__restrict__ subs, const int *__restrict__ ids)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SubState &st = subs[li[i].sub];
   st.n_src = li[i].n_src;
+  st.first_id = li[i].n_src > 0 ? ids[st.slot_base] : -1;
+  st.shuffled = li[i].shuffled;
   if (li[i].activate) st.status = kActive;
+}
+
+// sampled mode: 64-bit keys (job << 40 | shuffle_key) over the concatenated sources that are larger than the sample
+struct ShuffleJob
+{
+  int64_t slot_base;
+  int sub, n;
+};
+__global__ void __launch_bounds__(kBlock) shuffle_keys_kernel(const ShuffleJob *__restrict__ jobs, const int64_t *__restrict__ job_off, int njobs,
+                                                               int64_t total, uint64_t seed, uint64_t *__restrict__ key, int *__restrict__ val)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = find_seg64(job_off, njobs, i);
+  int64_t o = i - job_off[j];
+  key[i] = ((uint64_t)j << 40) | shuffle_key(seed, (uint64_t)jobs[j].sub, (uint64_t)o);
+  val[i] = (int)i;
+}
+__global__ void __launch_bounds__(kBlock) shuffle_read_kernel(const ShuffleJob *__restrict__ jobs, const int64_t *__restrict__ job_off, int njobs,
+                                                               int64_t total, const int *__restrict__ order, const int *__restrict__ ids,
+                                                               int *__restrict__ tmp)
+{
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  int64_t src = order[p];
+  int j = find_seg64(job_off, njobs, src);
+  tmp[p] = ids[jobs[j].slot_base + (src - job_off[j])];
+}
+__global__ void __launch_bounds__(kBlock) shuffle_write_kernel(const ShuffleJob *__restrict__ jobs, const int64_t *__restrict__ job_off, int njobs,
+                                                                int64_t total, const int *__restrict__ tmp, int *__restrict__ ids)
+{
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  int j = find_seg64(job_off, njobs, p);
+  ids[jobs[j].slot_base + (p - job_off[j])] = tmp[p];
+}
+// disrupted + shuffled: the old most-bound particle is swapped back to the front (src/subhalo_unbind.cpp:367-374)
+__global__ void __launch_bounds__(kBlock) restore_front_kernel(const CopyJob *__restrict__ jobs, const int64_t *__restrict__ job_off, int njobs,
+                                                                int64_t total, const int *__restrict__ job_sub, const SubState *__restrict__ subs,
+                                                                const int *__restrict__ ids_orig, int *__restrict__ ids)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = find_seg64(job_off, njobs, i);
+  const SubState &st = subs[job_sub[j]];
+  if (!st.shuffled || st.status != kDone || st.nbound != 1) return;
+  int64_t slot = jobs[j].dst + (i - job_off[j]);
+  if (ids_orig[slot] == st.first_id && slot != st.slot_base)
+  {
+    ids[st.slot_base] = st.first_id;
+    ids[slot] = ids_orig[st.slot_base];
+  }
 }
 
 // subhaloes whose source is too small to iterate (src/subhalo_unbind.cpp:269-293 and the disruption
@@ -118,7 +173,7 @@ __global__ void trivial_kernel(const int *__restrict__ list, int n, SubState *__
   { // disruption without iterating
     st.nbound = 1;
     for (int j = 0; j < 3; j++) { st.ref_pos[j] = st.mb_pos[j]; st.ref_vel[j] = st.mb_vel[j]; }
-    st.mbound = pos[ids[st.slot_base]].w;
+    st.mbound = pos[ids[st.slot_base]].w; // no shuffle below MinNumPartOfSub <= MaxSampleSize... see classify
     st.spec_pot = st.spec_kin = 0.f;
     st.am[0] = st.am[1] = st.am[2] = 0.f;
   }
@@ -138,7 +193,9 @@ __global__ void __launch_bounds__(kBlock) gather_src_kernel(const Segment *__res
   int a = find_seg(tree_off, nseg, k);
   const Segment sg = segs[a];
   int64_t slot = sg.slot_base + sg.tree_first + (k - sg.tree_off);
-  tpos[k] = pos[ids[slot]];
+  float4 p = pos[ids[slot]];
+  p.w = __fmul_rn(p.w, sg.mass_factor); // MassFactor of a sampled tree (src/subhalo_unbind.cpp:96-99), 1 otherwise
+  tpos[k] = p;
   ts_seg[k] = a;
 }
 
@@ -160,7 +217,7 @@ __global__ void __launch_bounds__(kBlock) sorted_ids_write_kernel(const Segment 
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   const Segment sg = segs[ts_seg[k]];
-  if (sg.mode == kWalkUnbindFull) ids[sg.slot_base + sg.tree_first + (k - sg.tree_off)] = tmp[k];
+  if (sg.mode == kWalkUnbindFull && !sg.keep_order) ids[sg.slot_base + sg.tree_first + (k - sg.tree_off)] = tmp[k];
 }
 
 __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_off, int nseg, int T,
@@ -175,12 +232,14 @@ __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restri
   int j = t - sg.tgt_off;
   int64_t slot = sg.slot_base + j;
   float4 p;
-  if (sg.mode == kWalkUnbindFull)
+  if (sg.mode == kWalkUnbindFull && !sg.keep_order)
     p = spos[sg.tree_off + j]; // target j is sorted source j; w = its own mass (self term)
   else
   {
     p = pos[ids[slot]];
-    p.w = 0.f; // not in the tree: no self term (src/subhalo_unbind.cpp:327)
+    // self term only for targets that are tree sources, with the tree's (scaled) mass (src/subhalo_unbind.cpp:345-349);
+    // correction targets are never in the tree (:327)
+    p.w = (sg.mode != kWalkUnbindCorrect && j < sg.tree_n) ? __fmul_rn(p.w, sg.mass_factor) : 0.f;
   }
   tgt_pm[t] = p;
   tgt_slot[t] = slot;
@@ -192,7 +251,7 @@ __global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubS
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nseg) return;
   SubState &st = subs[segs[a].sub];
-  st.iterations++;
+  if (segs[a].mode != kWalkRefine) st.iterations++;
   st.count_bound = 0;
   for (int j = 0; j < 8; j++) st.sums[j] = 0.0;
   if (segs[a].mode == kWalkUnbindCorrect)
@@ -230,8 +289,7 @@ __global__ void __launch_bounds__(kBlock) count_bound_kernel(const Segment *__re
 }
 
 // PartitionBindingEnergy result -> disruption / CorrectionLoop / convergence (src/subhalo_unbind.cpp:357-403)
-__global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids_orig,
-                              const float4 *__restrict__ pos, DevConfig cfg)
+__global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const float4 *__restrict__ pos, DevConfig cfg)
 {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nseg) return;
@@ -245,7 +303,7 @@ __global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubSta
     st.nlast = 1;
     if (st.death == -1) st.death = cfg.snapshot_index;
     for (int j = 0; j < 3; j++) { st.ref_pos[j] = st.mb_pos[j]; st.ref_vel[j] = st.mb_vel[j]; }
-    st.mbound = pos[ids_orig[st.slot_base]].w; // Particles[0] is the old most-bound particle (exact mode: untouched order)
+    st.mbound = pos[st.first_id].w; // Particles[0] after the old most-bound particle is swapped back (:367-377)
     st.spec_pot = st.spec_kin = 0.f;
     st.am[0] = st.am[1] = st.am[2] = 0.f;
     st.status = kDisrupted;
@@ -266,11 +324,50 @@ __global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubSta
   }
 }
 
+// Sampled mode, full-evaluation rounds with Nlast > MaxSampleSize: the order of the bound part after the
+// partition selects the next sample, so the reference's hole-based Hoare partition (src/subhalo_unbind.cpp:21-58)
+// is reproduced exactly.  With Nb bound elements, f_1<f_2<.. the unbound elements at indices [1,Nb) and
+// b_1>b_2>.. the bound elements at indices >= Nb:  new[0]=old[b_1], new[f_k]=old[b_(k+1)], old[0] (if bound)
+// ends at f_last; bound elements already in [1,Nb) stay.  hoare_flags marks the two misplaced sets, two scans rank
+// them, hoare_fpos inverts the front ranks.
+__global__ void __launch_bounds__(kBlock) hoare_flags_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
+                                                              const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
+                                                              const SubState *__restrict__ subs, int *__restrict__ uflag, int *__restrict__ bflag)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const Segment sg = segs[tgt_seg[t]];
+  int u = 0, b = 0;
+  if (sg.keep_order && sg.mode == kWalkUnbindFull)
+  {
+    const SubState &st = subs[sg.sub];
+    if (st.status == kActive)
+    {
+      int j = t - sg.tgt_off;
+      bool bound = E[tgt_slot[t]] < 0.f;
+      u = (!bound && j >= 1 && j < st.nbound);
+      b = (bound && j >= st.nbound);
+    }
+  }
+  uflag[t] = u;
+  bflag[t] = b;
+}
+__global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+                                                             const int *__restrict__ uflag, const int *__restrict__ uscan, int *__restrict__ fpos)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T || !uflag[t]) return;
+  const Segment sg = segs[tgt_seg[t]];
+  int before = sg.tgt_off > 0 ? uscan[sg.tgt_off - 1] : 0;
+  fpos[sg.tgt_off + (uscan[t] - before) - 1] = t - sg.tgt_off; // k-th misplaced unbound element of the front
+}
+
 // One key per target: (segment, bound|unbound) major, then E (where the reference sorts) or the current
 // position (where it does not): a single radix sort = partition + tail sort + final bound sort.
 __global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
                                                             const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
-                                                            const SubState *__restrict__ subs, uint64_t *__restrict__ key, int *__restrict__ val)
+                                                            const SubState *__restrict__ subs, const int *__restrict__ bscan,
+                                                            const int *__restrict__ fpos, uint64_t *__restrict__ key, int *__restrict__ val)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -282,7 +379,29 @@ __global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__rest
   uint64_t hi, low;
   if (status == kDisrupted) { hi = 2ull * a; low = j; }
   else if (!(e < 0.f)) { hi = 2ull * a + 1; low = float_to_ordered(e); }
-  else { hi = 2ull * a; low = (status == kConverged) ? float_to_ordered(e) : j; }
+  else
+  {
+    hi = 2ull * a;
+    if (status == kConverged)
+      low = float_to_ordered(e);
+    else if (bscan && sg.keep_order && sg.mode == kWalkUnbindFull)
+    { // Hoare destination of a bound element
+      const int nb = subs[sg.sub].nbound;
+      const int b0 = sg.tgt_off > 0 ? bscan[sg.tgt_off - 1] : 0;
+      const int mis = bscan[sg.tgt_off + sg.tgt_n - 1] - b0; // misplaced bound elements (= M)
+      if ((int)j >= nb)
+      {
+        int k = mis - (bscan[t] - b0 - 1); // 1 = last misplaced bound element of the segment
+        low = (k == 1) ? 0u : (uint32_t)fpos[sg.tgt_off + k - 2];
+      }
+      else if (j == 0)
+        low = mis >= 1 ? (uint32_t)fpos[sg.tgt_off + mis - 1] : 0u;
+      else
+        low = j;
+    }
+    else
+      low = j;
+  }
   key[t] = (hi << 32) | low;
   val[t] = t;
 }
@@ -574,6 +693,7 @@ static void run_round(Context &c, std::vector<int> &active)
   // walk warps per class of targets-per-lane (index 0: T=1, 1: T=2, 2: T=4); a segment belongs to one class
   std::vector<int> warp_off[3] = {std::vector<int>(nseg + 1), std::vector<int>(nseg + 1), std::vector<int>(nseg + 1)};
   int64_t S = 0, T = 0, W[3] = {0, 0, 0};
+  bool any_hoare = false;
   for (int a = 0; a < nseg; a++)
   {
     SubHost &h = c.subs[active[a]];
@@ -590,6 +710,18 @@ static void run_round(Context &c, std::vector<int> &active)
     {
       sg.tree_first = 0;
       sg.tree_n = h.nbound;
+    }
+    sg.keep_order = 0;
+    sg.mass_factor = 1.f;
+    if (c.cfg.max_sample > 0 && h.nbound > c.cfg.max_sample)
+    { // sampled potential: tree of the first MaxSampleSize entries, masses scaled by Nlast/MaxSampleSize (:333-339)
+      sg.keep_order = 1;
+      if (!h.correction)
+      {
+        sg.tree_n = (int)c.cfg.max_sample;
+        sg.mass_factor = (float)h.nbound / (float)c.cfg.max_sample;
+        any_hoare = true;
+      }
     }
     sg.tgt_n = h.nbound;
     sg.tree_off = (int)S;
@@ -671,12 +803,29 @@ static void run_round(Context &c, std::vector<int> &active)
 
   count_bound_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);
   HBT_CHECK_LAUNCH();
-  state1_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids_orig, c.d_pos, c.cfg);
+  state1_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_pos, c.cfg);
   HBT_CHECK_LAUNCH();
   // partition + E-sorts in one radix sort
   uint64_t *key_a = ar.alloc<uint64_t>(T), *key_b = ar.alloc<uint64_t>(T);
   int *val_a = ar.alloc<int>(T), *val_b = ar.alloc<int>(T);
-  sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, key_a, val_a);
+  int *bscan = nullptr, *fpos = nullptr;
+  if (any_hoare)
+  {
+    int *uflag = ar.alloc<int>(T), *bflag = ar.alloc<int>(T), *uscan = ar.alloc<int>(T);
+    bscan = ar.alloc<int>(T);
+    fpos = ar.alloc<int>(T);
+    hoare_flags_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, uflag, bflag);
+    HBT_CHECK_LAUNCH();
+    size_t sb = 0;
+    HBT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, sb, uflag, uscan, (int)T, st));
+    void *stmp = ar.alloc<char>((int64_t)sb);
+    HBT_CUDA(cub::DeviceScan::InclusiveSum(stmp, sb, uflag, uscan, (int)T, st));
+    HBT_CUDA(cub::DeviceScan::InclusiveSum(stmp, sb, bflag, bscan, (int)T, st));
+    hoare_fpos_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, uflag, uscan, fpos);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches += 6;
+  }
+  sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, bscan, fpos, key_a, val_a);
   HBT_CHECK_LAUNCH();
   c.ls.launches += 3;
   {
@@ -736,9 +885,127 @@ static void run_round(Context &c, std::vector<int> &active)
     {
       h.done = true;
       h.disrupted = res[a].status == kDisrupted;
+      if (res[a].status == kConverged && c.params.refine_mostbound_particle && c.cfg.max_sample > 0 && h.nbound > c.cfg.max_sample)
+        c.refine_list.push_back(active[a]);
     }
   }
   active.swap(next);
+}
+
+__global__ void refine_keys_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T, const float *__restrict__ einner,
+                                   uint64_t *__restrict__ key, int *__restrict__ val)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  key[t] = ((uint64_t)tgt_seg[t] << 32) | float_to_ordered(einner[t]);
+  val[t] = t;
+}
+__global__ void refine_mostbound_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
+                                        const float4 *__restrict__ pos, const float4 *__restrict__ vel)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nseg) return;
+  SubState &st = subs[segs[a].sub];
+  int id0 = ids[st.slot_base];
+  float4 x0 = pos[id0], v0 = vel[id0];
+  st.mb_pos[0] = x0.x; st.mb_pos[1] = x0.y; st.mb_pos[2] = x0.z;
+  st.mb_vel[0] = v0.x; st.mb_vel[1] = v0.y; st.mb_vel[2] = v0.z;
+}
+
+// RefineBindingEnergyOrder (src/subhalo_unbind.cpp:234-262) for every subhalo of the level that converged with
+// Nbound > MaxSampleSize: tree of its MaxSampleSize most-bound particles (unscaled masses), their binding energies among
+// themselves in the final frame, and the first MaxSampleSize Elist entries (pid AND the original E) re-ordered by that.
+static void run_refine(Context &c, const std::vector<int> &list)
+{
+  const int nseg = (int)list.size(), M = (int)c.cfg.max_sample;
+  std::vector<Segment> segs(nseg);
+  std::vector<int> off(nseg + 1), woff(nseg + 1);
+  for (int a = 0; a < nseg; a++)
+  {
+    Segment &sg = segs[a];
+    std::memset(&sg, 0, sizeof(sg));
+    sg.slot_base = c.subs[list[a]].slot_base;
+    sg.sub = list[a];
+    sg.mode = kWalkRefine;
+    sg.tree_n = sg.tgt_n = M;
+    sg.tree_off = sg.tgt_off = a * M;
+    sg.warp_off = a * ((M + 31) / 32);
+    sg.keep_order = 1;
+    sg.mass_factor = 1.f;
+    off[a] = a * M;
+    woff[a] = sg.warp_off;
+  }
+  const int64_t S = (int64_t)nseg * M;
+  if (S > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "refine round larger than 2^30 particles"};
+  off[nseg] = (int)S;
+  woff[nseg] = nseg * ((M + 31) / 32);
+  Arena &ar = c.arena;
+  ar.reset();
+  ar.reserve(tree_arena_bytes(S, nseg) + S * 96 + (int64_t)nseg * 128);
+  cudaStream_t st = c.stream;
+  Segment *d_segs = upload(ar, segs, st);
+  int *d_off = upload(ar, off, st), *d_woff = upload(ar, woff, st);
+  TreeArrays tr;
+  tr.S = (int)S;
+  tr.nseg = nseg;
+  tr.tree_off = d_off;
+  tr.tpos = ar.alloc<float4>(S);
+  tr.ts_seg = ar.alloc<int>(S);
+  tr.bbox = ar.alloc<uint32_t>(6 * (int64_t)nseg);
+  gather_src_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, d_off, nseg, (int)S, c.d_ids, c.d_pos, tr.tpos, tr.ts_seg);
+  HBT_CHECK_LAUNCH();
+  launch_init_bbox(tr.bbox, nseg, st, c.ls);
+  launch_bbox(tr.tpos, tr.ts_seg, (int)S, tr.bbox, st, c.ls);
+  build_trees(tr, ar, c.cfg, st, c.ls);
+  float4 *tgt_pm = ar.alloc<float4>(S);
+  int64_t *tgt_slot = ar.alloc<int64_t>(S);
+  int *tgt_seg = ar.alloc<int>(S);
+  targets_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, d_off, nseg, (int)S, tr.spos, c.d_ids, c.d_pos, tgt_pm, tgt_slot, tgt_seg);
+  HBT_CHECK_LAUNCH();
+  float *einner = ar.alloc<float>(S);
+  WalkArgs wa{};
+  wa.node_xm = tr.node_xm;
+  wa.node_aux = tr.node_aux;
+  wa.cellcount = tr.cellcount;
+  wa.tree_off = d_off;
+  wa.segs = d_segs;
+  wa.warp_off = d_woff;
+  wa.nseg = nseg;
+  wa.nwarps = woff[nseg];
+  wa.targets_per_lane = 1;
+  wa.tgt_pm = tgt_pm;
+  wa.tgt_slot = tgt_slot;
+  wa.ids = c.d_ids;
+  wa.vel = c.d_vel;
+  wa.E = c.d_E;
+  wa.subs = c.d_subs;
+  wa.out_f = einner;
+  wa.counters = c.count_interactions ? c.d_counters : nullptr;
+  launch_walk(wa, c.cfg, st, c.ls);
+  uint64_t *ka = ar.alloc<uint64_t>(S), *kb = ar.alloc<uint64_t>(S);
+  int *va = ar.alloc<int>(S), *vb = ar.alloc<int>(S);
+  refine_keys_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tgt_seg, (int)S, einner, ka, va);
+  HBT_CHECK_LAUNCH();
+  int bits = 33;
+  while ((1ll << (bits - 32)) < nseg) bits++;
+  cub::DoubleBuffer<uint64_t> dk(ka, kb);
+  cub::DoubleBuffer<int> dv(va, vb);
+  size_t tb = 0;
+  HBT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)S, 0, bits, st));
+  void *tmp = ar.alloc<char>((int64_t)tb);
+  HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)S, 0, bits, st));
+  int *tmp_id = ar.alloc<int>(S);
+  float *tmp_E = ar.alloc<float>(S);
+  permute_read_kernel<<<grid_for(S), kBlock, 0, st>>>(dv.Current(), tgt_slot, (int)S, c.d_ids, c.d_E, tmp_id, tmp_E);
+  HBT_CHECK_LAUNCH();
+  permute_write_kernel<<<grid_for(S), kBlock, 0, st>>>(tgt_slot, (int)S, tmp_id, tmp_E, c.d_ids, c.d_E);
+  HBT_CHECK_LAUNCH();
+  refine_mostbound_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches += 8 + (bits + 7) / 8;
+  c.stats.tree_builds += nseg;
+  c.stats.walk_targets += S;
+  HBT_CUDA(cudaStreamSynchronize(st));
 }
 
 void execute_batch(Context &c)
@@ -750,9 +1017,6 @@ void execute_batch(Context &c)
   std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms));
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
   if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
-  if (c.cfg.max_sample > 0)
-    for (int s = 0; s < nsub; s++)
-      if (c.subs[s].cap > c.cfg.max_sample) throw CudaError{HBTU_ERR_UNSUPPORTED, "MaxSampleSizeOfPotentialEstimate>0 with a larger source is not built yet"};
 
   // (re)initialise per-subhalo state from the staged inputs
   std::vector<SubState> init(nsub);
@@ -803,6 +1067,7 @@ void execute_batch(Context &c)
   for (int level = c.max_depth; level >= 0; level--)
   {
     const std::vector<int> &lv = c.levels[level];
+    const int64_t M = c.cfg.max_sample;
     // 1. feed children's unbound tails into this level's sources (src/subhalo_unbind.cpp:437-443)
     {
       std::vector<CopyJob> jobs;
@@ -825,23 +1090,18 @@ void execute_batch(Context &c)
         h.n_src = (int)n;
       }
       run_seg_copy(c, jobs, job_off, c.d_ids, c.d_ids);
-      // snapshot of the input order (needed for disrupted subhaloes and orphans)
-      std::vector<CopyJob> snap;
-      std::vector<int64_t> snap_off{0};
-      for (int s : lv)
-        if (c.subs[s].n_src > 0)
-        {
-          snap.push_back(CopyJob{c.subs[s].slot_base, c.subs[s].slot_base});
-          snap_off.push_back(snap_off.back() + c.subs[s].n_src);
-        }
-      run_seg_copy(c, snap, snap_off, c.d_ids, c.d_ids_orig);
     }
     // 2. classify
     std::vector<int> active, trivial;
-    for (int s : lv)
+    std::vector<ShuffleJob> shuf;
+    std::vector<int64_t> shuf_off{0};
+    std::vector<LevelInit> li(lv.size());
+    for (size_t i = 0; i < lv.size(); i++)
     {
+      int s = lv[i];
       SubHost &h = c.subs[s];
       int nu = h.is_orphan ? h.n_own : h.n_src;
+      bool shuffled = false;
       if (nu < 2 || nu < c.cfg.min_num_part)
       {
         trivial.push_back(s);
@@ -853,19 +1113,63 @@ void execute_batch(Context &c)
       {
         active.push_back(s);
         h.nbound = h.nlast = nu;
+        if (M > 0 && nu > M)
+        { // random_shuffle of the source before sampling (src/subhalo_unbind.cpp:302)
+          shuffled = true;
+          shuf.push_back(ShuffleJob{h.slot_base, s, nu});
+          shuf_off.push_back(shuf_off.back() + nu);
+        }
       }
+      li[i] = LevelInit{s, h.n_src, h.done ? 0 : 1, shuffled ? 1 : 0};
     }
-    { // n_src and the active flag on the device
-      std::vector<LevelInit> li(lv.size());
-      for (size_t i = 0; i < lv.size(); i++) li[i] = LevelInit{lv[i], c.subs[lv[i]].n_src, c.subs[lv[i]].done ? 0 : 1};
+    { // n_src, the entry value of Particles[0] and the active flag on the device
       LevelInit *d_li = nullptr;
       HBT_CUDA(cudaMalloc(&d_li, sizeof(LevelInit) * li.size()));
       HBT_CUDA(cudaMemcpyAsync(d_li, li.data(), sizeof(LevelInit) * li.size(), cudaMemcpyHostToDevice, st));
-      level_init_kernel<<<grid_for((int64_t)li.size()), kBlock, 0, st>>>(d_li, (int)li.size(), c.d_subs);
+      level_init_kernel<<<grid_for((int64_t)li.size()), kBlock, 0, st>>>(d_li, (int)li.size(), c.d_subs, c.d_ids);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
       HBT_CUDA(cudaStreamSynchronize(st));
       cudaFree(d_li);
+    }
+    if (!shuf.empty())
+    {
+      const int64_t total = shuf_off.back();
+      if (total > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "shuffle larger than 2^30 particles"};
+      Arena &ar = c.arena;
+      ar.reset();
+      ar.reserve(total * 40 + (int64_t)shuf.size() * 64 + (64 << 20));
+      ShuffleJob *d_jobs = upload(ar, shuf, st);
+      int64_t *d_off = upload(ar, shuf_off, st);
+      uint64_t *ka = ar.alloc<uint64_t>(total), *kb = ar.alloc<uint64_t>(total);
+      int *va = ar.alloc<int>(total), *vb = ar.alloc<int>(total), *tmp = ar.alloc<int>(total);
+      shuffle_keys_kernel<<<grid_for(total), kBlock, 0, st>>>(d_jobs, d_off, (int)shuf.size(), total, (uint64_t)c.params.shuffle_seed, ka, va);
+      HBT_CHECK_LAUNCH();
+      int bits = 41;
+      while ((1ll << (bits - 40)) < (int64_t)shuf.size()) bits++;
+      cub::DoubleBuffer<uint64_t> dk(ka, kb);
+      cub::DoubleBuffer<int> dv(va, vb);
+      size_t tb = 0;
+      HBT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)total, 0, bits, st));
+      void *tmpb = ar.alloc<char>((int64_t)tb);
+      HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmpb, tb, dk, dv, (int)total, 0, bits, st));
+      shuffle_read_kernel<<<grid_for(total), kBlock, 0, st>>>(d_jobs, d_off, (int)shuf.size(), total, dv.Current(), c.d_ids, tmp);
+      HBT_CHECK_LAUNCH();
+      shuffle_write_kernel<<<grid_for(total), kBlock, 0, st>>>(d_jobs, d_off, (int)shuf.size(), total, tmp, c.d_ids);
+      HBT_CHECK_LAUNCH();
+      c.ls.launches += 4 + (bits + 7) / 8;
+      HBT_CUDA(cudaStreamSynchronize(st));
+    }
+    { // snapshot of the (shuffled) input order: what Particles holds when Unbind does not reorder it
+      std::vector<CopyJob> snap;
+      std::vector<int64_t> snap_off{0};
+      for (int s : lv)
+        if (c.subs[s].n_src > 0)
+        {
+          snap.push_back(CopyJob{c.subs[s].slot_base, c.subs[s].slot_base});
+          snap_off.push_back(snap_off.back() + c.subs[s].n_src);
+        }
+      run_seg_copy(c, snap, snap_off, c.d_ids, c.d_ids_orig);
     }
     if (!trivial.empty())
     {
@@ -878,13 +1182,16 @@ void execute_batch(Context &c)
       HBT_CUDA(cudaStreamSynchronize(st));
       cudaFree(d_list);
     }
-    // 3. iterate
+    // 3. iterate; then re-rank the most-bound sample of converged sampled subhaloes (RefineBindingEnergyOrder)
+    c.refine_list.clear();
     while (!active.empty()) run_round(c, active);
+    if (!c.refine_list.empty()) run_refine(c, c.refine_list);
     // 4. restore the input order where the reference leaves Particles untouched: disrupted subhaloes
     //    (no permutation copy, :361-379) and orphans (the unbound backup is discarded, :444-446)
     {
       std::vector<CopyJob> jobs;
       std::vector<int64_t> job_off{0};
+      std::vector<int> job_sub;
       for (int s : lv)
       {
         SubHost &h = c.subs[s];
@@ -892,9 +1199,23 @@ void execute_batch(Context &c)
         {
           jobs.push_back(CopyJob{h.slot_base, h.slot_base});
           job_off.push_back(job_off.back() + h.n_src);
+          job_sub.push_back(s);
         }
       }
       run_seg_copy(c, jobs, job_off, c.d_ids_orig, c.d_ids);
+      if (M > 0 && !jobs.empty())
+      {
+        Arena &ar = c.arena;
+        ar.reset();
+        CopyJob *d_jobs = upload(ar, jobs, st);
+        int64_t *d_off = upload(ar, job_off, st);
+        int *d_sub = upload(ar, job_sub, st);
+        restore_front_kernel<<<grid_for(job_off.back()), kBlock, 0, st>>>(d_jobs, d_off, (int)jobs.size(), job_off.back(), d_sub, c.d_subs,
+                                                                           c.d_ids_orig, c.d_ids);
+        HBT_CHECK_LAUNCH();
+        c.ls.launches++;
+        HBT_CUDA(cudaStreamSynchronize(st));
+      }
     }
   }
   if (c.count_interactions)

@@ -242,6 +242,13 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
     const SubState &st = a.subs[sg.sub];
     float4 v4 = a.vel[a.ids[slot]];
     const float v[3] = {v4.x, v4.y, v4.z};
+    if (MODE == kWalkRefine)
+    { // Einner = BindingEnergy among the most-bound sample, current frame (src/subhalo_unbind.cpp:247)
+      float dv[3];
+      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
+      a.out_f[t] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+      continue;
+    }
     if (MODE == kWalkUnbindFull)
     { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
       float dv[3];

@@ -66,8 +66,11 @@ typedef struct hbtu_params
   double tree_alloc_factor;            /* TreeAllocFactor   (accepted; device tree self-sizes) */
   int64_t tree_min_num_of_cells;       /* TreeMinNumOfCells (accepted; unused)              */
   double G;                            /* PhysicalConst::G                                  */
-  int64_t direct_sum_max;              /* subhaloes with <= this many source particles use the
-                                          fused direct-sum kernel; <0 = library default, 0 = tree only */
+  int64_t direct_sum_max;              /* reserved: a direct-sum path cannot meet the parity gates against the
+                                          reference's monopole tree and is not enabled */
+  int64_t shuffle_seed;                /* sampled mode only (max_sample_size > 0): seed of the counter-based permutation
+                                          that replaces the reference's random_shuffle/rand() (subhalo_unbind.cpp:302),
+                                          whose stream depends on libc state and OpenMP scheduling */
 } hbtu_params;
 
 /* What Unbind reads from `epoch` (src/snapshot.h:17-39, src/snapshot_number.h). */

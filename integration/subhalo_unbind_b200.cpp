@@ -55,6 +55,8 @@ void fill_params(hbtu_params &p)
   p.tree_min_num_of_cells = HBTConfig.TreeMinNumOfCells;
   p.G = PhysicalConst::G;
   p.direct_sum_max = 0;
+  const char *seed = getenv("HBT_UNBIND_SHUFFLE_SEED");
+  p.shuffle_seed = seed ? atoll(seed) : 20240001;
 }
 
 hbtu_ctx *context()

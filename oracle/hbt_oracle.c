@@ -46,6 +46,7 @@ typedef struct
       TreeNodeResolutionHalf, G;
   HBTReal ScaleFactor, Hz;
   int SnapshotIndex;
+  int64_t ShuffleSeed;
 } Config;
 
 static void config_from(Config *c, const hbtu_params *p, const hbtu_epoch *e)
@@ -66,6 +67,7 @@ static void config_from(Config *c, const hbtu_params *p, const hbtu_epoch *e)
   c->ScaleFactor = (HBTReal)e->scale_factor;
   c->Hz = (HBTReal)e->hz;
   c->SnapshotIndex = e->snapshot_index;
+  c->ShuffleSeed = p->shuffle_seed;
 }
 
 /* NEAREST(), src/config_parser.h:142 - one instance per operand width */
@@ -367,9 +369,35 @@ typedef struct
   float *Energies;
   int64_t nE;
   int iterations;
+  int64_t index; /* batch-local subhalo index */
   const int32_t *nest;
   int64_t nnest;
 } Sub;
+
+/* Sampling permutation.  mode 0: libstdc++ random_shuffle on libc rand(), bit-identical to the reference when both run
+ * single-threaded from the same srand() state (pins this restatement to the reference).  mode 1: the counter-based
+ * permutation the CUDA path uses (sort positions by shuffle_key; same formula as hbtplus_b200/csrc/tree_core.cuh),
+ * because the reference's own stream depends on libc state and OpenMP scheduling and cannot be shared with a GPU. */
+static int g_shuffle_mode = 0;
+static uint64_t shuffle_key(uint64_t seed, uint64_t sub, uint64_t j)
+{
+  uint64_t z = seed ^ (0x9E3779B97F4A7C15ULL * (sub + 1)) ^ (j * 0xBF58476D1CE4E5B9ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return z >> 24; /* 40 bits: shares a 64-bit radix key with the segment index on the device */
+}
+typedef struct
+{
+  uint64_t key;
+  int64_t j;
+} ShuffleRec;
+static int comp_shuffle(const void *a, const void *b)
+{
+  const ShuffleRec *x = a, *y = b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->j < y->j ? -1 : (x->j > y->j);
+}
 
 static int64_t g_interactions; /* accepted pair interactions of the last call (roofline numerator) */
 static int64_t g_opened;
@@ -578,15 +606,34 @@ static void unbind(const Config *c, Sub *s)
   s->Nbound = (HBTInt)s->n;
   if (MaxSampleSize > 0 && s->Nbound > MaxSampleSize)
   { /* std::random_shuffle (libstdc++ stl_algo.h: j = rand() % (i+1)), src/subhalo_unbind.cpp:302 */
-    for (int64_t i = 1; i < s->n; i++)
+    if (g_shuffle_mode == 0)
     {
-      int64_t j = rand() % (i + 1);
-      if (i != j)
+      for (int64_t i = 1; i < s->n; i++)
       {
-        Particle tmp = s->P[i];
-        s->P[i] = s->P[j];
-        s->P[j] = tmp;
+        int64_t j = rand() % (i + 1);
+        if (i != j)
+        {
+          Particle tmp = s->P[i];
+          s->P[i] = s->P[j];
+          s->P[j] = tmp;
+        }
       }
+    }
+    else
+    {
+      ShuffleRec *rec = malloc(sizeof(ShuffleRec) * s->n);
+      Particle *np = malloc(sizeof(Particle) * s->n);
+      for (int64_t j = 0; j < s->n; j++)
+      {
+        rec[j].key = shuffle_key((uint64_t)c->ShuffleSeed, (uint64_t)s->index, (uint64_t)j);
+        rec[j].j = j;
+      }
+      qsort(rec, s->n, sizeof(ShuffleRec), comp_shuffle);
+      for (int64_t j = 0; j < s->n; j++) np[j] = s->P[rec[j].j];
+      free(s->P);
+      free(rec);
+      s->P = np;
+      s->cap = s->n;
     }
   }
   HBTInt Nlast = 0;
@@ -784,6 +831,7 @@ void hbto_set_num_threads(int n)
 int hbto_get_max_threads(void) { return omp_get_max_threads(); }
 int64_t hbto_last_interactions(void) { return g_interactions; }
 int64_t hbto_last_opened(void) { return g_opened; }
+void hbto_set_shuffle_mode(int mode) { g_shuffle_mode = mode; }
 void hbto_seed(unsigned s)
 {
   srand(s);
@@ -805,6 +853,7 @@ int hbto_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_
   {
     Sub *sub = &subs[s];
     int64_t b = part_offset[s], n = part_offset[s + 1] - b;
+    sub->index = s;
     sub->n = n;
     sub->cap = n > 0 ? n : 1;
     sub->P = malloc(sizeof(Particle) * sub->cap);

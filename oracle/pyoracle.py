@@ -39,7 +39,9 @@ def have_ref() -> bool:
 
 
 def load_ref():
-    return _bind(C.CDLL(REF_PATH), "hbtref")
+    lib = _bind(C.CDLL(REF_PATH), "hbtref")
+    lib.hbtref_seed.argtypes = [C.c_uint]
+    return lib
 
 
 def load_oracle():
@@ -48,6 +50,8 @@ def load_oracle():
                                      C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.hbto_walk_counts.restype = C.c_int
     lib.hbto_last_interactions.restype = C.c_int64
+    lib.hbto_set_shuffle_mode.argtypes = [C.c_int]
+    lib.hbto_seed.argtypes = [C.c_uint]
     return lib
 
 

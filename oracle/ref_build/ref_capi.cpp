@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <stdexcept>
 
 #include "datatypes.h"
 #include "config_parser.h"
@@ -323,7 +324,15 @@ int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, 
     snap.Subhalos.emplace_back();
     fill(snap.Subhalos.back(), s);
   }
-  snap.RefineParticles();
+  try
+  {
+    snap.RefineParticles();
+  }
+  catch (const std::exception &ex)
+  { /* only the drop-in build can throw (the reference path cannot fail) */
+    fprintf(stderr, "RefineParticles threw: %s\n", ex.what());
+    return HBTU_ERR_CUDA;
+  }
   std::vector<int64_t> full(nsub);
   for (int64_t s = 0; s < nsub; s++)
   {

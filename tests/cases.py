@@ -43,7 +43,18 @@ def case_massvar():
     return p, e, snap
 
 
-CASES = {"flat": case_flat, "periodic_straddle": case_periodic_straddle, "nested": case_nested, "massvar": case_massvar}
+def case_sampled():
+    """Reference default MaxSampleSizeOfPotentialEstimate=1000 (+RefineMostboundParticle): sources above and below the
+    sample size, nested.  CPU fixtures use srand(7) + one thread (the reference's shuffle draws from libc rand())."""
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True, max_sample_size=1000, refine_mostbound=True, shuffle_seed=99)
+    e = capi.make_epoch(1.0, snapshot_index=21)
+    snap = synth.make_snapshot([5000, 1200, 800, 20000, 300, 50, 2500, 70, 30], seed=1003, parent=[-1, 0, 0, -1, 3, 4, -1, 6, 6], wrap=True, f_contam=0.35)
+    return p, e, snap
+
+
+SAMPLED_SRAND = 7
+
+CASES = {"flat": case_flat, "periodic_straddle": case_periodic_straddle, "nested": case_nested, "massvar": case_massvar, "sampled": case_sampled}
 
 IO_EXACT = ["nbound", "snapshot_index_of_death", "snapshot_index_of_sink", "sink_track_id", "nsource", "nsource_full"]
 IO_FLOAT = ["mbound", "avg_pos", "avg_vel", "mostbound_pos", "mostbound_vel", "specific_self_potential_energy",

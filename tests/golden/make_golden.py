@@ -31,6 +31,7 @@ def main():
             "has_nest": np.array(snap.nest_offset is not None),
         }
         for tag, flags in (("full", 0), ("trunc", capi.HBTU_FLAG_TRUNCATE_SOURCE)):
+            ref.hbtref_seed(cases.SAMPLED_SRAND)  # only the sampled case draws from rand()
             r = po.run_batch(ref, "hbtref", p, e, snap, flags=flags)
             ntot = int(r.order_offset[-1])
             out[f"{tag}_io"] = r.io

@@ -16,7 +16,11 @@ from oracle import pyoracle as po
 def test_oracle_matches_golden(oracle_lib, name, tag, flags):
     p, e, _ = cases.CASES[name]()
     snap, z = load_golden(name)
+    oracle_lib.hbto_set_shuffle_mode(0)  # libstdc++ random_shuffle on rand(), as the reference
+    oracle_lib.hbto_set_num_threads(1)
+    oracle_lib.hbto_seed(cases.SAMPLED_SRAND)
     r = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=flags)
+    oracle_lib.hbto_set_num_threads(8)
     g = z[f"{tag}_io"]
     skip = cases.unbound_inputs(snap)
     for f in cases.IO_EXACT:
