@@ -129,6 +129,63 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
   return no;
 }
 
+// E / potential epilogue shared by the walk variants
+template <int T>
+__device__ __forceinline__ void walk_epilogue(const WalkArgs &a, const DevConfig &cfg, const Segment &sg, int j0, const bool (&valid)[T],
+                                              const float (&px)[T], const float (&py)[T], const float (&pz)[T], const float (&pm)[T],
+                                              const double (&accd)[T])
+{
+  const int MODE = sg.mode; // warp-uniform: one segment per warp
+#pragma unroll
+  for (int k = 0; k < T; k++)
+  {
+    if (!valid[k]) continue;
+    const int t = sg.tgt_off + j0 + 32 * k;
+    // pot = targetMass/eps + sum ; return pot*G/a   (src/gravity_tree.cpp:98,163)
+    double pot = accd[k] + (double)__fdiv_rn(pm[k], cfg.softening);
+    pot = pot * (double)cfg.G / (double)cfg.scale_factor;
+    if (MODE == kWalkPotential)
+    {
+      a.out[t] = pot;
+      continue;
+    }
+    const float x[3] = {px[k], py[k], pz[k]};
+    if (MODE == kWalkBindingEnergy)
+    {
+      float4 v4 = a.vel[t];
+      const float v[3] = {v4.x, v4.y, v4.z};
+      float dv[3];
+      relative_velocity(x, v, a.ref_pos, a.ref_vel, cfg, dv);
+      a.out[t] = (double)dot3_rn(dv, dv) * 0.5 + pot;
+      continue;
+    }
+    const int64_t slot = a.tgt_slot[t];
+    const SubState &st = a.subs[sg.sub];
+    float4 v4 = a.vel[a.ids[slot]];
+    const float v[3] = {v4.x, v4.y, v4.z};
+    if (MODE == kWalkRefine)
+    { // Einner = BindingEnergy among the most-bound sample, current frame (src/subhalo_unbind.cpp:247)
+      float dv[3];
+      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
+      a.out_f[t] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+      continue;
+    }
+    if (MODE == kWalkUnbindFull)
+    { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
+      float dv[3];
+      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
+      a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+    }
+    else
+    { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
+      float ov[3];
+      relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
+      float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
+      a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
+    }
+  }
+}
+
 // T targets per lane: a warp owns 32*T consecutive targets (lane l holds targets l, l+32, ...).  T=1 for small
 // subhaloes; T=4 for large ones, where it quarters the dependent tile loads and the control instructions per
 // interaction at the price of a ~1.3x larger node union.
@@ -265,11 +322,160 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
   }
 }
 
+// Variant without shared-memory staging: every step loads the (warp-uniform) node with two broadcast loads that hit
+// L1 for runs of consecutive nodes.  One REDUX.OR per step carries both warp decisions: bit 0 = some lane opens the
+// node, bit 1 = some lane accepted a spline-softened pair (then this node alone is accumulated with the exact kernel).
+template <int T, bool PERIODIC, bool COUNT>
+__global__ void __launch_bounds__(kWalkWarps * 32) walk_direct_kernel(const WalkArgs a, const DevConfig cfg)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kWalkWarps + w;
+  if (warp >= a.nwarps) return;
+  int lo = 0, hi = a.nseg;
+  while (hi - lo > 1)
+  {
+    int mid = (lo + hi) >> 1;
+    if (a.warp_off[mid] <= warp) lo = mid; else hi = mid;
+  }
+  const Segment sg = a.segs[lo];
+  const int j0 = (warp - a.warp_off[lo]) * (32 * T) + lane;
+  float px[T], py[T], pz[T], pm[T];
+  int skip[T];
+  bool valid[T];
+#pragma unroll
+  for (int k = 0; k < T; k++)
+  {
+    const int j = j0 + 32 * k;
+    valid[k] = j < sg.tgt_n;
+    const float4 tp = a.tgt_pm[sg.tgt_off + (valid[k] ? j : 0)];
+    px[k] = tp.x; py[k] = tp.y; pz[k] = tp.z; pm[k] = tp.w;
+    skip[k] = valid[k] ? 0 : 0x7fffffff;
+  }
+  const int t0 = a.tree_off[lo], t1 = a.tree_off[lo + 1];
+  const int node_begin = t0 + (t0 > 0 ? a.cellcount[t0 - 1] : 0);
+  const int node_end = t1 + a.cellcount[t1 - 1];
+  const float h = 2.8f * cfg.softening, h2 = h * h, hinv = 1.0f / h;
+  int no = node_begin;
+  double accd[T];
+  float accf[T];
+#pragma unroll
+  for (int k = 0; k < T; k++) { accd[k] = 0.0; accf[k] = 0.f; }
+  unsigned n_acc = 0, n_vis = 0, it = 0;
+
+  while (no < node_end)
+  {
+    const float4 n = __ldg(&a.node_xm[no]);
+    const float2 ax = __ldg(&a.node_aux[no]);
+    const float lenq = ax.x;
+    const int nend = __float_as_int(ax.y);
+    float r2[T], rinv[T];
+    bool acc[T];
+    unsigned code = 0;
+#pragma unroll
+    for (int k = 0; k < T; k++)
+    {
+      float dx = n.x - px[k], dy = n.y - py[k], dz = n.z - pz[k];
+      if (PERIODIC)
+      {
+        dx = nearest_f(dx, cfg.box_size, cfg.box_half);
+        dy = nearest_f(dy, cfg.box_size, cfg.box_half);
+        dz = nearest_f(dz, cfg.box_size, cfg.box_half);
+      }
+      r2[k] = dx * dx + dy * dy + dz * dz;
+      const bool active = no >= skip[k];
+      const bool open = active && (lenq > r2[k]);
+      acc[k] = active && !(lenq > r2[k]);
+      rinv[k] = rsqrt_raw(r2[k]);
+      if (open) code |= 1u;
+      if (acc[k] && r2[k] < h2) code |= 2u;
+    }
+    const unsigned red = __reduce_or_sync(kFull, code);
+    if (red & 2u)
+    { // exact kernel for this node (src/gravity_tree.cpp:141-161)
+#pragma unroll
+      for (int k = 0; k < T; k++)
+      {
+        float contrib = -n.w * rinv[k];
+        if (r2[k] < h2)
+        {
+          float u = sqrtf(r2[k]) * hinv, wp;
+          if (u < 0.5f)
+            wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
+          else
+            wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
+          contrib = n.w * hinv * wp;
+        }
+        if (acc[k]) accf[k] += contrib;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < T; k++)
+        if (acc[k]) accf[k] = fmaf(-n.w, rinv[k], accf[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < T; k++)
+      if (acc[k])
+      {
+        skip[k] = nend;
+        if (COUNT) n_acc++;
+      }
+    if (COUNT) n_vis++;
+    no = (red & 1u) ? no + 1 : nend;
+    if (((++it) & 63u) == 0u)
+    {
+#pragma unroll
+      for (int k = 0; k < T; k++) { accd[k] += (double)accf[k]; accf[k] = 0.f; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < T; k++) accd[k] += (double)accf[k];
+  if (COUNT)
+  {
+    unsigned long long na = n_acc;
+    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(kFull, na, o);
+    if (lane == 0)
+    {
+      atomicAdd(&a.counters[0], na);
+      atomicAdd(&a.counters[1], (unsigned long long)n_vis);
+    }
+  }
+  walk_epilogue<T>(a, cfg, sg, j0, valid, px, py, pz, pm, accd);
+}
+
+// 0 = shared-memory tiles (default), 1 = direct broadcast loads, 2 = direct for T=1 only (experiments: HBTU_WALK_DIRECT)
+static int walk_direct()
+{
+  static int v = -1;
+  if (v < 0)
+  {
+    const char *e = getenv("HBTU_WALK_DIRECT");
+    v = e ? atoi(e) : 0; // default: shared-memory tiles; the direct variant lost in the bench workload (profiles/r01_walk_notes.md)
+  }
+  return v;
+}
+
 template <int T>
 static void launch_t(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream)
 {
   const int grid = div_up(a.nwarps, kWalkWarps);
   const bool count = a.counters != nullptr;
+  const int pol = walk_direct();
+  if (pol == 1 || (pol == 2 && T == 1))
+  {
+    if (cfg.periodic)
+    {
+      if (count) walk_direct_kernel<T, true, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+      else walk_direct_kernel<T, true, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+    }
+    else
+    {
+      if (count) walk_direct_kernel<T, false, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+      else walk_direct_kernel<T, false, false><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
+    }
+    return;
+  }
   if (cfg.periodic)
   {
     if (count) walk_kernel<T, true, true><<<grid, kWalkWarps * 32, 0, stream>>>(a, cfg);
