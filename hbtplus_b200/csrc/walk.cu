@@ -70,7 +70,7 @@ __device__ __forceinline__ float rsqrt_raw(float x)
 template <int T, bool PERIODIC, bool COUNT, bool CAREFUL>
 __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int tile_base, int tile_lim, int no, const float (&px)[T],
                                          const float (&py)[T], const float (&pz)[T], int (&skip)[T], float (&accf)[T], float &minr2,
-                                         const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis)
+                                         double (&accs)[T], const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis)
 {
   do
   {
@@ -97,20 +97,28 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
       any_open |= open;
       if (CAREFUL)
       {
-        float contrib = -n.w * rinv;
         if (__any_sync(kFull, acc && (r2 < h2)))
-        {
-          if (r2 < h2)
-          { // Gadget spline kernel, src/gravity_tree.cpp:146-160
-            float u = sqrtf(r2) * hinv, wp;
-            if (u < 0.5f)
-              wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
+        { // Gadget spline kernel in double, like the reference (src/gravity_tree.cpp:146-160): the self term
+          // -m*h_inv*2.8 then cancels targetMass/eps to the reference's own residual instead of fp32 round-off
+          if (acc)
+          {
+            if (r2 < h2)
+            {
+              const double hd = 2.8 * (double)cfg.softening, hinv_d = 1.0 / hd;
+              const double u = sqrt((double)r2) * hinv_d;
+              double wp;
+              if (u < 0.5)
+                wp = -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6));
+              else
+                wp = -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
+              accs[k] += (double)n.w * hinv_d * wp;
+            }
             else
-              wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
-            contrib = n.w * hinv * wp;
+              accf[k] = fmaf(-n.w, rinv, accf[k]);
           }
         }
-        if (acc) accf[k] += contrib;
+        else if (acc)
+          accf[k] = fmaf(-n.w, rinv, accf[k]);
       }
       else if (acc)
       {
@@ -248,14 +256,14 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
     for (int k = 0; k < T; k++) { skip0[k] = skip[k]; accf[k] = 0.f; }
     float minr2 = INFINITY;
     const unsigned c0 = n_acc, c1 = n_vis;
-    int nx = walk_tile<T, PERIODIC, COUNT, false>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, cfg, h2, hinv, n_acc, n_vis);
+    int nx = walk_tile<T, PERIODIC, COUNT, false>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, accd, cfg, h2, hinv, n_acc, n_vis);
     if (__any_sync(kFull, minr2 < h2))
     { // some lane met a softened pair in this tile: redo the tile exactly
 #pragma unroll
       for (int k = 0; k < T; k++) { skip[k] = skip0[k]; accf[k] = 0.f; }
       n_acc = c0;
       n_vis = c1;
-      nx = walk_tile<T, PERIODIC, COUNT, true>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, cfg, h2, hinv, n_acc, n_vis);
+      nx = walk_tile<T, PERIODIC, COUNT, true>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, accd, cfg, h2, hinv, n_acc, n_vis);
     }
     no = nx;
 #pragma unroll

@@ -72,12 +72,15 @@ class UnbindContext:
         return st
 
     # -- RefineParticles / RecursiveUnbind / Unbind / TruncateSource ---------------------------------
-    def unbind_batch(self, epoch, snap, flags: int = 0, want_energy: bool = True) -> BatchResult:
+    def unbind_batch(self, epoch, snap, flags: int = 0, want_energy: bool = True, order_buf=None, energy_buf=None) -> BatchResult:
+        """One RefineParticles-equivalent call.  ``order_buf`` / ``energy_buf`` may be caller-owned (e.g. pinned) int32 /
+        float32 arrays of at least ``capi.order_capacity(...)`` entries; otherwise they are allocated here."""
         cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
         io = snap.io.copy()
         order_offset = np.zeros(snap.nsub + 1, np.int64)
-        order = np.full(max(cap, 1), -1, np.int32)
-        energy = np.zeros(max(cap, 1), np.float32) if want_energy else None
+        order = order_buf if order_buf is not None else np.empty(max(cap, 1), np.int32)
+        energy = (energy_buf if energy_buf is not None else np.empty(max(cap, 1), np.float32)) if want_energy else None
+        assert order.dtype == np.int32 and len(order) >= cap
         pm = np.ascontiguousarray(snap.pos_mass, np.float32)
         vv = np.ascontiguousarray(snap.vel, np.float32)
         rc = self._lib.hbtu_unbind_batch(
@@ -101,8 +104,8 @@ class UnbindContext:
         cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
         io = snap.io.copy()
         order_offset = np.zeros(snap.nsub + 1, np.int64)
-        order = np.full(max(cap, 1), -1, np.int32)
-        energy = np.zeros(max(cap, 1), np.float32) if want_energy else None
+        order = np.empty(max(cap, 1), np.int32)
+        energy = np.empty(max(cap, 1), np.float32) if want_energy else None
         P = capi._ptr
         rc = self._lib.hbtu_fetch(self._ctx, io.ctypes.data_as(C.POINTER(capi.SubIO)), cap, P(order_offset, C.c_int64), P(order, C.c_int32), P(energy, C.c_float))
         self._check(rc)

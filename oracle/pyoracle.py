@@ -105,13 +105,23 @@ def tree_potential(lib, prefix, params, epoch, src_pos_mass, tgt_pos, self_mass=
 DROPIN_PATH = os.path.join(_HERE, "_ref", "libhbtdropin_v32.so")
 
 
-def have_dropin() -> bool:
-    return os.path.exists(DROPIN_PATH)
+def variant_paths(variant: str = "v32"):
+    return os.path.join(_HERE, "_ref", f"libhbtref_{variant}.so"), os.path.join(_HERE, "_ref", f"libhbtdropin_{variant}.so")
 
 
-def load_dropin():
+def have_dropin(variant: str = "v32") -> bool:
+    return all(os.path.exists(p) for p in variant_paths(variant))
+
+
+def load_dropin(variant: str = "v32"):
     """The reference harness linked against integration/subhalo_unbind_b200.o + libhbtunbind.so (GPU backend)."""
-    return _bind(C.CDLL(DROPIN_PATH), "hbtref")
+    return _bind(C.CDLL(variant_paths(variant)[1]), "hbtref")
+
+
+def load_ref_variant(variant: str):
+    lib = _bind(C.CDLL(variant_paths(variant)[0]), "hbtref")
+    lib.hbtref_seed.argtypes = [C.c_uint]
+    return lib
 
 
 def refine_particles(lib, params, epoch, snap, host_halo_id, n_old, nhalos, mbound_in):
