@@ -219,8 +219,9 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
   Arena &ar = c.arena;
   ar.reset();
   ar.reserve(tree_arena_bytes(S, 1) + (int64_t)T * 96 + (1 << 20));
-  const int tpl = walk_targets_per_lane(T);
-  std::vector<int> tree_off{0, S}, warp_off{0, (T + 32 * tpl - 1) / (32 * tpl)};
+  const WalkClass wcl = walk_class(T);
+  const int tpl = wcl.targets_per_lane;
+  std::vector<int> tree_off{0, S}, warp_off{0, (T + wcl.targets_per_warp - 1) / wcl.targets_per_warp};
   Segment sg{};
   sg.mode = tgt_vel ? kWalkBindingEnergy : kWalkPotential;
   sg.tree_n = S;

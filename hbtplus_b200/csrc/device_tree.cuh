@@ -130,7 +130,7 @@ struct WalkArgs
   const Segment *segs;   // [nseg]
   const int *warp_off;   // [nseg+1]
   int nseg, nwarps;
-  int targets_per_lane;  // 1, 2 or 4: warps own 32*T consecutive targets; warp_off is per class
+  int targets_per_lane;  // walk class: 1, 2 or 4 (walk.cu, warps own 32*T consecutive targets) or kWalkGroup4/8 (walk_group.cu)
   const float4 *tgt_pm;  // [T] x,y,z,self mass
   const int64_t *tgt_slot; // [T] slot in ids/E (unbind modes)
   const int *ids;        // Elist pid per slot
@@ -143,7 +143,17 @@ struct WalkArgs
   unsigned long long *counters; // [2]: accepted interactions, warp node visits (nullptr = do not count)
 };
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
-// targets per lane the walk uses for a segment with tgt_n targets (env HBTU_WALK_TPL / HBTU_WALK_BIG override)
-int walk_targets_per_lane(int tgt_n);
+// Walk classes.  A segment belongs to one class; every class has its own warp numbering (warp_off) and launch.
+constexpr int kWalkGroup4 = 104, kWalkGroup8 = 108; // group walk with 128 / 256 targets per warp
+constexpr int kWalkClasses = 4;
+struct WalkClass
+{
+  int index;            // 0..kWalkClasses-1
+  int targets_per_lane; // value for WalkArgs::targets_per_lane
+  int targets_per_warp;
+};
+// class used for a segment with tgt_n targets (env HBTU_WALK_TPL / HBTU_WALK_BIG* / HBTU_WALK_GROUP* override)
+WalkClass walk_class(int tgt_n);
+int walk_class_tpl(int index); // targets_per_lane value of class `index` (the group class depends on the environment)
 
 } // namespace hbt

@@ -690,9 +690,10 @@ static void run_round(Context &c, std::vector<int> &active)
   const int nseg = (int)active.size();
   std::vector<Segment> segs(nseg);
   std::vector<int> tree_off(nseg + 1), tgt_off(nseg + 1);
-  // walk warps per class of targets-per-lane (index 0: T=1, 1: T=2, 2: T=4); a segment belongs to one class
-  std::vector<int> warp_off[3] = {std::vector<int>(nseg + 1), std::vector<int>(nseg + 1), std::vector<int>(nseg + 1)};
-  int64_t S = 0, T = 0, W[3] = {0, 0, 0};
+  // walk warps per walk class (device_tree.cuh: T=1, 2, 4 per-lane walks and the group walk); a segment belongs to one class
+  std::vector<int> warp_off[kWalkClasses];
+  for (auto &v : warp_off) v.resize(nseg + 1);
+  int64_t S = 0, T = 0, W[kWalkClasses] = {0, 0, 0, 0};
   bool any_hoare = false;
   for (int a = 0; a < nseg; a++)
   {
@@ -726,19 +727,20 @@ static void run_round(Context &c, std::vector<int> &active)
     sg.tgt_n = h.nbound;
     sg.tree_off = (int)S;
     sg.tgt_off = (int)T;
-    const int tpl = walk_targets_per_lane(sg.tgt_n), cls = tpl == 4 ? 2 : (tpl == 2 ? 1 : 0);
+    const WalkClass wcl = walk_class(sg.tgt_n);
+    const int cls = wcl.index;
     sg.warp_off = (int)W[cls];
     tree_off[a] = (int)S;
     tgt_off[a] = (int)T;
-    for (int q = 0; q < 3; q++) warp_off[q][a] = (int)W[q];
+    for (int q = 0; q < kWalkClasses; q++) warp_off[q][a] = (int)W[q];
     S += sg.tree_n;
     T += sg.tgt_n;
-    W[cls] += (sg.tgt_n + 32 * tpl - 1) / (32 * tpl);
+    W[cls] += (sg.tgt_n + wcl.targets_per_warp - 1) / wcl.targets_per_warp;
     if (S > 0x3fffffff || T > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "round larger than 2^30 particles"};
   }
   tree_off[nseg] = (int)S;
   tgt_off[nseg] = (int)T;
-  for (int q = 0; q < 3; q++) warp_off[q][nseg] = (int)W[q];
+  for (int q = 0; q < kWalkClasses; q++) warp_off[q][nseg] = (int)W[q];
 
   Arena &ar = c.arena;
   ar.reset();
@@ -746,7 +748,8 @@ static void run_round(Context &c, std::vector<int> &active)
   cudaStream_t st = c.stream;
   Segment *d_segs = upload(ar, segs, st);
   int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st);
-  int *d_warp_off[3] = {upload(ar, warp_off[0], st), upload(ar, warp_off[1], st), upload(ar, warp_off[2], st)};
+  int *d_warp_off[kWalkClasses];
+  for (int q = 0; q < kWalkClasses; q++) d_warp_off[q] = upload(ar, warp_off[q], st);
 
   HBT_CUDA(cudaEventRecord(c.ev[0], st));
   TreeArrays tr;
@@ -792,11 +795,11 @@ static void run_round(Context &c, std::vector<int> &active)
   wa.subs = c.d_subs;
   wa.out = nullptr;
   wa.counters = c.count_interactions ? c.d_counters : nullptr;
-  for (int q = 0; q < 3; q++)
-  {
+  for (int q = kWalkClasses - 1; q >= 0; q--)
+  { // largest segments first: their long-running warps start while the small classes fill the tail
     wa.warp_off = d_warp_off[q];
     wa.nwarps = (int)W[q];
-    wa.targets_per_lane = 1 << q;
+    wa.targets_per_lane = walk_class_tpl(q);
     launch_walk(wa, c.cfg, st, c.ls);
   }
   HBT_CUDA(cudaEventRecord(c.ev[2], st));

@@ -22,177 +22,12 @@
 // Roofline: FP32 issue.  Tensor cores are deliberately not used.
 #include <cstdlib>
 
-#include "device_tree.cuh"
+#include "walk_common.cuh"
 
 namespace hbt
 {
 
 static constexpr int kWalkWarps = 4;
-static constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ void relative_velocity(const float tp[3], const float tv[3], const float rp[3], const float rv[3],
-                                                  const DevConfig &cfg, float dv[3])
-{ // Snapshot_t::RelativeVelocity, src/snapshot.h:100-111, in HBTReal=float with no FMA contraction
-#pragma unroll
-  for (int j = 0; j < 3; j++)
-  {
-    float dx = __fsub_rn(tp[j], rp[j]);
-    if (cfg.periodic) dx = nearest_f(dx, cfg.box_size, cfg.box_half);
-    float d = __fsub_rn(tv[j], rv[j]);
-    dv[j] = __fadd_rn(d, __fmul_rn(__fmul_rn(cfg.hz, cfg.scale_factor), dx));
-  }
-}
-__device__ __forceinline__ float dot3_rn(const float a[3], const float b[3])
-{ // VecDot macro, src/mymath.h:20, float arithmetic left to right
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
-}
-
-struct __align__(16) TileNode
-{ // one staged node: 32 B so that a warp's tile is 1 KB and both loads are broadcasts
-  float4 xm;  // x, y, z, mass
-  float lenq; // len^2/theta^2 (0 for particles)
-  int end;    // index of the first node after this node's subtree
-  int pad0, pad1;
-};
-
-__device__ __forceinline__ float rsqrt_raw(float x)
-{ // single MUFU.RSQ; r2 == 0 (self / co-located pair) gives +inf and is replaced by the spline branch
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// One pass over the staged tile [tile_base, tile_lim) starting at node `no`, for the T targets of every lane.
-//   CAREFUL=false: every accepted source is added as -m/r and the smallest accepted r^2 is tracked; the caller
-//                  redoes the tile with CAREFUL=true if any lane met r < 2.8 eps (spline-softened pair, or r = 0).
-//   CAREFUL=true : the reference's full kernel (src/gravity_tree.cpp:141-161), branch taken on a warp vote.
-// Returns the node index at which the warp left the tile.
-template <int T, bool PERIODIC, bool COUNT, bool CAREFUL>
-__device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int tile_base, int tile_lim, int no, const float (&px)[T],
-                                         const float (&py)[T], const float (&pz)[T], int (&skip)[T], float (&accf)[T], float &minr2,
-                                         double (&accs)[T], const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis)
-{
-  do
-  {
-    const TileNode *nd = &tile[no - tile_base];
-    const float4 n = nd->xm;
-    const float lenq = nd->lenq;
-    const int nend = nd->end;
-    bool any_open = false;
-#pragma unroll
-    for (int k = 0; k < T; k++)
-    {
-      float dx = n.x - px[k], dy = n.y - py[k], dz = n.z - pz[k];
-      if (PERIODIC)
-      {
-        dx = nearest_f(dx, cfg.box_size, cfg.box_half);
-        dy = nearest_f(dy, cfg.box_size, cfg.box_half);
-        dz = nearest_f(dz, cfg.box_size, cfg.box_half);
-      }
-      const float r2 = dx * dx + dy * dy + dz * dz;
-      const bool active = no >= skip[k];
-      const bool open = active && (lenq > r2); // reference criterion, per target (src/gravity_tree.cpp:135)
-      const bool acc = active && !(lenq > r2);
-      const float rinv = rsqrt_raw(r2);
-      any_open |= open;
-      if (CAREFUL)
-      {
-        if (__any_sync(kFull, acc && (r2 < h2)))
-        { // Gadget spline kernel in double, like the reference (src/gravity_tree.cpp:146-160): the self term
-          // -m*h_inv*2.8 then cancels targetMass/eps to the reference's own residual instead of fp32 round-off
-          if (acc)
-          {
-            if (r2 < h2)
-            {
-              const double hd = 2.8 * (double)cfg.softening, hinv_d = 1.0 / hd;
-              const double u = sqrt((double)r2) * hinv_d;
-              double wp;
-              if (u < 0.5)
-                wp = -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6));
-              else
-                wp = -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
-              accs[k] += (double)n.w * hinv_d * wp;
-            }
-            else
-              accf[k] = fmaf(-n.w, rinv, accf[k]);
-          }
-        }
-        else if (acc)
-          accf[k] = fmaf(-n.w, rinv, accf[k]);
-      }
-      else if (acc)
-      {
-        accf[k] = fmaf(-n.w, rinv, accf[k]);
-        minr2 = fminf(minr2, r2);
-      }
-      if (acc)
-      {
-        skip[k] = nend; // resume after this subtree (a particle's end is no+1)
-        if (COUNT) n_acc++;
-      }
-    }
-    if (COUNT) n_vis++;
-    no = __any_sync(kFull, any_open) ? no + 1 : nend;
-  } while (no < tile_lim);
-  return no;
-}
-
-// E / potential epilogue shared by the walk variants
-template <int T>
-__device__ __forceinline__ void walk_epilogue(const WalkArgs &a, const DevConfig &cfg, const Segment &sg, int j0, const bool (&valid)[T],
-                                              const float (&px)[T], const float (&py)[T], const float (&pz)[T], const float (&pm)[T],
-                                              const double (&accd)[T])
-{
-  const int MODE = sg.mode; // warp-uniform: one segment per warp
-#pragma unroll
-  for (int k = 0; k < T; k++)
-  {
-    if (!valid[k]) continue;
-    const int t = sg.tgt_off + j0 + 32 * k;
-    // pot = targetMass/eps + sum ; return pot*G/a   (src/gravity_tree.cpp:98,163)
-    double pot = accd[k] + (double)__fdiv_rn(pm[k], cfg.softening);
-    pot = pot * (double)cfg.G / (double)cfg.scale_factor;
-    if (MODE == kWalkPotential)
-    {
-      a.out[t] = pot;
-      continue;
-    }
-    const float x[3] = {px[k], py[k], pz[k]};
-    if (MODE == kWalkBindingEnergy)
-    {
-      float4 v4 = a.vel[t];
-      const float v[3] = {v4.x, v4.y, v4.z};
-      float dv[3];
-      relative_velocity(x, v, a.ref_pos, a.ref_vel, cfg, dv);
-      a.out[t] = (double)dot3_rn(dv, dv) * 0.5 + pot;
-      continue;
-    }
-    const int64_t slot = a.tgt_slot[t];
-    const SubState &st = a.subs[sg.sub];
-    float4 v4 = a.vel[a.ids[slot]];
-    const float v[3] = {v4.x, v4.y, v4.z};
-    if (MODE == kWalkRefine)
-    { // Einner = BindingEnergy among the most-bound sample, current frame (src/subhalo_unbind.cpp:247)
-      float dv[3];
-      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-      a.out_f[t] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
-      continue;
-    }
-    if (MODE == kWalkUnbindFull)
-    { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
-      float dv[3];
-      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-      a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
-    }
-    else
-    { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
-      float ov[3];
-      relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
-      float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
-      a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
-    }
-  }
-}
 
 // T targets per lane: a warp owns 32*T consecutive targets (lane l holds targets l, l+32, ...).  T=1 for small
 // subhaloes; T=4 for large ones, where it quarters the dependent tile loads and the control instructions per
@@ -237,38 +72,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
   unsigned n_acc = 0, n_vis = 0;
   TileNode *const tile = s_tile[w];
 
-  while (no < node_end)
-  {
-    // stage nodes [no, no+32): one coalesced 16 B + 8 B load per lane (arrays are padded by 32 nodes)
-    const int tile_base = no;
-    const int tile_lim = min(no + 32, node_end);
-    {
-      const float4 xm = __ldg(&a.node_xm[no + lane]);
-      const float2 ax = __ldg(&a.node_aux[no + lane]);
-      __syncwarp();
-      tile[lane].xm = xm;
-      *reinterpret_cast<float2 *>(&tile[lane].lenq) = ax;
-      __syncwarp();
-    }
-    int skip0[T];
-    float accf[T];
-#pragma unroll
-    for (int k = 0; k < T; k++) { skip0[k] = skip[k]; accf[k] = 0.f; }
-    float minr2 = INFINITY;
-    const unsigned c0 = n_acc, c1 = n_vis;
-    int nx = walk_tile<T, PERIODIC, COUNT, false>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, accd, cfg, h2, hinv, n_acc, n_vis);
-    if (__any_sync(kFull, minr2 < h2))
-    { // some lane met a softened pair in this tile: redo the tile exactly
-#pragma unroll
-      for (int k = 0; k < T; k++) { skip[k] = skip0[k]; accf[k] = 0.f; }
-      n_acc = c0;
-      n_vis = c1;
-      nx = walk_tile<T, PERIODIC, COUNT, true>(tile, tile_base, tile_lim, no, px, py, pz, skip, accf, minr2, accd, cfg, h2, hinv, n_acc, n_vis);
-    }
-    no = nx;
-#pragma unroll
-    for (int k = 0; k < T; k++) accd[k] += (double)accf[k]; // <= 32 fp32 terms per flush
-  }
+  walk_range<T, PERIODIC, COUNT>(a.node_xm, a.node_aux, tile, no, node_end, px, py, pz, skip, accd, cfg, h2, hinv, n_acc, n_vis);
   if (COUNT)
   {
     unsigned long long na = n_acc;
@@ -279,55 +83,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
       atomicAdd(&a.counters[1], (unsigned long long)n_vis);
     }
   }
-  const int MODE = sg.mode; // warp-uniform: one segment per warp
-#pragma unroll
-  for (int k = 0; k < T; k++)
-  {
-    if (!valid[k]) continue;
-    const int t = sg.tgt_off + j0 + 32 * k;
-    // pot = targetMass/eps + sum ; return pot*G/a   (src/gravity_tree.cpp:98,163)
-    double pot = accd[k] + (double)__fdiv_rn(pm[k], cfg.softening);
-    pot = pot * (double)cfg.G / (double)cfg.scale_factor;
-    if (MODE == kWalkPotential)
-    {
-      a.out[t] = pot;
-      continue;
-    }
-    const float x[3] = {px[k], py[k], pz[k]};
-    if (MODE == kWalkBindingEnergy)
-    {
-      float4 v4 = a.vel[t];
-      const float v[3] = {v4.x, v4.y, v4.z};
-      float dv[3];
-      relative_velocity(x, v, a.ref_pos, a.ref_vel, cfg, dv);
-      a.out[t] = (double)dot3_rn(dv, dv) * 0.5 + pot;
-      continue;
-    }
-    const int64_t slot = a.tgt_slot[t];
-    const SubState &st = a.subs[sg.sub];
-    float4 v4 = a.vel[a.ids[slot]];
-    const float v[3] = {v4.x, v4.y, v4.z};
-    if (MODE == kWalkRefine)
-    { // Einner = BindingEnergy among the most-bound sample, current frame (src/subhalo_unbind.cpp:247)
-      float dv[3];
-      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-      a.out_f[t] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
-      continue;
-    }
-    if (MODE == kWalkUnbindFull)
-    { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
-      float dv[3];
-      relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-      a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
-    }
-    else
-    { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
-      float ov[3];
-      relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
-      float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
-      a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
-    }
-  }
+  walk_epilogue<T>(a, cfg, sg, j0, valid, px, py, pz, pm, accd);
 }
 
 // Variant without shared-memory staging: every step loads the (warp-uniform) node with two broadcast loads that hit
@@ -496,9 +252,36 @@ static void launch_t(const WalkArgs &a, const DevConfig &cfg, cudaStream_t strea
   }
 }
 
+namespace
+{
+struct WalkPolicy
+{
+  int forced, big4, big2, group_min, group_t;
+  WalkPolicy()
+  {
+    auto env = [](const char *n, int d) { const char *e = getenv(n); return e ? atoi(e) : d; };
+    forced = env("HBTU_WALK_TPL", 0);
+    big4 = env("HBTU_WALK_BIG4", 1 << 20);
+    big2 = env("HBTU_WALK_BIG2", 1 << 19);
+    group_min = env("HBTU_WALK_GROUP_MIN", 1 << 15); // segments with at least this many targets use the group walk (0 = never)
+    group_t = env("HBTU_WALK_GROUP_T", 4) == 8 ? 8 : 4;
+  }
+};
+const WalkPolicy &policy()
+{
+  static WalkPolicy p;
+  return p;
+}
+} // namespace
+
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls)
 {
   if (a.nwarps <= 0) return;
+  if (a.targets_per_lane == kWalkGroup4 || a.targets_per_lane == kWalkGroup8)
+  {
+    launch_walk_group(a, cfg, stream, ls);
+    return;
+  }
   if (a.targets_per_lane == 4) launch_t<4>(a, cfg, stream);
   else if (a.targets_per_lane == 2) launch_t<2>(a, cfg, stream);
   else launch_t<1>(a, cfg, stream);
@@ -506,23 +289,19 @@ void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, L
   ls.launches++;
 }
 
-} // namespace hbt
 
-namespace hbt
-{
-int walk_targets_per_lane(int tgt_n)
-{ // measured on B200 (profiles/r01_walk_notes.md): T=4 wins once a segment alone fills the GPU (~1e6 targets),
-  // T=1 wins below ~5e5 where the warp count, not the instruction count, limits throughput
-  static int forced = -1, big4 = 0, big2 = 0;
-  if (forced < 0)
-  {
-    const char *e = getenv("HBTU_WALK_TPL");
-    forced = e ? atoi(e) : 0;
-    const char *b4 = getenv("HBTU_WALK_BIG4"), *b2 = getenv("HBTU_WALK_BIG2");
-    big4 = b4 ? atoi(b4) : (1 << 20);
-    big2 = b2 ? atoi(b2) : (1 << 19);
-  }
-  if (forced == 1 || forced == 2 || forced == 4) return tgt_n >= 32 * forced ? forced : 1;
-  return tgt_n >= big4 ? 4 : (tgt_n >= big2 ? 2 : 1);
+int walk_class_tpl(int index) { return index == 3 ? (policy().group_t == 8 ? kWalkGroup8 : kWalkGroup4) : (1 << index); }
+
+WalkClass walk_class(int tgt_n)
+{ // measured on B200 (profiles/): the group walk wins for large segments; below it T=1 per-lane walks win, where the
+  // warp count, not the instruction count, limits throughput
+  const WalkPolicy &p = policy();
+  if (p.group_min > 0 && tgt_n >= p.group_min && !(p.forced == 1 || p.forced == 2 || p.forced == 4))
+    return WalkClass{3, walk_class_tpl(3), 32 * p.group_t};
+  int t;
+  if (p.forced == 1 || p.forced == 2 || p.forced == 4) t = tgt_n >= 32 * p.forced ? p.forced : 1;
+  else t = tgt_n >= p.big4 ? 4 : (tgt_n >= p.big2 ? 2 : 1);
+  return WalkClass{t == 4 ? 2 : (t == 2 ? 1 : 0), t, 32 * t};
 }
+
 } // namespace hbt
