@@ -141,6 +141,7 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
     grow(c.d_ids_orig, cap1, c.total_cap);
     grow(c.d_E, cap2, c.total_cap);
     c.cap_slots = cap0;
+    if (c.cfg.periodic) grow(c.d_rho, c.cap_rho, c.total_cap);
   }
   {
     int64_t cap0 = c.cap_subs, cap1 = c.cap_subs, cap2 = c.cap_subs;
@@ -401,6 +402,7 @@ void hbtu_destroy(hbtu_ctx *ctx)
   cudaFree(c.d_ids);
   cudaFree(c.d_ids_orig);
   cudaFree(c.d_E);
+  cudaFree(c.d_rho);
   cudaFree(c.d_subs);
   cudaFree(c.d_part_offset);
   cudaFree(c.d_slot_base);

@@ -42,7 +42,8 @@ struct Context
   int64_t cap_particles = 0, cap_vel = 0;
   int *d_ids = nullptr, *d_ids_orig = nullptr;
   float *d_E = nullptr;
-  int64_t cap_slots = 0;
+  int *d_rho = nullptr; // periodic runs: index of every Elist entry in the REFERENCE's Elist order (unbind_batch.cu, rho_*)
+  int64_t cap_slots = 0, cap_rho = 0;
   SubState *d_subs = nullptr;
   int64_t *d_part_offset = nullptr, *d_slot_base = nullptr;
   int64_t cap_subs = 0;

@@ -74,7 +74,9 @@ struct SubState
   float mbound, spec_pot, spec_kin, am[3];
   float ref_diff[3], dK; // RefVelDiff and dK of the current correction round
   int count_bound;       // scratch: number of E<0 among this round's targets
-  int pad;
+  int origin_id;         // periodic: particle that is Elist[0] in the reference's order (origin of AveragePosition, :152-154)
+  int hoare_last;        // scratch: largest reference index in [1,Nbound) of a bound entry (0 = none)
+  int hoare_first_bound; // scratch: the reference's Elist[0] is bound
   double sums[8]; // scratch: reduction accumulators
 };
 

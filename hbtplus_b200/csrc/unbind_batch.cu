@@ -203,21 +203,43 @@ __global__ void __launch_bounds__(kBlock) gather_src_kernel(const Segment *__res
 // the Elist order inside [0,Nlast) is free in exact mode, and key order makes walk targets coherent.
 __global__ void __launch_bounds__(kBlock) sorted_ids_read_kernel(const Segment *__restrict__ segs, const int *__restrict__ ts_seg,
                                                                   const int *__restrict__ sperm, int S, const int *__restrict__ ids,
-                                                                  int *__restrict__ tmp)
+                                                                  int *__restrict__ tmp, const int *__restrict__ rho, int *__restrict__ tmp_rho)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   const Segment sg = segs[ts_seg[k]];
   int src = sperm[k]; // S-index before sorting (same segment)
-  tmp[k] = ids[sg.slot_base + sg.tree_first + (src - sg.tree_off)];
+  const int64_t slot = sg.slot_base + sg.tree_first + (src - sg.tree_off);
+  tmp[k] = ids[slot];
+  if (rho) tmp_rho[k] = rho[slot];
 }
 __global__ void __launch_bounds__(kBlock) sorted_ids_write_kernel(const Segment *__restrict__ segs, const int *__restrict__ ts_seg, int S,
-                                                                   const int *__restrict__ tmp, int *__restrict__ ids)
+                                                                   const int *__restrict__ tmp, int *__restrict__ ids,
+                                                                   const int *__restrict__ tmp_rho, int *__restrict__ rho)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   const Segment sg = segs[ts_seg[k]];
-  if (sg.mode == kWalkUnbindFull && !sg.keep_order) ids[sg.slot_base + sg.tree_first + (k - sg.tree_off)] = tmp[k];
+  if (sg.mode == kWalkUnbindFull && !sg.keep_order)
+  {
+    const int64_t slot = sg.slot_base + sg.tree_first + (k - sg.tree_off);
+    ids[slot] = tmp[k];
+    if (rho) rho[slot] = tmp_rho[k];
+  }
+}
+
+// Periodic runs: rho[slot] = index of that Elist entry in the REFERENCE's Elist.  The reference's AveragePosition
+// measures NEAREST offsets from Elist[0] (src/subhalo_unbind.cpp:152-154), and which particle that is follows from
+// its hole-based partition (:21-58) - while this library keeps the bound part in key order.  So the reference order is
+// carried as one int per entry: identity when a subhalo starts (its Particles order: own list + children's tails),
+// moved with every permutation, and advanced by the Hoare rule each round (rho_update_kernel).
+__global__ void __launch_bounds__(kBlock) rho_init_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+                                                           const SubState *__restrict__ subs, int *__restrict__ rho)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const Segment sg = segs[tgt_seg[t]];
+  if (subs[sg.sub].iterations == 0) rho[sg.slot_base + (t - sg.tgt_off)] = t - sg.tgt_off;
 }
 
 __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_off, int nseg, int T,
@@ -246,6 +268,12 @@ __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restri
   tgt_seg[t] = a;
 }
 
+__global__ void __launch_bounds__(kBlock) fill_tgt_seg_kernel(const int *__restrict__ tgt_off, int nseg, int T, int *__restrict__ tgt_seg)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) tgt_seg[t] = find_seg(tgt_off, nseg, t);
+}
+
 __global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, DevConfig cfg)
 {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,6 +281,8 @@ __global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubS
   SubState &st = subs[segs[a].sub];
   if (segs[a].mode != kWalkRefine) st.iterations++;
   st.count_bound = 0;
+  st.hoare_last = 0;
+  st.hoare_first_bound = 0;
   for (int j = 0; j < 8; j++) st.sums[j] = 0.0;
   if (segs[a].mode == kWalkUnbindCorrect)
   { // RefVelDiff = RelativeVelocity(OldRef -> Ref), dK = 0.5*|RefVelDiff|^2  (src/subhalo_unbind.cpp:314-316)
@@ -330,27 +360,34 @@ __global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubSta
 // b_1>b_2>.. the bound elements at indices >= Nb:  new[0]=old[b_1], new[f_k]=old[b_(k+1)], old[0] (if bound)
 // ends at f_last; bound elements already in [1,Nb) stay.  hoare_flags marks the two misplaced sets, two scans rank
 // them, hoare_fpos inverts the front ranks.
-__global__ void __launch_bounds__(kBlock) hoare_flags_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
-                                                              const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
-                                                              const SubState *__restrict__ subs, int *__restrict__ uflag, int *__restrict__ bflag)
+// `rho` == nullptr (non-periodic): only the sampled full-evaluation segments take part and the reference index of an
+// entry is its position.  Periodic: every active segment takes part, indexed through rho (flags live in rho space).
+__device__ __forceinline__ bool hoare_segment(const Segment &sg, const int *rho) { return rho ? true : (sg.keep_order && sg.mode == kWalkUnbindFull); }
+
+__global__ void __launch_bounds__(kBlock) hoare_clear_kernel(int T, int *__restrict__ uflag, int *__restrict__ bflag)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
+  uflag[t] = 0;
+  bflag[t] = 0;
+}
+__global__ void __launch_bounds__(kBlock) hoare_flags_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
+                                                              const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
+                                                              SubState *__restrict__ subs, const int *__restrict__ rho,
+                                                              int *__restrict__ uflag, int *__restrict__ bflag)
+{ // uflag/bflag are pre-cleared; every entry writes the flags of ITS reference index
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
   const Segment sg = segs[tgt_seg[t]];
-  int u = 0, b = 0;
-  if (sg.keep_order && sg.mode == kWalkUnbindFull)
-  {
-    const SubState &st = subs[sg.sub];
-    if (st.status == kActive)
-    {
-      int j = t - sg.tgt_off;
-      bool bound = E[tgt_slot[t]] < 0.f;
-      u = (!bound && j >= 1 && j < st.nbound);
-      b = (bound && j >= st.nbound);
-    }
-  }
-  uflag[t] = u;
-  bflag[t] = b;
+  if (!hoare_segment(sg, rho)) return;
+  SubState &st = subs[sg.sub];
+  if (st.status == kDisrupted) return;
+  const int r = rho ? rho[tgt_slot[t]] : t - sg.tgt_off;
+  const bool bound = E[tgt_slot[t]] < 0.f;
+  uflag[sg.tgt_off + r] = (!bound && r >= 1 && r < st.nbound);
+  bflag[sg.tgt_off + r] = (bound && r >= st.nbound);
+  if (bound && r == 0) st.hoare_first_bound = 1;
+  if (bound && r >= 1 && r < st.nbound) atomicMax(&st.hoare_last, r);
 }
 __global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
                                                              const int *__restrict__ uflag, const int *__restrict__ uscan, int *__restrict__ fpos)
@@ -362,12 +399,59 @@ __global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__res
   fpos[sg.tgt_off + (uscan[t] - before) - 1] = t - sg.tgt_off; // k-th misplaced unbound element of the front
 }
 
+// Reference index of a BOUND entry after the hole-based partition (src/subhalo_unbind.cpp:21-58), from its index r
+// before it.  Elist[0] is lifted out (Etmp) and the hole travels: with f_1<f_2<..<f_K the unbound entries at indices
+// [1,Nb) and b_1>b_2>.. the bound entries at indices >= Nb,
+//     new[0] = old[b_1],  new[f_k] = old[b_(k+1)]  (while such b exist),
+// and when Elist[0] itself is bound (then there are exactly K such b) the backward scan goes on below Nb: the LAST bound
+// entry L of [1,Nb) moves into the hole f_K if L > f_K (f_0 = 0), and old[0] lands in the last hole (L, else f_K).
+// bscan = inclusive scan of the misplaced-bound flags, fpos = the holes f_k in ascending order.
+__device__ __forceinline__ int hoare_dest(const Segment &sg, const SubState &st, int r, const int *__restrict__ bscan,
+                                          const int *__restrict__ fpos)
+{
+  const int nb = st.nbound;
+  const int b0 = sg.tgt_off > 0 ? bscan[sg.tgt_off - 1] : 0;
+  const int mis = bscan[sg.tgt_off + sg.tgt_n - 1] - b0; // bound entries at indices >= Nb
+  if (r >= nb)
+  {
+    const int k = mis - (bscan[sg.tgt_off + r] - b0 - 1); // 1 = last misplaced bound element of the segment
+    return (k == 1) ? 0 : fpos[sg.tgt_off + k - 2];
+  }
+  if (!st.hoare_first_bound) return r; // Elist[0] unbound: K = mis - 1 holes, all filled by the b's
+  const int fK = mis >= 1 ? fpos[sg.tgt_off + mis - 1] : 0;
+  const int L = st.hoare_last;
+  const bool moveL = L > fK;
+  if (r == 0) return moveL ? L : fK;
+  if (r == L && moveL) return fK;
+  return r;
+}
+
+// periodic runs: advance rho of the bound entries, remember which particle is now the reference's Elist[0]
+__global__ void __launch_bounds__(kBlock) rho_update_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
+                                                             const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
+                                                             SubState *__restrict__ subs, const int *__restrict__ ids, const int *__restrict__ bscan,
+                                                             const int *__restrict__ fpos, const int *__restrict__ rho, int *__restrict__ rho_new)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const Segment sg = segs[tgt_seg[t]];
+  SubState &st = subs[sg.sub];
+  int r = -1; // unbound entries get their index from the sort (position in the E-sorted tail)
+  if (st.status != kDisrupted && E[tgt_slot[t]] < 0.f)
+  {
+    r = hoare_dest(sg, st, rho[tgt_slot[t]], bscan, fpos);
+    if (r == 0) st.origin_id = ids[tgt_slot[t]];
+  }
+  rho_new[t] = r;
+}
+
 // One key per target: (segment, bound|unbound) major, then E (where the reference sorts) or the current
 // position (where it does not): a single radix sort = partition + tail sort + final bound sort.
 __global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
                                                             const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
                                                             const SubState *__restrict__ subs, const int *__restrict__ bscan,
-                                                            const int *__restrict__ fpos, uint64_t *__restrict__ key, int *__restrict__ val)
+                                                            const int *__restrict__ fpos, const int *__restrict__ rho, uint64_t *__restrict__ key,
+                                                            int *__restrict__ val)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -385,20 +469,7 @@ __global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__rest
     if (status == kConverged)
       low = float_to_ordered(e);
     else if (bscan && sg.keep_order && sg.mode == kWalkUnbindFull)
-    { // Hoare destination of a bound element
-      const int nb = subs[sg.sub].nbound;
-      const int b0 = sg.tgt_off > 0 ? bscan[sg.tgt_off - 1] : 0;
-      const int mis = bscan[sg.tgt_off + sg.tgt_n - 1] - b0; // misplaced bound elements (= M)
-      if ((int)j >= nb)
-      {
-        int k = mis - (bscan[t] - b0 - 1); // 1 = last misplaced bound element of the segment
-        low = (k == 1) ? 0u : (uint32_t)fpos[sg.tgt_off + k - 2];
-      }
-      else if (j == 0)
-        low = mis >= 1 ? (uint32_t)fpos[sg.tgt_off + mis - 1] : 0u;
-      else
-        low = j;
-    }
+      low = (uint32_t)hoare_dest(sg, subs[sg.sub], rho ? rho[tgt_slot[t]] : (int)j, bscan, fpos); // Hoare destination of a bound element
     else
       low = j;
   }
@@ -407,22 +478,33 @@ __global__ void __launch_bounds__(kBlock) sort_keys_kernel(const Segment *__rest
 }
 __global__ void __launch_bounds__(kBlock) permute_read_kernel(const int *__restrict__ order, const int64_t *__restrict__ tgt_slot, int T,
                                                                const int *__restrict__ ids, const float *__restrict__ E,
-                                                               int *__restrict__ tmp_id, float *__restrict__ tmp_E)
+                                                               int *__restrict__ tmp_id, float *__restrict__ tmp_E,
+                                                               const int *__restrict__ rho_new = nullptr, int *__restrict__ tmp_rho = nullptr)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= T) return;
   int64_t slot = tgt_slot[order[p]];
   tmp_id[p] = ids[slot];
   tmp_E[p] = E[slot];
+  if (rho_new) tmp_rho[p] = rho_new[order[p]];
 }
 __global__ void __launch_bounds__(kBlock) permute_write_kernel(const int64_t *__restrict__ tgt_slot, int T, const int *__restrict__ tmp_id,
-                                                                const float *__restrict__ tmp_E, int *__restrict__ ids, float *__restrict__ E)
+                                                                const float *__restrict__ tmp_E, int *__restrict__ ids, float *__restrict__ E,
+                                                                const Segment *__restrict__ segs = nullptr, const int *__restrict__ tgt_seg = nullptr,
+                                                                const int *__restrict__ tmp_rho = nullptr, int *__restrict__ rho = nullptr)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= T) return;
   int64_t slot = tgt_slot[p];
   ids[slot] = tmp_id[p];
   E[slot] = tmp_E[p];
+  if (rho)
+  { // bound entries keep the Hoare index; the unbound tail is E-sorted in the reference too (:382): index = position.
+    // Sampled full-evaluation segments were physically arranged by the Hoare rule: index = position as well.
+    const Segment sg = segs[tgt_seg[p]];
+    const int r = tmp_rho[p];
+    rho[slot] = (r < 0 || (sg.keep_order && sg.mode == kWalkUnbindFull)) ? p - sg.tgt_off : r;
+  }
 }
 
 __device__ __forceinline__ double warp_sum_d(double v)
@@ -509,7 +591,7 @@ __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__r
       v[3] = (double)__fmul_rn(u.z, m);
       if (cfg.periodic)
       {
-        float4 o = pos[ids[sg.slot_base]]; // origin = first particle (:152-154)
+        float4 o = pos[st.origin_id]; // origin = the reference's Elist[0] (:152-154)
         v[4] = nearest_d((double)x.x - (double)o.x, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
         v[5] = nearest_d((double)x.y - (double)o.y, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
         v[6] = nearest_d((double)x.z - (double)o.z, (double)cfg.box_size, (double)cfg.box_half) * (double)m;
@@ -534,6 +616,7 @@ __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubSta
   if (st.status == kDisrupted) return;
   int id0 = ids[st.slot_base];
   float4 x0 = pos[id0], v0 = vel[id0];
+  const float4 xo = pos[cfg.periodic ? st.origin_id : id0];
   if (st.nbound == 1)
   {
     st.ref_vel[0] = v0.x; st.ref_vel[1] = v0.y; st.ref_vel[2] = v0.z;
@@ -545,7 +628,7 @@ __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubSta
     double msum = st.sums[0];
     st.mbound = (float)msum;
     for (int j = 0; j < 3; j++) st.ref_vel[j] = (float)(st.sums[1 + j] / msum);
-    double o[3] = {(double)x0.x, (double)x0.y, (double)x0.z};
+    double o[3] = {(double)xo.x, (double)xo.y, (double)xo.z};
     for (int j = 0; j < 3; j++)
     {
       double s = st.sums[4 + j] / msum;
@@ -765,14 +848,23 @@ static void run_round(Context &c, std::vector<int> &active)
   launch_init_bbox(tr.bbox, nseg, st, c.ls);
   launch_bbox(tr.tpos, tr.ts_seg, (int)S, tr.bbox, st, c.ls);
   build_trees(tr, ar, c.cfg, st, c.ls);
-  int *tmp_ids = ar.alloc<int>(S);
-  sorted_ids_read_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, tr.sperm, (int)S, c.d_ids, tmp_ids);
-  HBT_CHECK_LAUNCH();
-  sorted_ids_write_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, (int)S, tmp_ids, c.d_ids);
-  HBT_CHECK_LAUNCH();
+  int *const rho = c.cfg.periodic ? c.d_rho : nullptr; // reference Elist order, tracked in periodic runs only
   float4 *tgt_pm = ar.alloc<float4>(T);
   int64_t *tgt_slot = ar.alloc<int64_t>(T);
   int *tgt_seg = ar.alloc<int>(T);
+  if (rho)
+  { // a subhalo's first round sees its whole source in the reference's Particles order: rho = identity
+    fill_tgt_seg_kernel<<<grid_for(T), kBlock, 0, st>>>(d_tgt_off, nseg, (int)T, tgt_seg);
+    HBT_CHECK_LAUNCH();
+    rho_init_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_subs, rho);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches += 2;
+  }
+  int *tmp_ids = ar.alloc<int>(S), *tmp_rho_s = rho ? ar.alloc<int>(S) : nullptr;
+  sorted_ids_read_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, tr.sperm, (int)S, c.d_ids, tmp_ids, rho, tmp_rho_s);
+  HBT_CHECK_LAUNCH();
+  sorted_ids_write_kernel<<<grid_for(S), kBlock, 0, st>>>(d_segs, tr.ts_seg, (int)S, tmp_ids, c.d_ids, tmp_rho_s, rho);
+  HBT_CHECK_LAUNCH();
   targets_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, d_tgt_off, nseg, (int)T, tr.spos, c.d_ids, c.d_pos, tgt_pm, tgt_slot, tgt_seg);
   HBT_CHECK_LAUNCH();
   pre_walk_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.cfg);
@@ -811,13 +903,15 @@ static void run_round(Context &c, std::vector<int> &active)
   // partition + E-sorts in one radix sort
   uint64_t *key_a = ar.alloc<uint64_t>(T), *key_b = ar.alloc<uint64_t>(T);
   int *val_a = ar.alloc<int>(T), *val_b = ar.alloc<int>(T);
-  int *bscan = nullptr, *fpos = nullptr;
-  if (any_hoare)
+  int *bscan = nullptr, *fpos = nullptr, *rho_new = nullptr;
+  if (any_hoare || rho)
   {
     int *uflag = ar.alloc<int>(T), *bflag = ar.alloc<int>(T), *uscan = ar.alloc<int>(T);
     bscan = ar.alloc<int>(T);
     fpos = ar.alloc<int>(T);
-    hoare_flags_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, uflag, bflag);
+    hoare_clear_kernel<<<grid_for(T), kBlock, 0, st>>>((int)T, uflag, bflag);
+    HBT_CHECK_LAUNCH();
+    hoare_flags_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, rho, uflag, bflag);
     HBT_CHECK_LAUNCH();
     size_t sb = 0;
     HBT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, sb, uflag, uscan, (int)T, st));
@@ -826,9 +920,16 @@ static void run_round(Context &c, std::vector<int> &active)
     HBT_CUDA(cub::DeviceScan::InclusiveSum(stmp, sb, bflag, bscan, (int)T, st));
     hoare_fpos_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, uflag, uscan, fpos);
     HBT_CHECK_LAUNCH();
-    c.ls.launches += 6;
+    c.ls.launches += 7;
+    if (rho)
+    {
+      rho_new = ar.alloc<int>(T);
+      rho_update_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, c.d_ids, bscan, fpos, rho, rho_new);
+      HBT_CHECK_LAUNCH();
+      c.ls.launches++;
+    }
   }
-  sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, bscan, fpos, key_a, val_a);
+  sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, bscan, fpos, rho, key_a, val_a);
   HBT_CHECK_LAUNCH();
   c.ls.launches += 3;
   {
@@ -841,11 +942,11 @@ static void run_round(Context &c, std::vector<int> &active)
     void *tmp = ar.alloc<char>((int64_t)tb);
     HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)T, 0, bits, st));
     c.ls.launches += 1 + (bits + 7) / 8;
-    int *tmp_id = ar.alloc<int>(T);
+    int *tmp_id = ar.alloc<int>(T), *tmp_rho = rho ? ar.alloc<int>(T) : nullptr;
     float *tmp_E = ar.alloc<float>(T);
-    permute_read_kernel<<<grid_for(T), kBlock, 0, st>>>(dv.Current(), tgt_slot, (int)T, c.d_ids, c.d_E, tmp_id, tmp_E);
+    permute_read_kernel<<<grid_for(T), kBlock, 0, st>>>(dv.Current(), tgt_slot, (int)T, c.d_ids, c.d_E, tmp_id, tmp_E, rho_new, tmp_rho);
     HBT_CHECK_LAUNCH();
-    permute_write_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_slot, (int)T, tmp_id, tmp_E, c.d_ids, c.d_E);
+    permute_write_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_slot, (int)T, tmp_id, tmp_E, c.d_ids, c.d_E, d_segs, tgt_seg, tmp_rho, rho);
     HBT_CHECK_LAUNCH();
     c.ls.launches += 2;
   }

@@ -117,20 +117,24 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
 // Per-lane pre-order walk of the node range [first, pend): 32 nodes at a time are staged in the warp's shared-memory
 // tile by one coalesced 16 B + 8 B load per lane (the node arrays are padded by 32 entries); a tile is walked with the
 // fast pass and redone exactly if some lane met a softened pair.  Target k of a lane takes part from node skip[k] on.
-template <int T, bool PERIODIC, bool COUNT>
+template <int T, bool PERIODIC, bool COUNT, bool PRELOADED = false>
 __device__ __forceinline__ void walk_range(const float4 *__restrict__ node_xm, const float2 *__restrict__ node_aux, TileNode *tile, int first,
                                            int pend, const float (&px)[T], const float (&py)[T], const float (&pz)[T], int (&skip)[T],
-                                           double (&accd)[T], const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis)
-{
+                                           double (&accd)[T], const DevConfig &cfg, float h2, float hinv, unsigned &n_acc, unsigned &n_vis,
+                                           float4 xm0 = float4(), float2 ax0 = float2())
+{ // PRELOADED: the caller already loaded node first+lane into (xm0, ax0) (prefetched while it did other work)
   const int lane = threadIdx.x & 31;
   int no = first;
+  bool pre = PRELOADED;
   while (no < pend)
   {
     const int tile_base = no;
     const int tile_lim = min(no + 32, pend);
     {
-      const float4 xm = __ldg(&node_xm[no + lane]);
-      const float2 ax = __ldg(&node_aux[no + lane]);
+      float4 xm;
+      float2 ax;
+      if (pre) { xm = xm0; ax = ax0; pre = false; }
+      else { xm = __ldg(&node_xm[no + lane]); ax = __ldg(&node_aux[no + lane]); }
       __syncwarp();
       tile[lane].xm = xm;
       *reinterpret_cast<float2 *>(&tile[lane].lenq) = ax;

@@ -29,7 +29,7 @@ namespace hbt
 {
 
 static constexpr int kGW = 4;      // warps per CTA (warps are independent)
-static constexpr int kWork = 768;  // ints per warp: chain stack (bottom, int pairs) + MIXED list (top, grows down)
+static constexpr int kWork = 768;  // ints per warp: chain stack (bottom) + MIXED list (top, grows down), both (node, end) pairs
 
 struct GroupSmem
 {
@@ -212,20 +212,30 @@ __global__ void __launch_bounds__(kGW * 32) walk_group_kernel(const WalkArgs a, 
     const int room = mtop - 2 * ncs;
     if (mtop < kWork && (ncs == 0 || room < 16 * 32))
     {
-      for (int i = kWork - 1; i >= mtop; i--)
+      // entries are (node, end) pairs; the first tile of the next entry is prefetched while the current one is walked
+      float4 nxm = __ldg(&a.node_xm[sm.work[kWork - 2] + lane]);
+      float2 nax = __ldg(&a.node_aux[sm.work[kWork - 2] + lane]);
+      for (int i = kWork - 2; i >= mtop; i -= 2)
       {
-        const int no = sm.work[i];
-        const int ne = __float_as_int(__ldg(&a.node_aux[no]).y);
+        const int no = sm.work[i], ne = sm.work[i + 1];
+        const float4 xm0 = nxm;
+        const float2 ax0 = nax;
+        if (i - 2 >= mtop)
+        {
+          const int nn = sm.work[i - 2];
+          nxm = __ldg(&a.node_xm[nn + lane]);
+          nax = __ldg(&a.node_aux[nn + lane]);
+        }
         int skip[T];
 #pragma unroll
         for (int k = 0; k < T; k++) skip[k] = valid[k] ? no : 0x7fffffff;
-        walk_range<T, PERIODIC, COUNT>(a.node_xm, a.node_aux, sm.tile, no, ne, px, py, pz, skip, accd, cfg, h2, hinv, n_acc, n_vis);
+        walk_range<T, PERIODIC, COUNT, true>(a.node_xm, a.node_aux, sm.tile, no, ne, px, py, pz, skip, accd, cfg, h2, hinv, n_acc, n_vis, xm0, ax0);
       }
       mtop = kWork;
       __syncwarp();
     }
     if (ncs == 0) break;
-    const int take = min(min(32, ncs), max(1, (mtop - 2 * ncs) >> 4));
+    const int take = min(min(32, ncs), max(1, (mtop - 2 * ncs) >> 4)); // a chain has <= 8 children, each queues one pair
     ncs -= take;
     int cur = 0, pend = 0;
     if (lane < take)
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(kGW * 32) walk_group_kernel(const WalkArgs a, 
       na += __popc(mA);
       nc += __popc(mC);
       const int cO = __popc(mO), cM = __popc(mM);
-      if (2 * (ncs + cO) > mtop - cM)
+      if (2 * (ncs + cO) > mtop - 2 * cM)
       { // stacks exhausted (pathologically deep tree): redo this group with the per-lane walk from scratch
         overflow = true;
         break;
@@ -289,9 +299,14 @@ __global__ void __launch_bounds__(kGW * 32) walk_group_kernel(const WalkArgs a, 
         sm.work[2 * s] = cur + 1;
         sm.work[2 * s + 1] = kend;
       }
-      if (cls == 4) sm.work[mtop - 1 - __popc(mM & lt)] = cur;
+      if (cls == 4)
+      {
+        const int s = mtop - 2 - 2 * __popc(mM & lt);
+        sm.work[s] = cur;
+        sm.work[s + 1] = kend;
+      }
       ncs += cO;
-      mtop -= cM;
+      mtop -= 2 * cM;
       __syncwarp();
       if (na >= 32)
       {

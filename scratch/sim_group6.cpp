@@ -3,7 +3,7 @@
 #define main main_unused
 #include "sim_group.cpp"
 #undef main
-struct Cost { double A = 0, Aint = 0, iters = 0, nM = 0, dfs = 0, dfsint = 0, dfssteps = 0, tiles = 0; };
+struct Cost { double slices = 0, slices_sticky = 0; double A = 0, Aint = 0, iters = 0, nM = 0, dfs = 0, dfsint = 0, dfssteps = 0, tiles = 0; };
 static float g_h2;
 static void sub_dfs(int b, int e, const float *tg, int n, Cost &c)
 {
@@ -11,11 +11,11 @@ static void sub_dfs(int b, int e, const float *tg, int n, Cost &c)
   while (no < e)
   {
     if (no >= tile_base + 32) { tile_base = no; c.tiles++; }
-    const Node &nd = nodes[no]; bool any_open = false;
-    for (int q = 0; q < n; q++) { if (no < skip[q]) continue;
+    const Node &nd = nodes[no]; bool any_open = false; unsigned sl = 0;
+    for (int q = 0; q < n; q++) { if (no < skip[q]) continue; sl |= 1u << (q / 32);
       float dx = nd.x - tg[4 * q], dy = nd.y - tg[4 * q + 1], dz = nd.z - tg[4 * q + 2]; float r2 = dx * dx + dy * dy + dz * dz;
       if (nd.lenq > r2) any_open = true; else { skip[q] = nd.end; c.dfsint++; } }
-    c.dfs += 13.0 * Tp + 15; c.dfssteps++;
+    c.dfs += 13.0 * Tp + 15; c.dfssteps++; c.slices += __builtin_popcount(sl);
     no = any_open ? no + 1 : nd.end;
   }
 }
@@ -74,7 +74,7 @@ int main(int argc, char **argv)
       }
       double inter = c.Aint + c.dfsint; double CIT = 80 + 25 * NB;
       double cost = c.A + c.iters * CIT + c.dfs + c.tiles * 40;
-      printf("G=%3d boxes=%d: inter/target %.0f | inter share A %.2f dfs %.2f | cost share A %.2f iters %.2f dfs %.2f tiles %.2f | per warp: iters %.0f nM %.0f dfssteps %.0f tiles %.0f dfs lane-util %.2f | slots per 32 inter %.1f\n", G, NB, inter / tot,
+      printf("[active slices/step %.2f of %d] G=%3d boxes=%d: inter/target %.0f | inter share A %.2f dfs %.2f | cost share A %.2f iters %.2f dfs %.2f tiles %.2f | per warp: iters %.0f nM %.0f dfssteps %.0f tiles %.0f dfs lane-util %.2f | slots per 32 inter %.1f\n", c.slices / c.dfssteps, T, G, NB, inter / tot,
              c.Aint / inter, c.dfsint / inter, c.A / cost, c.iters * CIT / cost, c.dfs / cost, c.tiles * 40 / cost, c.iters / ngroups, c.nM / ngroups, c.dfssteps / ngroups, c.tiles / ngroups, c.dfsint / (c.dfssteps * G), cost / (inter / 32));
     }
   return 0;

@@ -65,7 +65,7 @@ def test_cfg3_box_of_groups(make_ctx, oracle_lib):
     ctx = make_ctx(p)
     got = ctx.unbind_batch(e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE)
     want = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE)
-    check_batch(snap, got, want, box=62.5)
+    check_batch(snap, got, want)
 
 
 def test_cfg1_snapshot_series(make_ctx, oracle_lib):
@@ -84,7 +84,7 @@ def test_cfg1_snapshot_series(make_ctx, oracle_lib):
         e = capi.make_epoch(a, snapshot_index=10 + k)
         got = ctx.unbind_batch(e, snap_g, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE)
         want = po.run_batch(oracle_lib, "hbto", p, e, snap_o, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE)
-        check_batch(snap_o, got, want, exact_frames=(k == 0), box=62.5)
+        check_batch(snap_o, got, want, exact_frames=(k == 0))
         snap_g = next_snapshot(snap_g, got, 62.5)
         snap_o = next_snapshot(snap_o, want, 62.5)
         if not np.array_equal(snap_g.part_offset, snap_o.part_offset):
