@@ -38,15 +38,16 @@ def make_ctx():
         c.close()
 
 
-def check_batch(snap, got, want, exact_frames=True, exact_counts=False, box=None):
+def check_batch(snap, got, want, exact_frames=True, exact_counts=False):
     """The north-star gates.  Survival (Nbound > 1, death/sink flags: what subhalo counts and track IDs depend on) must be
     bit-exact; bound mass within 0.1 %; membership Jaccard >= 0.999.  A particle whose |E| is within fp32 round-off of 0
     may flip (observed: ~1 per 1e6 particle evaluations), so Nbound itself is compared to 2e-4 unless exact_counts is
     asked for (the golden fixtures, where no flip occurs).  A subhalo of < 2000 particles cannot lose one particle and
     keep Jaccard >= 0.999, so for those a flip of <= 2 particles is tolerated in at most 0.2 % of the subhaloes; the mass
     gate is applied to subhaloes with unchanged Nbound and to all subhaloes above 2000 particles.
-    ``box``: periodic runs - average positions are compared modulo the box (the image depends on which
-    particle is first in the Elist, src/subhalo_unbind.cpp:152-154)."""
+    Average positions are compared as they are, NOT modulo the box: in periodic runs the image the reference reports
+    depends on which particle its hole-based partition leaves in Elist[0] (src/subhalo_unbind.cpp:21-58,152-154), and the
+    library tracks exactly that (unbind_batch.cu, rho_*)."""
     skip = cases.unbound_inputs(snap)
     for f in ("snapshot_index_of_death", "snapshot_index_of_sink", "sink_track_id"):
         assert np.array_equal(got.io[f], want.io[f]), f
@@ -77,9 +78,6 @@ def check_batch(snap, got, want, exact_frames=True, exact_counts=False, box=None
     sel = ~skip & same if not exact_counts else ~skip
     for f in ("avg_pos", "avg_vel", "mostbound_pos", "mostbound_vel"):
         a, b = got.io[f][sel].astype(np.float64), want.io[f][sel].astype(np.float64)
-        if box is not None and f == "avg_pos":
-            d = a - b
-            a = b + (d - box * np.round(d / box))
         if exact_frames:
             assert np.allclose(a, b, rtol=2e-6, atol=1e-6), f
     for f in ("specific_self_potential_energy", "specific_self_kinetic_energy", "specific_angular_momentum"):
