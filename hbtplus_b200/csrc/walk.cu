@@ -263,7 +263,7 @@ struct WalkPolicy
     forced = env("HBTU_WALK_TPL", 0);
     big4 = env("HBTU_WALK_BIG4", 1 << 20);
     big2 = env("HBTU_WALK_BIG2", 1 << 19);
-    group_min = env("HBTU_WALK_GROUP_MIN", 1 << 15); // segments with at least this many targets use the group walk (0 = never)
+    group_min = env("HBTU_WALK_GROUP_MIN", 1 << 13); // segments with at least this many targets use the group walk (0 = never)
     group_t = env("HBTU_WALK_GROUP_T", 4) == 8 ? 8 : 4;
   }
 };
