@@ -107,6 +107,42 @@ def run_cpu(snap, threads: int | None = None):
     return dt, kind, ncpu, int(r.io["nbound"].sum())
 
 
+def bench_profile_row(ctx, e, snap, res, csnap, peaks):
+    """SURVEY.md 8(f) next-2, measured beside the headline: Subhalo_t::CalculateProfileProperties + CalculateShape
+    (src/subhalo.cpp:242-398) of every subhalo of the step through hbtu_profile_batch, HBM roofline, and the reference's
+    own functions (oracle/_ref) on the bound lists of the CPU sample."""
+    from oracle import pyoracle as po
+    import cases_bench
+
+    part_offset, pm, io = cases_bench.profile_inputs(snap, res)
+    nb = int(np.where(io["nbound"] > 1, io["nbound"], 0).sum())
+    t_e2e, t_k = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.profile_batch(e, part_offset, pm, io)
+        t_e2e.append(time.perf_counter() - t0)
+        t_k.append(ctx.stats().execute_ms * 1e-3)
+    # algorithmic bytes per bound particle (DESIGN.md section 9): radius/shape 16 B read + 12 B key/index write; sort 12 + 12;
+    # cumulative mass 12 + 4 (mass gather) read + 8 write; select 8 + 8 read
+    bytes_per = 16 + 12 + 24 + 24 + 16
+    row = {"bound_particles": nb, "subhaloes": int(snap.nsub), "kernel_ms": float(np.min(t_k)) * 1e3, "e2e_ms": float(np.min(t_e2e)) * 1e3,
+           "value": nb / float(np.min(t_k)), "e2e_value": nb / float(np.min(t_e2e)), "unit": "bound particles/s",
+           "roofline": {"bound": "hbm", "achieved": bytes_per * nb / float(np.min(t_k)) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                        "frac": bytes_per * nb / float(np.min(t_k)) / 1e9 / peaks.get("hbm_gbs", 6650.0), "bytes_per_particle": bytes_per}}
+    if po.have_ref():
+        ref = po.load_ref()
+        ref.hbtref_set_num_threads(os.cpu_count() or 1)
+        cres = po.run_batch(ref, "hbtref", params_for(), e, csnap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE, want_energy=False)
+        cpo, cpm, cio = cases_bench.profile_inputs(csnap, cres)
+        t0 = time.perf_counter()
+        po.profile_batch(ref, "hbtref", params_for(), e, cpo, cpm, cio)
+        dt = time.perf_counter() - t0
+        cnb = int(np.where(cio["nbound"] > 1, cio["nbound"], 0).sum())
+        row["cpu_baseline"] = {"value": cnb / dt, "unit": "bound particles/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                               "sample": f"bound lists of the unbinding CPU sample ({cnb} bound particles, {csnap.nsub} subhaloes)", "seconds": dt}
+    return row
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -323,6 +359,7 @@ def main():
             csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
             dt, kind, ncpu, _ = run_cpu(csnap)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
+            out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks)}
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:

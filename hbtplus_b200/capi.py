@@ -125,6 +125,49 @@ SUBIO_DTYPE = np.dtype(
 assert SUBIO_DTYPE.itemsize == C.sizeof(SubIO), (SUBIO_DTYPE.itemsize, C.sizeof(SubIO))
 
 
+class ProfileIO(C.Structure):
+    _fields_ = [
+        ("mostbound_pos", C.c_double * 3),
+        ("nbound", C.c_int64),
+        ("mbound", C.c_float),
+        ("rmax_comoving", C.c_float),
+        ("vmax_physical", C.c_float),
+        ("last_max_vmax_physical", C.c_float),
+        ("snapshot_index_of_last_max_vmax", C.c_int32),
+        ("r2sigma_comoving", C.c_float),
+        ("rhalf_comoving", C.c_float),
+        ("bound_r200crit_comoving", C.c_float),
+        ("bound_m200crit", C.c_float),
+        ("inertial_tensor", C.c_float * 6),
+        ("inertial_tensor_weighted", C.c_float * 6),
+        ("reserved", C.c_int32),
+    ]
+
+
+#: numpy view of ProfileIO (hbtu_profile_io: Subhalo_t::CalculateProfileProperties / CalculateShape, src/subhalo.cpp:242-398)
+PROFILEIO_DTYPE = np.dtype(
+    [
+        ("mostbound_pos", "<f8", 3),
+        ("nbound", "<i8"),
+        ("mbound", "<f4"),
+        ("rmax_comoving", "<f4"),
+        ("vmax_physical", "<f4"),
+        ("last_max_vmax_physical", "<f4"),
+        ("snapshot_index_of_last_max_vmax", "<i4"),
+        ("r2sigma_comoving", "<f4"),
+        ("rhalf_comoving", "<f4"),
+        ("bound_r200crit_comoving", "<f4"),
+        ("bound_m200crit", "<f4"),
+        ("inertial_tensor", "<f4", 6),
+        ("inertial_tensor_weighted", "<f4", 6),
+        ("reserved", "<i4"),
+    ],
+    align=True,
+)
+assert PROFILEIO_DTYPE.itemsize == C.sizeof(ProfileIO), (PROFILEIO_DTYPE.itemsize, C.sizeof(ProfileIO))
+PROFILE_ARGTYPES = [C.POINTER(Epoch), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(ProfileIO)]
+
+
 def f32(x: float) -> float:
     """Round to HBTReal=float, as the reference stores every Parameter_t real (V32 build)."""
     return float(np.float32(x))
@@ -235,7 +278,9 @@ EXPORTS = [
     "hbtu_execute",
     "hbtu_fetch",
     "hbtu_tree_potential",
+    "hbtu_profile_batch",
     "hbtu_get_stats",
+    "hbtu_set_counting",
 ]
 
 
@@ -292,6 +337,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hbtu_fetch.restype = C.c_int
     lib.hbtu_tree_potential.argtypes = [C.c_void_p] + POTENTIAL_ARGTYPES
     lib.hbtu_tree_potential.restype = C.c_int
+    lib.hbtu_profile_batch.argtypes = [C.c_void_p] + PROFILE_ARGTYPES
+    lib.hbtu_profile_batch.restype = C.c_int
     lib.hbtu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.hbtu_get_stats.restype = C.c_int
     return lib

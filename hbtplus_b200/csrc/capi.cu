@@ -466,6 +466,12 @@ int hbtu_tree_potential(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsrc, co
   });
 }
 
+int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+                       hbtu_profile_io *io)
+{
+  return guarded(ctx, [&](Context &c) { profile_batch(c, epoch, nsub, part_offset, pos_mass, io); });
+}
+
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out)
 {
   if (!ctx || !out) return HBTU_ERR_INVALID;

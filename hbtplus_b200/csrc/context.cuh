@@ -56,6 +56,8 @@ struct Context
 };
 
 void execute_batch(Context &c);
+// profile.cu: Subhalo_t::CalculateProfileProperties + CalculateShape for a batch of particle lists
+void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io);
 void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out);
 
 } // namespace hbt

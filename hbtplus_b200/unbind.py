@@ -111,6 +111,18 @@ class UnbindContext:
         self._check(rc)
         return BatchResult(io, order_offset, order, energy)
 
+    # -- Subhalo_t::CalculateProfileProperties + CalculateShape (src/subhalo.cpp:242-398) --------------
+    def profile_batch(self, epoch, part_offset, pos_mass, io) -> np.ndarray:
+        """``io``: structured array (capi.PROFILEIO_DTYPE) with the [in]/[io] fields set; returns the updated copy."""
+        out = np.ascontiguousarray(io, capi.PROFILEIO_DTYPE).copy()
+        po = np.ascontiguousarray(part_offset, np.int64)
+        pm = np.ascontiguousarray(pos_mass, np.float32)
+        P = capi._ptr
+        rc = self._lib.hbtu_profile_batch(self._ctx, C.byref(epoch), len(po) - 1, P(po, C.c_int64), P(pm, C.c_float),
+                                          out.ctypes.data_as(C.POINTER(capi.ProfileIO)))
+        self._check(rc)
+        return out
+
     # -- GravityTree_t::Build + EvaluatePotential / BindingEnergy -------------------------------------
     def tree_potential(self, epoch, src_pos_mass, tgt_pos, self_mass=None, tgt_vel=None, ref_pos=None, ref_vel=None) -> np.ndarray:
         src = np.ascontiguousarray(src_pos_mass, np.float32)

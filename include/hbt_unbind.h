@@ -168,6 +168,39 @@ int hbtu_tree_potential(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsrc, co
                         int64_t ntgt, const float *tgt_pos, const float *tgt_self_mass,
                         const float *tgt_vel, const double *ref_pos, const double *ref_vel, double *out);
 
+
+/* ---------------------------------------------------------------------------------------------------
+ * Post-unbinding per-subhalo properties: the step right after the path in
+ * SubhaloSnapshot_t::UpdateTracks (src/subhalo_tracking.cpp:901-906),
+ *   void Subhalo_t::CalculateProfileProperties(const Snapshot_t&)   src/subhalo.h:124, src/subhalo.cpp:242-332
+ *   void Subhalo_t::CalculateShape()                                src/subhalo.h:125, src/subhalo.cpp:334-398
+ * with Snapshot_t::SphericalOverdensitySize (src/snapshot.cpp:264-281, virial factor c200 = 200 of
+ * HaloVirialFactors, :328-336) and PeriodicDistance (src/config_parser.h:143-156).
+ * The eigen-vectors (EigenAxis, HAS_GSL builds only) stay on the host: they are a 3x3 problem per subhalo. */
+typedef struct hbtu_profile_io
+{
+  double mostbound_pos[3];                 /* [in]  ComovingMostBoundPosition (centre of the profile)        */
+  int64_t nbound;                          /* [in]  Nbound: the first nbound particles of the list are used  */
+  float mbound;                            /* [in]  Mbound (normalises the inertia tensors, :391-392)        */
+  float rmax_comoving;                     /* [out] RmaxComoving                                             */
+  float vmax_physical;                     /* [out] VmaxPhysical                                             */
+  float last_max_vmax_physical;            /* [io]  LastMaxVmaxPhysical                                      */
+  int32_t snapshot_index_of_last_max_vmax; /* [io]  SnapshotIndexOfLastMaxVmax                               */
+  float r2sigma_comoving;                  /* [out] R2SigmaComoving                                          */
+  float rhalf_comoving;                    /* [out] RHalfComoving                                            */
+  float bound_r200crit_comoving;           /* [io]  BoundR200CritComoving: untouched when no radius encloses 200 rho_crit */
+  float bound_m200crit;                    /* [io]  BoundM200Crit                                            */
+  float inertial_tensor[6];                /* [out] InertialTensor {xx,xy,xz,yy,yz,zz}                        */
+  float inertial_tensor_weighted[6];       /* [out] InertialTensorWeighted                                   */
+  int32_t reserved;
+} hbtu_profile_io;
+
+/*  part_offset[nsub+1]  subhalo s's particle list (bound particles first, Particles[0] = most bound) is
+ *                       pos_mass[part_offset[s] .. part_offset[s+1]); only the first io[s].nbound are read
+ *  pos_mass[4*N]        x,y,z (comoving), mass (HOST memory)                                                  */
+int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                       const float *pos_mass, hbtu_profile_io *io);
+
 /* Counters of the last hbtu_execute / hbtu_tree_potential (for bench.py's roofline and
  * gpu_launches fields). */
 typedef struct hbtu_stats

@@ -1,0 +1,15 @@
+// hbt_b200.h - the one declaration a maintainer adds to HBT+ to use the batched post-unbinding properties.
+//
+// src/subhalo_tracking.cpp:901-906 of the reference reads
+//     #pragma omp parallel for if(ParallelizeHaloes)
+//     for(HBTInt i=0;i<Subhalos.size();i++)
+//     {
+//       Subhalos[i].CalculateProfileProperties(*this);
+//       Subhalos[i].CalculateShape();
+//     }
+// and becomes
+//     HBT_B200_CalculateProperties(Subhalos, *this);
+// (defined in integration/subhalo_unbind_b200.cpp on top of hbtu_profile_batch, include/hbt_unbind.h).
+#pragma once
+#include "subhalo.h"
+void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch);

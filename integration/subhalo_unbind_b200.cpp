@@ -276,3 +276,73 @@ void SubhaloSnapshot_t::RefineParticles()
   for (size_t i = 0; i < Subhalos.size(); i++)
     if (!done[i]) Subhalos[i].TruncateSource();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Post-unbinding properties.  The reference computes them one subhalo at a time at
+// the end of SubhaloSnapshot_t::UpdateTracks (src/subhalo_tracking.cpp:901-906):
+//     for(i...) { Subhalos[i].CalculateProfileProperties(*this); Subhalos[i].CalculateShape(); }
+// Those two members live in src/subhalo.cpp, which is NOT replaced; the maintainer swaps that loop for one call of
+//     HBT_B200_CalculateProperties(Subhalos, *this);        // declared in integration/hbt_b200.h
+// which packs the bound part of every particle list, calls hbtu_profile_batch and writes the same members back.
+// The eigen-vectors (EigenAxis, HAS_GSL builds, src/subhalo.cpp:393-396) are a 3x3 problem per subhalo and stay on
+// the host, computed from the tensors returned here.
+void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch)
+{
+  const int64_t nsub = Subhalos.size();
+  if (nsub == 0) return;
+  std::vector<int64_t> part_offset(nsub + 1, 0);
+  for (int64_t s = 0; s < nsub; s++)
+  { // only the bound particles are read (Nbound <= 1: nothing is, the outputs are zeroed)
+    const int64_t nb = Subhalos[s].Nbound > 1 ? (int64_t)Subhalos[s].Nbound : 0;
+    part_offset[s + 1] = part_offset[s] + nb;
+  }
+  std::vector<float> pos_mass(4 * (size_t)part_offset[nsub]);
+  std::vector<hbtu_profile_io> io(nsub);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    const Subhalo_t &sub = Subhalos[s];
+    const int64_t b = part_offset[s], nb = part_offset[s + 1] - b;
+    for (int64_t i = 0; i < nb; i++)
+    {
+      const Particle_t &p = sub.Particles[i];
+      float *x = &pos_mass[4 * (b + i)];
+      x[0] = p.ComovingPosition[0]; x[1] = p.ComovingPosition[1]; x[2] = p.ComovingPosition[2]; x[3] = p.Mass;
+    }
+    hbtu_profile_io &o = io[s];
+    std::memset(&o, 0, sizeof(o));
+    for (int j = 0; j < 3; j++) o.mostbound_pos[j] = sub.ComovingMostBoundPosition[j];
+    o.nbound = nb; // 0 or Nbound
+    o.mbound = sub.Mbound;
+    o.last_max_vmax_physical = sub.LastMaxVmaxPhysical;
+    o.snapshot_index_of_last_max_vmax = sub.SnapshotIndexOfLastMaxVmax;
+    o.bound_r200crit_comoving = sub.BoundR200CritComoving;
+    o.bound_m200crit = sub.BoundM200Crit;
+  }
+  hbtu_ctx *ctx = context();
+  hbtu_epoch e;
+  e.scale_factor = epoch.Cosmology.ScaleFactor;
+  e.hz = epoch.Cosmology.Hz;
+  e.snapshot_index = epoch.GetSnapshotIndex();
+  e.reserved = 0;
+  int rc = hbtu_profile_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), io.data());
+  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_profile_batch failed: ") + hbtu_last_error(ctx));
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalo_t &sub = Subhalos[s];
+    const hbtu_profile_io &o = io[s];
+    sub.RmaxComoving = o.rmax_comoving;
+    sub.VmaxPhysical = o.vmax_physical;
+    sub.LastMaxVmaxPhysical = o.last_max_vmax_physical;
+    sub.SnapshotIndexOfLastMaxVmax = o.snapshot_index_of_last_max_vmax;
+    sub.R2SigmaComoving = o.r2sigma_comoving;
+    sub.RHalfComoving = o.rhalf_comoving;
+    sub.BoundR200CritComoving = o.bound_r200crit_comoving;
+    sub.BoundM200Crit = o.bound_m200crit;
+    for (int j = 0; j < 6; j++)
+    {
+      sub.InertialTensor[j] = o.inertial_tensor[j];
+      sub.InertialTensorWeighted[j] = o.inertial_tensor_weighted[j];
+    }
+  }
+}

@@ -1025,3 +1025,140 @@ int hbto_walk_counts(const hbtu_params *params, const hbtu_epoch *epoch, int64_t
   free(P);
   return ncell;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Post-unbinding properties: Subhalo_t::CalculateProfileProperties
+ * (src/subhalo.cpp:242-332) and Subhalo_t::CalculateShape (src/subhalo.cpp:334-398).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct
+{ /* RadMassVel_t, src/snapshot.h:41-49 */
+  HBTReal r, m, v;
+} RadMassVel;
+
+static int comp_prof_radius(const void *a, const void *b)
+{ /* CompProfRadius, src/subhalo.cpp:233-236 (std::sort is unstable: ties carry equal r) */
+  const HBTReal x = ((const RadMassVel *)a)->r, y = ((const RadMassVel *)b)->r;
+  return (x > y) - (x < y);
+}
+
+static HBTReal periodic_distance(const Config *c, const HBTReal x[3], const HBTReal y[3])
+{ /* PeriodicDistance, src/config_parser.h:143-156: HBTReal differences, NEAREST, sqrt of the HBTReal sum */
+  HBTReal dx[3];
+  for (int j = 0; j < 3; j++)
+  {
+    dx[j] = x[j] - y[j];
+    if (c->Periodic) dx[j] = nearest_f(c, dx[j]);
+  }
+  return sqrtf(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+}
+
+static void profile_properties(const Config *c, const float *pm, hbtu_profile_io *o)
+{ /* src/subhalo.cpp:242-332; pm = the subhalo's particle list (x,y,z,m per particle) */
+  const HBTInt Nbound = (HBTInt)o->nbound;
+  if (Nbound <= 1)
+  { /* :265-286 */
+    o->rmax_comoving = 0.f;
+    o->vmax_physical = 0.f;
+    o->r2sigma_comoving = 0.f;
+    o->rhalf_comoving = 0.f;
+    o->bound_r200crit_comoving = 0.f;
+    o->bound_m200crit = 0.f;
+    return;
+  }
+  const HBTReal VelocityUnit = c->G / c->ScaleFactor; /* :287 */
+  const HBTReal cen[3] = {(HBTReal)o->mostbound_pos[0], (HBTReal)o->mostbound_pos[1], (HBTReal)o->mostbound_pos[2]};
+  RadMassVel *prof = (RadMassVel *)malloc(sizeof(RadMassVel) * (size_t)Nbound);
+  for (HBTInt i = 0; i < Nbound; i++)
+  { /* :290-294 */
+    prof[i].r = periodic_distance(c, cen, &pm[4 * (size_t)i]);
+    prof[i].m = pm[4 * (size_t)i + 3];
+  }
+  qsort(prof, (size_t)Nbound, sizeof(RadMassVel), comp_prof_radius); /* :297 */
+  double m_cum = 0.;
+  for (HBTInt i = 0; i < Nbound; i++) prof[i].m = (HBTReal)(m_cum += prof[i].m); /* :298-299 */
+  for (HBTInt i = 0; i < Nbound; i++)
+  { /* :302-306 */
+    if (prof[i].r < c->SofteningHalo) prof[i].r = c->SofteningHalo;
+    prof[i].v = prof[i].m / prof[i].r;
+  }
+  HBTInt imax = 0; /* max_element: first of the largest, :308 */
+  for (HBTInt i = 1; i < Nbound; i++)
+    if (prof[imax].v < prof[i].v) imax = i;
+  o->rmax_comoving = prof[imax].r;
+  o->vmax_physical = sqrtf(prof[imax].v * VelocityUnit);
+  o->rhalf_comoving = prof[Nbound / 2].r;
+  o->r2sigma_comoving = prof[(HBTInt)(Nbound * 0.955)].r;
+  /* HaloVirialFactors: virialF_c200 = 200 (src/snapshot.cpp:334); SphericalOverdensitySize(prof), :264-281 */
+  const HBTReal VirialFactor = 200.f;
+  const HBTReal RhoVirial =
+      (HBTReal)(VirialFactor * c->Hz * c->Hz / 2.0 / c->G * c->ScaleFactor * c->ScaleFactor * c->ScaleFactor);
+  for (HBTInt i = Nbound - 1; i >= 0; i--)
+  {
+    const HBTReal r = prof[i].r, m = prof[i].m;
+    if (m > RhoVirial * r * r * r)
+    {
+      o->bound_m200crit = m;
+      o->bound_r200crit_comoving = (float)pow(m / RhoVirial, 1.0 / 3);
+      break;
+    }
+  }
+  if (o->vmax_physical >= o->last_max_vmax_physical)
+  { /* :322-326 */
+    o->snapshot_index_of_last_max_vmax = c->SnapshotIndex;
+    o->last_max_vmax_physical = o->vmax_physical;
+  }
+  free(prof);
+}
+
+static void shape(const Config *c, const float *pm, hbtu_profile_io *o)
+{ /* src/subhalo.cpp:334-398 (without the HAS_GSL eigen-vectors) */
+  const HBTInt Nbound = (HBTInt)o->nbound;
+  if (Nbound <= 1)
+  {
+    for (int j = 0; j < 6; j++) o->inertial_tensor[j] = o->inertial_tensor_weighted[j] = 0.f;
+    return;
+  }
+  const HBTReal cen[3] = {(HBTReal)o->mostbound_pos[0], (HBTReal)o->mostbound_pos[1], (HBTReal)o->mostbound_pos[2]};
+  double I[6] = {0, 0, 0, 0, 0, 0}, Iw[6] = {0, 0, 0, 0, 0, 0}; /* xx, xy, xz, yy, yz, zz */
+  for (HBTInt i = 1; i < Nbound; i++)
+  {
+    const HBTReal m = pm[4 * (size_t)i + 3];
+    HBTReal dx = pm[4 * (size_t)i] - cen[0], dy = pm[4 * (size_t)i + 1] - cen[1], dz = pm[4 * (size_t)i + 2] - cen[2];
+    if (c->Periodic)
+    {
+      dx = nearest_f(c, dx);
+      dy = nearest_f(c, dy);
+      dz = nearest_f(c, dz);
+    }
+    const HBTReal dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
+    I[0] += dx2 * m; I[3] += dy2 * m; I[5] += dz2 * m;
+    I[1] += dx * dy * m; I[2] += dx * dz * m; I[4] += dy * dz * m;
+    HBTReal dr2 = dx2 + dy2 + dz2;
+    dr2 /= m;
+    Iw[0] += dx2 / dr2; Iw[3] += dy2 / dr2; Iw[5] += dz2 / dr2;
+    Iw[1] += dx * dy / dr2; Iw[2] += dx * dz / dr2; Iw[4] += dy * dz / dr2;
+  }
+  for (int j = 0; j < 6; j++)
+  { /* assigned to float, then /= Mbound (float), :389-392 */
+    float a = (float)I[j], b = (float)Iw[j];
+    a /= o->mbound;
+    b /= o->mbound;
+    o->inertial_tensor[j] = a;
+    o->inertial_tensor_weighted[j] = b;
+  }
+}
+
+int hbto_profile_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                       const float *pos_mass, hbtu_profile_io *io)
+{
+  Config c;
+  config_from(&c, params, epoch);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    if (io[s].nbound > part_offset[s + 1] - part_offset[s]) continue; /* caller error; the GPU entry point rejects it */
+    profile_properties(&c, &pos_mass[4 * part_offset[s]], &io[s]);
+    shape(&c, &pos_mass[4 * part_offset[s]], &io[s]);
+  }
+  return HBTU_OK;
+}

@@ -29,6 +29,10 @@ def _bind(lib, prefix):
     tp = getattr(lib, prefix + "_tree_potential")
     tp.argtypes = [C.POINTER(capi.Params)] + capi.POTENTIAL_ARGTYPES
     tp.restype = C.c_int
+    pb = getattr(lib, prefix + "_profile_batch", None)
+    if pb is not None:
+        pb.argtypes = [C.POINTER(capi.Params)] + capi.PROFILE_ARGTYPES
+        pb.restype = C.c_int
     getattr(lib, prefix + "_set_num_threads").argtypes = [C.c_int]
     getattr(lib, prefix + "_get_max_threads").restype = C.c_int
     return lib
@@ -147,3 +151,15 @@ def refine_particles(lib, params, epoch, snap, host_halo_id, n_old, nhalos, mbou
     if rc != 0:
         raise RuntimeError(f"hbtref_refine_particles failed: {rc}")
     return Result(io, order_offset, order, energy)
+
+
+def profile_batch(lib, prefix, params, epoch, part_offset, pos_mass, io):
+    """CalculateProfileProperties + CalculateShape on the CPU checker `lib` (same contract as hbtu_profile_batch)."""
+    out = np.ascontiguousarray(io, capi.PROFILEIO_DTYPE).copy()
+    po = np.ascontiguousarray(part_offset, np.int64)
+    pm = np.ascontiguousarray(pos_mass, np.float32)
+    rc = getattr(lib, prefix + "_profile_batch")(C.byref(params), C.byref(epoch), len(po) - 1, capi._ptr(po, C.c_int64), capi._ptr(pm, C.c_float),
+                                                 out.ctypes.data_as(C.POINTER(capi.ProfileIO)))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_profile_batch failed: {rc}")
+    return out

@@ -26,6 +26,9 @@
 
 #include "hbt_unbind.h"
 
+/* defined by integration/subhalo_unbind_b200.cpp in the drop-in build only */
+void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch) __attribute__((weak));
+
 /* the real body lives in src/io/subhalo_io.cpp, which needs libhdf5 (absent) */
 void SubhaloSnapshot_t::BuildHDFDataType()
 {
@@ -340,6 +343,79 @@ int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, 
     read_subhalo(snap.Subhalos[s], io[s]);
   }
   return write_orders(snap.Subhalos, full, io, order_capacity, order_offset, order_out, energy_out);
+}
+
+/* Subhalo_t::CalculateProfileProperties + CalculateShape of the reference (src/subhalo.cpp:242-398); same contract as
+ * hbtu_profile_batch.  In the drop-in build (libhbtdropin_*.so) the shim's batched replacement of the loop at
+ * src/subhalo_tracking.cpp:901-906 is linked in and used instead of the two member functions. */
+int hbtref_profile_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                         const float *pos_mass, hbtu_profile_io *io)
+{
+  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  apply_params(params);
+  Epoch_t snap;
+  set_epoch(snap, epoch);
+  omp_set_max_active_levels(1);
+  std::vector<Subhalo_t> subs(nsub);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalo_t &sub = subs[s];
+    const int64_t b = part_offset[s], n = part_offset[s + 1] - b;
+    sub.Particles.resize(n);
+    for (int64_t i = 0; i < n; i++)
+    {
+      Particle_t &p = sub.Particles[i];
+      p.Id = (HBTInt)(b + i);
+      for (int j = 0; j < 3; j++)
+      {
+        p.ComovingPosition[j] = pos_mass[4 * (b + i) + j];
+        p.PhysicalVelocity[j] = 0;
+      }
+      p.Mass = pos_mass[4 * (b + i) + 3];
+#ifndef DM_ONLY
+      p.Type = TypeDM;
+#endif
+    }
+    hbtu_profile_io &o = io[s];
+    sub.Nbound = (HBTInt)o.nbound;
+    sub.Mbound = o.mbound;
+    for (int j = 0; j < 3; j++) sub.ComovingMostBoundPosition[j] = o.mostbound_pos[j];
+    sub.LastMaxVmaxPhysical = o.last_max_vmax_physical;
+    sub.SnapshotIndexOfLastMaxVmax = o.snapshot_index_of_last_max_vmax;
+    sub.BoundR200CritComoving = o.bound_r200crit_comoving;
+    sub.BoundM200Crit = o.bound_m200crit;
+  }
+  if (HBT_B200_CalculateProperties)
+    HBT_B200_CalculateProperties(subs, snap);
+  else
+  {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t s = 0; s < nsub; s++)
+    {
+      subs[s].CalculateProfileProperties(snap);
+      subs[s].CalculateShape();
+    }
+  }
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    const Subhalo_t &sub = subs[s];
+    hbtu_profile_io &o = io[s];
+    o.rmax_comoving = sub.RmaxComoving;
+    o.vmax_physical = sub.VmaxPhysical;
+    o.last_max_vmax_physical = sub.LastMaxVmaxPhysical;
+    o.snapshot_index_of_last_max_vmax = sub.SnapshotIndexOfLastMaxVmax;
+    o.r2sigma_comoving = sub.R2SigmaComoving;
+    o.rhalf_comoving = sub.RHalfComoving;
+    o.bound_r200crit_comoving = sub.BoundR200CritComoving;
+    o.bound_m200crit = sub.BoundM200Crit;
+    for (int j = 0; j < 6; j++)
+    {
+      o.inertial_tensor[j] = sub.InertialTensor[j];
+      o.inertial_tensor_weighted[j] = sub.InertialTensorWeighted[j];
+    }
+  }
+  return HBTU_OK;
 }
 
 } // extern "C"

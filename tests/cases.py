@@ -70,3 +70,28 @@ def unbound_inputs(snap):
 def jaccard(a, b) -> float:
     a, b = set(np.asarray(a).tolist()), set(np.asarray(b).tolist())
     return len(a & b) / len(a | b) if (a or b) else 1.0
+
+
+def profile_inputs(snap, res, last_vmax=None, seed=0):
+    """Inputs of CalculateProfileProperties / CalculateShape from an unbinding result: every subhalo's particle list in
+    its new order (bound first), centre = most-bound position, Nbound, Mbound; a previous Vmax record and a previous
+    overdensity size are invented so that the [io] semantics are exercised."""
+    n = res.io["nsource"].astype(np.int64)
+    part_offset = np.zeros(snap.nsub + 1, np.int64)
+    np.cumsum(n, out=part_offset[1:])
+    idx = np.concatenate([res.particles(s) for s in range(snap.nsub)]) if part_offset[-1] else np.zeros(0, np.int64)
+    pm = np.ascontiguousarray(snap.pos_mass[idx])
+    io = np.zeros(snap.nsub, capi.PROFILEIO_DTYPE)
+    io["mostbound_pos"] = res.io["mostbound_pos"]
+    io["nbound"] = res.io["nbound"]
+    io["mbound"] = res.io["mbound"]
+    rng = np.random.default_rng(seed)
+    io["last_max_vmax_physical"] = rng.choice([0.0, 1e9], snap.nsub) if last_vmax is None else last_vmax
+    io["snapshot_index_of_last_max_vmax"] = np.where(io["last_max_vmax_physical"] > 0, 3, -1)
+    io["bound_r200crit_comoving"] = 7.0
+    io["bound_m200crit"] = 11.0
+    return part_offset, pm, io
+
+
+PROFILE_FIELDS = ["rmax_comoving", "vmax_physical", "last_max_vmax_physical", "snapshot_index_of_last_max_vmax", "r2sigma_comoving",
+                  "rhalf_comoving", "bound_r200crit_comoving", "bound_m200crit", "inertial_tensor", "inertial_tensor_weighted"]

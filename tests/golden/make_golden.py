@@ -51,6 +51,11 @@ def main():
         out["be"] = po.tree_potential(ref, "hbtref", p, e, src, tgt, self_mass=tgt[:, 3].copy(), tgt_vel=tv,
                                       ref_pos=snap.io["avg_pos"][s], ref_vel=snap.io["avg_vel"][s])
         out["be_vel"] = tv
+        # Subhalo_t::CalculateProfileProperties + CalculateShape on the truncated result (src/subhalo.cpp:242-398)
+        r = po.Result(out["trunc_io"], out["trunc_order_offset"], out["trunc_order"], out["trunc_energy"])
+        ppo, ppm, pio = cases.profile_inputs(snap, r, seed=len(name))
+        out["prof_part_offset"], out["prof_pos_mass"], out["prof_io_in"] = ppo, ppm, pio
+        out["prof_io"] = po.profile_batch(ref, "hbtref", p, e, ppo, ppm, pio)
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "nbound", out["full_io"]["nbound"])

@@ -53,3 +53,24 @@ def test_refine_particles_drop_in(periodic, variant):
     # the central of halo 0 was fed by its heads (1, 2) and, through them, by 3 and 4
     assert want.io["nsource_full"][0] == 0 or want.io["nsource"][0] >= want.io["nbound"][0]
     assert (want.io["nbound"][[0, 5]] > 1000).all()
+
+
+@pytest.mark.parametrize("variant", ["v32", "v64"])
+def test_profile_properties_drop_in(variant):
+    """SURVEY.md 8(f) next-2 through the reference-facing side: the harness fills the reference's own Subhalo_t objects and
+    calls either Subhalo_t::CalculateProfileProperties/CalculateShape (libhbtref) or the shim's batched replacement of the
+    loop at src/subhalo_tracking.cpp:901-906 (libhbtdropin -> hbtu_profile_batch)."""
+    if not po.have_dropin(variant):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
+    ref.hbtref_set_num_threads(1)
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True)
+    e = capi.make_epoch(0.9, snapshot_index=15)
+    snap, host, n_old, nhalos, mb = snapshot_with_hosts(21, True)
+    res = po.refine_particles(ref, p, e, snap, host, n_old, nhalos, mb)
+    part_offset, pm, io = cases.profile_inputs(snap, res, seed=3)
+    want = po.profile_batch(ref, "hbtref", p, e, part_offset, pm, io)
+    got = po.profile_batch(drop, "hbtref", p, e, part_offset, pm, io)
+    from test_gpu_profile import check_profile
+    check_profile(got, want)
+    assert (want["nbound"] > 1).sum() >= 5

@@ -155,3 +155,51 @@ def test_partition_edge_cases(oracle_lib):
     for s in np.nonzero(nb > 1)[0]:
         en = r.energy[r.order_offset[s]: r.order_offset[s] + nb[s]]
         assert (en < 0).all() and (np.diff(en) >= 0).all()
+
+
+# ---- post-unbinding properties: Subhalo_t::CalculateProfileProperties / CalculateShape ----------
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_profile_matches_golden(oracle_lib, name):
+    """The C restatement against the fixture minted from the unmodified reference (tests/golden/make_golden.py): bit-exact."""
+    p, e, _ = cases.CASES[name]()
+    _, z = load_golden(name)
+    got = po.profile_batch(oracle_lib, "hbto", p, e, z["prof_part_offset"], z["prof_pos_mass"], z["prof_io_in"])
+    want = z["prof_io"]
+    assert (want["nbound"] > 1).sum() >= 2
+    for f in cases.PROFILE_FIELDS:
+        assert np.array_equal(got[f], want[f]), f
+    # the [io] semantics: a previous record larger than Vmax survives, Nbound <= 1 zeroes the overdensity size
+    small = want["nbound"] <= 1
+    assert np.all(want["bound_m200crit"][small] == 0) and np.all(want["rmax_comoving"][small] == 0)
+    kept = z["prof_io_in"]["last_max_vmax_physical"] > 1e8
+    assert np.all(want["snapshot_index_of_last_max_vmax"][kept] == 3)
+    assert np.all(want["snapshot_index_of_last_max_vmax"][~kept & ~small] == e.snapshot_index)
+
+
+def test_oracle_profile_matches_reference_random(oracle_lib, ref_lib):
+    """Fresh random lists through both CPU libraries, incl. unequal masses, a periodic wrap and tiny lists."""
+    rng = np.random.default_rng(77)
+    for periodic in (False, True):
+        p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
+        e = capi.make_epoch(0.6, snapshot_index=17)
+        sizes = [0, 1, 2, 3, 25, 400, 5000]
+        part_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        pm = np.zeros((part_offset[-1], 4), np.float32)
+        io = np.zeros(len(sizes), capi.PROFILEIO_DTYPE)
+        for s, n in enumerate(sizes):
+            c = np.array([0.02, 31.0, 62.49]) if periodic else rng.uniform(10, 50, 3)
+            x = c + rng.normal(0, 0.05, (n, 3)) * rng.uniform(0.02, 1, (n, 1))
+            if n:
+                x[0] = c
+            pm[part_offset[s]:part_offset[s + 1], :3] = np.mod(x, 62.5) if periodic else x
+            pm[part_offset[s]:part_offset[s + 1], 3] = 0.01 * rng.uniform(0.5, 2, n)
+            io["mostbound_pos"][s] = pm[part_offset[s], :3] if n else c
+            io["nbound"][s] = max(0, n - rng.integers(0, 3)) if n > 3 else n
+            io["mbound"][s] = pm[part_offset[s]:part_offset[s] + io["nbound"][s], 3].sum()
+        io["last_max_vmax_physical"] = rng.choice([0.0, 1e9], len(sizes))
+        io["snapshot_index_of_last_max_vmax"] = -1
+        io["bound_r200crit_comoving"], io["bound_m200crit"] = 7.0, 11.0
+        a = po.profile_batch(oracle_lib, "hbto", p, e, part_offset, pm, io)
+        b = po.profile_batch(ref_lib, "hbtref", p, e, part_offset, pm, io)
+        for f in cases.PROFILE_FIELDS:
+            assert np.array_equal(a[f], b[f], equal_nan=True), (periodic, f)
