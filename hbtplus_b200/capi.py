@@ -21,6 +21,8 @@ HBTU_ERR_NODEVICE = -4
 HBTU_ERR_UNSUPPORTED = -5
 HBTU_ERR_CAPACITY = -6
 HBTU_FLAG_TRUNCATE_SOURCE = 1
+HBTU_FLAG_NO_STRIPPING = 2  # the reference's -DNO_STRIPPING build
+HBTU_FLAG_THERMAL_ENERGY = 4  # -DUNBIND_WITH_THERMAL_ENERGY: vel[:, 3] is Particle_t::InternalEnergy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libhbtunbind.so")

@@ -127,6 +127,8 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
   c.nsub = nsub;
   c.N = N;
   c.flags = flags;
+  c.cfg.no_stripping = (flags & HBTU_FLAG_NO_STRIPPING) != 0;
+  c.cfg.thermal_energy = (flags & HBTU_FLAG_THERMAL_ENERGY) != 0;
   c.cfg.scale_factor = (float)epoch->scale_factor;
   c.cfg.hz = (float)epoch->hz;
   c.cfg.snapshot_index = epoch->snapshot_index;

@@ -112,6 +112,8 @@ struct DevConfig
   float box_size, box_half, softening, theta2, resolution, resolution_half, G, bound_mass_precision, relax_factor;
   float scale_factor, hz;
   int periodic, min_num_part, snapshot_index;
+  int no_stripping;   // HBTU_FLAG_NO_STRIPPING of the staged batch (-DNO_STRIPPING builds of the reference)
+  int thermal_energy; // HBTU_FLAG_THERMAL_ENERGY: vel.w is Particle_t::InternalEnergy and is added to E in full evaluations
   int64_t max_sample;
 };
 

@@ -77,6 +77,7 @@ struct SubState
   int origin_id;         // periodic: particle that is Elist[0] in the reference's order (origin of AveragePosition, :152-154)
   int hoare_last;        // scratch: largest reference index in [1,Nbound) of a bound entry (0 = none)
   int hoare_first_bound; // scratch: the reference's Elist[0] is bound
+  int hoare_nb;          // scratch: entries with E<0 this round (= Nbound unless NO_STRIPPING forces Nbound = Nlast)
   double sums[8]; // scratch: reduction accumulators
 };
 

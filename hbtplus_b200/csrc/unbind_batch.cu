@@ -325,7 +325,8 @@ __global__ void state1_kernel(const Segment *__restrict__ segs, int nseg, SubSta
   if (a >= nseg) return;
   SubState &st = subs[segs[a].sub];
   const int Nlast = segs[a].tgt_n;
-  const int Nbound = st.count_bound;
+  st.hoare_nb = st.count_bound; // what the partition saw
+  const int Nbound = cfg.no_stripping ? Nlast : st.count_bound; // NO_STRIPPING: Nbound=Nlast (src/subhalo_unbind.cpp:358-360)
   st.nlast = Nlast;
   if (Nbound < cfg.min_num_part)
   {
@@ -384,10 +385,10 @@ __global__ void __launch_bounds__(kBlock) hoare_flags_kernel(const Segment *__re
   if (st.status == kDisrupted) return;
   const int r = rho ? rho[tgt_slot[t]] : t - sg.tgt_off;
   const bool bound = E[tgt_slot[t]] < 0.f;
-  uflag[sg.tgt_off + r] = (!bound && r >= 1 && r < st.nbound);
-  bflag[sg.tgt_off + r] = (bound && r >= st.nbound);
+  uflag[sg.tgt_off + r] = (!bound && r >= 1 && r < st.hoare_nb);
+  bflag[sg.tgt_off + r] = (bound && r >= st.hoare_nb);
   if (bound && r == 0) st.hoare_first_bound = 1;
-  if (bound && r >= 1 && r < st.nbound) atomicMax(&st.hoare_last, r);
+  if (bound && r >= 1 && r < st.hoare_nb) atomicMax(&st.hoare_last, r);
 }
 __global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
                                                              const int *__restrict__ uflag, const int *__restrict__ uscan, int *__restrict__ fpos)
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__res
 __device__ __forceinline__ int hoare_dest(const Segment &sg, const SubState &st, int r, const int *__restrict__ bscan,
                                           const int *__restrict__ fpos)
 {
-  const int nb = st.nbound;
+  const int nb = st.hoare_nb;
   const int b0 = sg.tgt_off > 0 ? bscan[sg.tgt_off - 1] : 0;
   const int mis = bscan[sg.tgt_off + sg.tgt_n - 1] - b0; // bound entries at indices >= Nb
   if (r >= nb)
@@ -442,6 +443,9 @@ __global__ void __launch_bounds__(kBlock) rho_update_kernel(const Segment *__res
     r = hoare_dest(sg, st, rho[tgt_slot[t]], bscan, fpos);
     if (r == 0) st.origin_id = ids[tgt_slot[t]];
   }
+  else if (st.status != kDisrupted && st.hoare_nb == 0 && rho[tgt_slot[t]] == 0)
+    st.origin_id = ids[tgt_slot[t]]; // NO_STRIPPING with nothing bound: the partition leaves Elist[0] where it is
+
   rho_new[t] = r;
 }
 

@@ -206,7 +206,9 @@ __device__ __forceinline__ void walk_epilogue(const WalkArgs &a, const DevConfig
     { // E = VecNorm(dv)*0.5 + pot, stored as float  (src/gravity_tree.cpp:174, src/subhalo_unbind.cpp:350)
       float dv[3];
       relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
-      a.E[slot] = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+      float e = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
+      if (cfg.thermal_energy) e = __fadd_rn(e, v4.w); // UNBIND_WITH_THERMAL_ENERGY: E += InternalEnergy (src/subhalo_unbind.cpp:351-353)
+      a.E[slot] = e;
     }
     else
     { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)

@@ -108,6 +108,11 @@ typedef struct hbtu_sub_io
 #define HBTU_FLAG_TRUNCATE_SOURCE 1 /* apply Subhalo_t::TruncateSource to every subhalo at the end
                                        (what RefineParticles does, src/subhalo_unbind.cpp:511-513) */
 
+/* the reference's compile-time physics variants, selected per batch: */
+#define HBTU_FLAG_NO_STRIPPING 2    /* -DNO_STRIPPING: Nbound = Nlast after the partition (src/subhalo_unbind.cpp:358-360) */
+#define HBTU_FLAG_THERMAL_ENERGY 4  /* -DUNBIND_WITH_THERMAL_ENERGY: E += Particle_t::InternalEnergy in full evaluations
+                                       (src/subhalo_unbind.cpp:351-353); the internal energy travels in vel[4*i+3] */
+
 typedef struct hbtu_ctx hbtu_ctx;
 
 /* Create / destroy a context bound to one CUDA device.  One context per host
@@ -126,7 +131,7 @@ int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int6
  *
  *  part_offset[nsub+1]  subhalo s owns input particles [part_offset[s], part_offset[s+1])
  *  pos_mass[4*N]        x,y,z (comoving), mass      per input particle (HOST memory)
- *  vel[4*N]             vx,vy,vz (physical), unused per input particle (HOST memory)
+ *  vel[4*N]             vx,vy,vz (physical), InternalEnergy (read with HBTU_FLAG_THERMAL_ENERGY only) per input particle (HOST memory)
  *  nest_offset/nest_list CSR of NestedSubhalos (batch-local subhalo indices), may be NULL (no nesting).
  *                       Subhaloes that appear in nobody's list are roots.  Each root is processed
  *                       like Subhalo_t::RecursiveUnbind: children first, each child's unbound tail

@@ -88,6 +88,13 @@ struct Batch
   {
     const int64_t nsub = subs.size();
     if (nsub == 0) return;
+    // the caller's compile-time physics variant travels as batch flags
+#ifdef NO_STRIPPING
+    flags |= HBTU_FLAG_NO_STRIPPING;
+#endif
+#ifdef UNBIND_WITH_THERMAL_ENERGY
+    flags |= HBTU_FLAG_THERMAL_ENERGY;
+#endif
     part_offset.assign(nsub + 1, 0);
     for (int64_t s = 0; s < nsub; s++) part_offset[s + 1] = part_offset[s] + (int64_t)subs[s]->Particles.size();
     const int64_t N = part_offset[nsub];
@@ -105,7 +112,12 @@ struct Batch
         all[b + i] = p;
         float *x = &pos_mass[4 * (b + i)], *v = &vel[4 * (b + i)];
         x[0] = p.ComovingPosition[0]; x[1] = p.ComovingPosition[1]; x[2] = p.ComovingPosition[2]; x[3] = p.Mass;
-        v[0] = p.PhysicalVelocity[0]; v[1] = p.PhysicalVelocity[1]; v[2] = p.PhysicalVelocity[2]; v[3] = 0.f;
+        v[0] = p.PhysicalVelocity[0]; v[1] = p.PhysicalVelocity[1]; v[2] = p.PhysicalVelocity[2];
+#ifdef UNBIND_WITH_THERMAL_ENERGY
+        v[3] = p.InternalEnergy; // E += InternalEnergy (src/subhalo_unbind.cpp:351-353), HBTU_FLAG_THERMAL_ENERGY
+#else
+        v[3] = 0.f;
+#endif
       }
       hbtu_sub_io &o = io[s];
       std::memset(&o, 0, sizeof(o));

@@ -30,6 +30,7 @@ typedef struct
 { /* Particle_t, src/snapshot.h:51-72 (DM_ONLY) */
   HBTInt Id;
   HBTReal x[3], v[3], m;
+  HBTReal u; /* InternalEnergy (HAS_THERMAL_ENERGY builds, src/snapshot.h:58-60) */
 } Particle;
 
 typedef struct
@@ -47,6 +48,7 @@ typedef struct
   HBTReal ScaleFactor, Hz;
   int SnapshotIndex;
   int64_t ShuffleSeed;
+  int NoStripping, ThermalEnergy; /* the -DNO_STRIPPING / -DUNBIND_WITH_THERMAL_ENERGY builds (batch flags) */
 } Config;
 
 static void config_from(Config *c, const hbtu_params *p, const hbtu_epoch *e)
@@ -68,6 +70,7 @@ static void config_from(Config *c, const hbtu_params *p, const hbtu_epoch *e)
   c->Hz = (HBTReal)e->hz;
   c->SnapshotIndex = e->snapshot_index;
   c->ShuffleSeed = p->shuffle_seed;
+  c->NoStripping = c->ThermalEnergy = 0;
 }
 
 /* NEAREST(), src/config_parser.h:142 - one instance per operand width */
@@ -690,6 +693,7 @@ static void unbind(const Config *c, Sub *s)
         int64_t cnt[2] = {0, 0};
         HBTReal mass = (i < np_tree) ? view_mass(&ESnap, i) : 0.f;
         Elist[i].E = binding_energy(&tree, p->x, p->v, RefPos, RefVel, mass, cnt);
+        if (c->ThermalEnergy) Elist[i].E += p->u; /* UNBIND_WITH_THERMAL_ENERGY, src/subhalo_unbind.cpp:351-353 */
         cnt0 += cnt[0];
         cnt1 += cnt[1];
       }
@@ -698,6 +702,7 @@ static void unbind(const Config *c, Sub *s)
       ESnap.MassFactor = 1.f;
     }
     s->Nbound = partition_binding_energy(Elist, Nlast);
+    if (c->NoStripping) s->Nbound = Nlast; /* NO_STRIPPING, src/subhalo_unbind.cpp:358-360 */
     if (s->Nbound < c->MinNumPartOfSub)
     { /* disruption, src/subhalo_unbind.cpp:361-379 */
       s->Nbound = 1;
@@ -846,6 +851,8 @@ int hbto_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_
   if (params->real_bytes != 4) return HBTU_ERR_UNSUPPORTED;
   Config c;
   config_from(&c, params, epoch);
+  c.NoStripping = (flags & HBTU_FLAG_NO_STRIPPING) != 0;
+  c.ThermalEnergy = (flags & HBTU_FLAG_THERMAL_ENERGY) != 0;
   g_interactions = g_opened = 0;
   Sub *subs = calloc(nsub > 0 ? nsub : 1, sizeof(Sub));
   char *is_child = calloc(nsub > 0 ? nsub : 1, 1);
@@ -865,6 +872,7 @@ int hbto_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_
       {
         p->x[j] = pos_mass[4 * (b + i) + j];
         p->v[j] = vel[4 * (b + i) + j];
+        p->u = vel[4 * (b + i) + 3];
       }
       p->m = pos_mass[4 * (b + i) + 3];
     }
@@ -956,6 +964,7 @@ static Particle *particles_from(int64_t n, const float *pos_mass)
       P[i].v[j] = 0;
     }
     P[i].m = pos_mass[4 * i + 3];
+    P[i].u = 0;
   }
   return P;
 }

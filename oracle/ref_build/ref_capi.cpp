@@ -111,6 +111,9 @@ void fill_subhalo(Subhalo_t &sub, int64_t s, const int64_t *part_offset, const f
 #ifndef DM_ONLY
     p.Type = TypeDM;
 #endif
+#ifdef HAS_THERMAL_ENERGY
+    p.InternalEnergy = vel[4 * (b + i) + 3];
+#endif
   }
   for (int j = 0; j < 3; j++)
   {
@@ -174,7 +177,23 @@ int write_orders(const std::vector<Subhalo_t> &subs, const std::vector<int64_t> 
 }
 } // namespace
 
+/* the physics variants are compile-time in the reference: a library built with -DNO_STRIPPING /
+ * -DUNBIND_WITH_THERMAL_ENERGY answers only batches that ask for exactly that variant */
+static int variant_flags(void)
+{
+  int f = 0;
+#ifdef NO_STRIPPING
+  f |= HBTU_FLAG_NO_STRIPPING;
+#endif
+#ifdef UNBIND_WITH_THERMAL_ENERGY
+  f |= HBTU_FLAG_THERMAL_ENERGY;
+#endif
+  return f;
+}
+static bool variant_ok(int32_t flags) { return (flags & (HBTU_FLAG_NO_STRIPPING | HBTU_FLAG_THERMAL_ENERGY)) == variant_flags(); }
+
 extern "C" {
+int hbtref_variant_flags(void) { return variant_flags(); }
 
 int hbtref_sizeof_particle(void) { return (int)sizeof(Particle_t); }
 int hbtref_sizeof_subhalo(void) { return (int)sizeof(Subhalo_t); }
@@ -201,7 +220,7 @@ int hbtref_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int6
                         hbtu_sub_io *io, int32_t flags, int64_t order_capacity, int64_t *order_offset,
                         int32_t *order_out, float *energy_out)
 {
-  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  if (params->real_bytes != (int)sizeof(HBTReal) || !variant_ok(flags)) return HBTU_ERR_UNSUPPORTED;
   apply_params(params);
   Epoch_t snap;
   set_epoch(snap, epoch);

@@ -52,7 +52,34 @@ def case_sampled():
     return p, e, snap
 
 
+def case_nostrip():
+    """-DNO_STRIPPING build of the reference (batch flag HBTU_FLAG_NO_STRIPPING): Nbound = Nlast, one evaluation, everything
+    kept and E-sorted; periodic and across the box face so that the Elist[0] origin matters; one all-unbound source."""
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True)
+    e = capi.make_epoch(0.9, snapshot_index=8)
+    snap = synth.make_snapshot([900, 300, 60, 25, 15, 40], seed=15, wrap=True, parent=[-1, 0, 1, -1, -1, -1], centre=[62.45, 0.03, 31.0], f_contam=0.3)
+    b, en = snap.part_offset[5], snap.part_offset[6]
+    snap.vel[b:en, :3] *= 40.0  # source 5: nothing is bound
+    return p, e, snap
+
+
+def case_thermal():
+    """-DUNBIND_WITH_THERMAL_ENERGY build (batch flag HBTU_FLAG_THERMAL_ENERGY): vel[:,3] carries Particle_t::InternalEnergy,
+    here a fraction of each subhalo's velocity dispersion squared with a hot tail."""
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=False)
+    e = capi.make_epoch(1.0, snapshot_index=9)
+    snap = synth.make_snapshot([3000, 800, 200, 50, 22], seed=16, wrap=False, parent=[-1, 0, 0, 1, -1], f_contam=0.25)
+    rng = np.random.default_rng(16)
+    for s in range(snap.nsub):
+        b, en = snap.part_offset[s], snap.part_offset[s + 1]
+        v = snap.vel[b:en, :3]
+        sig2 = float(((v - v.mean(0)) ** 2).sum(1).mean())
+        snap.vel[b:en, 3] = (0.05 * sig2 * rng.exponential(1.0, en - b)).astype(np.float32)
+    return p, e, snap
+
+
 SAMPLED_SRAND = 7
+VARIANT_CASES = {"nostrip": (case_nostrip, "v32ns", capi.HBTU_FLAG_NO_STRIPPING), "thermal": (case_thermal, "v32th", capi.HBTU_FLAG_THERMAL_ENERGY)}
 
 CASES = {"flat": case_flat, "periodic_straddle": case_periodic_straddle, "nested": case_nested, "massvar": case_massvar, "sampled": case_sampled}
 

@@ -61,5 +61,26 @@ def main():
         print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "nbound", out["full_io"]["nbound"])
 
 
+def variants():
+    """The reference's compile-time physics variants (oracle/_ref/libhbtref_v32ns.so, libhbtref_v32th.so)."""
+    for name, (fn, variant, vflag) in cases.VARIANT_CASES.items():
+        ref = po.load_ref_variant(variant)
+        ref.hbtref_set_num_threads(1)
+        p, e, snap = fn()
+        out = {"pos_mass": snap.pos_mass, "vel": snap.vel, "part_offset": snap.part_offset, "io_in": snap.io,
+               "nest_offset": snap.nest_offset if snap.nest_offset is not None else np.zeros(0, np.int64),
+               "nest_list": snap.nest_list if snap.nest_list is not None else np.zeros(0, np.int32), "has_nest": np.array(snap.nest_offset is not None)}
+        for tag, flags in (("full", vflag), ("trunc", vflag | capi.HBTU_FLAG_TRUNCATE_SOURCE)):
+            r = po.run_batch(ref, "hbtref", p, e, snap, flags=flags)
+            ntot = int(r.order_offset[-1])
+            out[f"{tag}_io"], out[f"{tag}_order_offset"], out[f"{tag}_order"], out[f"{tag}_energy"] = r.io, r.order_offset, r.order[:ntot], r.energy[:ntot]
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "nbound", out["full_io"]["nbound"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants()
+        sys.exit(0)
     main()

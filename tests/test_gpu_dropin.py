@@ -24,15 +24,17 @@ def snapshot_with_hosts(seed, periodic):
     return snap, np.asarray(host, np.int32), n_old, 2, mb
 
 
-@pytest.mark.parametrize("variant", ["v32", "v64"])
+@pytest.mark.parametrize("variant", ["v32", "v64", "v32ns", "v32th", "v32im"])
 @pytest.mark.parametrize("periodic", [False, True])
 def test_refine_particles_drop_in(periodic, variant):
-    """v32 = -DDM_ONLY (HBTInt=int); v64 = -DHBT_INT8 (HBTInt=long, Particle_t with Type: the CMake default / EAGLE ABI).
-    The CUDA library is the same binary for both; only the shim is compiled with the caller's -D flags."""
+    """v32 = -DDM_ONLY (HBTInt=int); v64 = -DHBT_INT8 (HBTInt=long, Particle_t with Type: the CMake default / EAGLE ABI);
+    v32ns = -DNO_STRIPPING; v32th = -DUNBIND_WITH_THERMAL_ENERGY (Particle_t with InternalEnergy + Type);
+    v32im = -DINCLUSIVE_MASS (flat RefineParticles loop).  The CUDA library is the same binary for all of them; only the
+    shim is compiled with the caller's -D flags and passes the physics variant as batch flags."""
     if not po.have_dropin(variant):
         pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
     ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
-    assert ref.hbtref_sizeof_hbtint() == (4 if variant == "v32" else 8)
+    assert ref.hbtref_sizeof_hbtint() == (8 if variant == "v64" else 4)
     ref.hbtref_set_num_threads(4)
     p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
     e = capi.make_epoch(0.9, snapshot_index=15)

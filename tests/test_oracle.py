@@ -203,3 +203,34 @@ def test_oracle_profile_matches_reference_random(oracle_lib, ref_lib):
         b = po.profile_batch(ref_lib, "hbtref", p, e, part_offset, pm, io)
         for f in cases.PROFILE_FIELDS:
             assert np.array_equal(a[f], b[f], equal_nan=True), (periodic, f)
+
+
+# ---- the reference's compile-time physics variants as batch flags ----------------------------------------
+@pytest.mark.parametrize("name", list(cases.VARIANT_CASES))
+@pytest.mark.parametrize("trunc", [0, capi.HBTU_FLAG_TRUNCATE_SOURCE])
+def test_oracle_variant_matches_golden(oracle_lib, name, trunc):
+    """-DNO_STRIPPING / -DUNBIND_WITH_THERMAL_ENERGY: the restatement with the batch flag against the fixture minted from the
+    reference compiled with that -D flag (oracle/_ref/libhbtref_v32ns.so / _v32th.so)."""
+    fn, _, vflag = cases.VARIANT_CASES[name]
+    p, e, _ = fn()
+    snap, z = load_golden(name)
+    tag = "trunc" if trunc else "full"
+    oracle_lib.hbto_set_num_threads(1)
+    r = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=vflag | trunc)
+    oracle_lib.hbto_set_num_threads(8)
+    g = z[f"{tag}_io"]
+    skip = cases.unbound_inputs(snap)
+    for f in cases.IO_EXACT:
+        assert np.array_equal(r.io[f], g[f]), f
+    for f in cases.IO_FLOAT:
+        assert np.array_equal(r.io[f][~skip], g[f][~skip]), f
+    go, ge = z[f"{tag}_order"], z[f"{tag}_energy"]
+    for s in range(snap.nsub):
+        b, n = r.order_offset[s], r.io["nsource"][s]
+        assert orders_equal_modulo_ties(r.order[b:b + n], go[b:b + n], ge[b:b + n], int(g["nbound"][s])), (name, s)
+    if name == "nostrip":  # everything with >= MinNumPartOfSub particles stays "bound", even the all-unbound source 5
+        n = np.diff(snap.part_offset)
+        assert np.array_equal(g["nbound"][n >= 20], n[n >= 20])
+    else:  # the internal energy unbinds particles that the plain run keeps
+        plain = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=trunc)
+        assert plain.io["nbound"].sum() > g["nbound"].sum() and g["nbound"][0] > 1000
