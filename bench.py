@@ -107,6 +107,23 @@ def run_cpu(snap, threads: int | None = None):
     return dt, kind, ncpu, int(r.io["nbound"].sum())
 
 
+def phase_rooflines(st0, build_ms, other_ms, peaks):
+    """HBM rooflines of the two non-walk phases of a step: algorithmic bytes per particle per round
+     x particles summed over the step's rounds / CUDA-event time of the phase."""
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    # tree build, per source particle: gather 16 R + 16 W, bbox 16 R, key 16 R + 12 W, sort 12 R + 12 W (one algorithmic
+    # pass), sorted copy 28 R + 28 W, cell pairs 8 R + 13 W, moment scan 16 R + 32 W, node emit 32 R + 24+24 W
+    build_bytes = 16 + 16 + 16 + 16 + 12 + 12 + 12 + 28 + 28 + 8 + 13 + 16 + 32 + 32 + 48
+    # partition / sort / reduce, per target: E count 4 R, key 4 R + 12 W, sort 12 R + 12 W, permute 8 R + 8 W,
+    # frame reduction 4 + 32 R, kinematics 4 + 32 + 4 R (converged only: counted once)
+    other_bytes = 4 + 4 + 12 + 12 + 12 + 8 + 8 + 36 + 40
+    out = {}
+    for name, n, ms, b in (("tree_build", st0.tree_sources, build_ms, build_bytes), ("partition_sort_reduce", st0.walk_targets, other_ms, other_bytes)):
+        ach = b * n / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out[name] = {"bound": "hbm", "particles_over_rounds": int(n), "bytes_per_particle": b, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+    return out
+
+
 def bench_profile_row(ctx, e, snap, res, csnap, peaks):
     """SURVEY.md 8(f) next-2, measured beside the headline: Subhalo_t::CalculateProfileProperties + CalculateShape
     (src/subhalo.cpp:242-398) of every subhalo of the step through hbtu_profile_batch, HBM roofline, and the reference's
@@ -140,6 +157,41 @@ def bench_profile_row(ctx, e, snap, res, csnap, peaks):
         cnb = int(np.where(cio["nbound"] > 1, cio["nbound"], 0).sum())
         row["cpu_baseline"] = {"value": cnb / dt, "unit": "bound particles/s", "cores": os.cpu_count() or 1, "kind": "reference",
                                "sample": f"bound lists of the unbinding CPU sample ({cnb} bound particles, {csnap.nsub} subhaloes)", "seconds": dt}
+    return row
+
+
+def bench_mask_row(ctx, snap, csnap, peaks):
+    """SURVEY.md 8(f) next-1, measured beside the headline: SubhaloSnapshot_t::MaskSubhalos (src/subhalo_tracking.cpp:793-841)
+    of the step's whole forest through hbtu_mask_batch, HBM roofline, and the reference's own member on the CPU sample."""
+    from oracle import pyoracle as po
+    import cases_bench
+
+    args = cases_bench.mask_inputs(snap)
+    n = int(args[0][-1])
+    t_e2e, t_k, kept = [], [], 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        new_count, _ = ctx.mask_batch(*args)
+        t_e2e.append(time.perf_counter() - t0)
+        t_k.append(ctx.stats().execute_ms * 1e-3)
+        kept = int(new_count.sum())
+    # algorithmic bytes per list entry (DESIGN.md section 10): keys 8 R + 20 W, sort 12 R + 12 W (one algorithmic pass),
+    # runs 12 + 4 R + 4 W, scan 4 R + 4 W, scatter 12 R + 4 W
+    bytes_per = 28 + 24 + 20 + 8 + 16
+    row = {"list_entries": n, "kept": kept, "subhaloes": int(snap.nsub), "kernel_ms": float(np.min(t_k)) * 1e3, "e2e_ms": float(np.min(t_e2e)) * 1e3,
+           "value": n / float(np.min(t_k)), "e2e_value": n / float(np.min(t_e2e)), "unit": "list entries/s",
+           "roofline": {"bound": "hbm", "achieved": bytes_per * n / float(np.min(t_k)) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                        "frac": bytes_per * n / float(np.min(t_k)) / 1e9 / peaks.get("hbm_gbs", 6650.0), "bytes_per_entry": bytes_per}}
+    if po.have_ref():
+        ref = po.load_ref()
+        ref.hbtref_set_num_threads(os.cpu_count() or 1)
+        cargs = cases_bench.mask_inputs(csnap)
+        t0 = time.perf_counter()
+        po.mask_batch(ref, "hbtref", params_for(), *cargs)
+        dt = time.perf_counter() - t0
+        row["cpu_baseline"] = {"value": int(cargs[0][-1]) / dt, "unit": "list entries/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                               "sample": f"the forest of the unbinding CPU sample ({int(cargs[0][-1])} list entries, {csnap.nsub} subhaloes); includes the harness' fill of the reference's Subhalo_t lists",
+                               "seconds": dt}
     return row
 
 
@@ -344,7 +396,8 @@ def main():
                        "l2_policy": "inputs (5.8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the library stream around hbtu_execute, max over ranks", "wall_ms_per_step": float(np.mean(wall)) * 1e3,
                        "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
-                       "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all},
+                       "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all,
+                       "phase_rooflines": phase_rooflines(st0, float(np.mean(build_ms)), float(np.mean(other_ms)), peaks)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
                     "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "api": "hbtu_unbind_batch from pinned host buffers"},
@@ -359,7 +412,8 @@ def main():
             csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
             dt, kind, ncpu, _ = run_cpu(csnap)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
-            out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks)}
+            out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
+                                          "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks)}
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:

@@ -99,6 +99,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
         ("execute_ms", C.c_double),
+        ("tree_sources", C.c_int64),
     ]
 
 
@@ -167,6 +168,8 @@ PROFILEIO_DTYPE = np.dtype(
     align=True,
 )
 assert PROFILEIO_DTYPE.itemsize == C.sizeof(ProfileIO), (PROFILEIO_DTYPE.itemsize, C.sizeof(ProfileIO))
+MASK_ARGTYPES = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                 C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
 PROFILE_ARGTYPES = [C.POINTER(Epoch), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(ProfileIO)]
 
 
@@ -281,6 +284,7 @@ EXPORTS = [
     "hbtu_fetch",
     "hbtu_tree_potential",
     "hbtu_profile_batch",
+    "hbtu_mask_batch",
     "hbtu_get_stats",
     "hbtu_set_counting",
 ]
@@ -341,6 +345,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hbtu_tree_potential.restype = C.c_int
     lib.hbtu_profile_batch.argtypes = [C.c_void_p] + PROFILE_ARGTYPES
     lib.hbtu_profile_batch.restype = C.c_int
+    lib.hbtu_mask_batch.argtypes = [C.c_void_p] + MASK_ARGTYPES
+    lib.hbtu_mask_batch.restype = C.c_int
     lib.hbtu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.hbtu_get_stats.restype = C.c_int
     return lib
@@ -364,3 +370,9 @@ def batch_args(epoch, part_offset, pos_mass, vel, nest_offset, nest_list, io, fl
         _ptr(order_out, C.c_int32),
         _ptr(energy_out, C.c_float),
     )
+
+
+def mask_args(part_offset, particle_id, nest_offset, nest_list, nbound, new_count, keep_index):
+    """Marshal numpy arrays into the positional tail of ``*_mask_batch``."""
+    return (C.c_int64(len(part_offset) - 1), _ptr(part_offset, C.c_int64), _ptr(particle_id, C.c_int64), _ptr(nest_offset, C.c_int64),
+            _ptr(nest_list, C.c_int32), _ptr(nbound, C.c_int64), _ptr(new_count, C.c_int64), _ptr(keep_index, C.c_int32))

@@ -474,6 +474,12 @@ int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, con
   return guarded(ctx, [&](Context &c) { profile_batch(c, epoch, nsub, part_offset, pos_mass, io); });
 }
 
+int hbtu_mask_batch(hbtu_ctx *ctx, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id, const int64_t *nest_offset,
+                    const int32_t *nest_list, const int64_t *nbound, int64_t *new_count, int32_t *keep_index)
+{
+  return guarded(ctx, [&](Context &c) { mask_batch(c, nsub, part_offset, particle_id, nest_offset, nest_list, nbound, new_count, keep_index); });
+}
+
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out)
 {
   if (!ctx || !out) return HBTU_ERR_INVALID;

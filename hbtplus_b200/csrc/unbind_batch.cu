@@ -978,6 +978,7 @@ static void run_round(Context &c, std::vector<int> &active)
   c.stats.rounds++;
   c.stats.tree_builds += nseg;
   c.stats.walk_targets += T;
+  c.stats.tree_sources += S;
 
   std::vector<int> next;
   for (int a = 0; a < nseg; a++)

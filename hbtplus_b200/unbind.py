@@ -111,6 +111,20 @@ class UnbindContext:
         self._check(rc)
         return BatchResult(io, order_offset, order, energy)
 
+    # -- SubhaloSnapshot_t::MaskSubhalos (src/subhalo_tracking.cpp:793-841) -----------------------------
+    def mask_batch(self, part_offset, particle_id, nest_offset, nest_list, nbound):
+        """Exclusive particle ownership inside every hierarchy of the nest forest.  Returns (new_count[nsub], keep_index[N]):
+        subhalo s keeps the entries keep_index[part_offset[s] : part_offset[s] + new_count[s]]."""
+        po = np.ascontiguousarray(part_offset, np.int64)
+        ids = np.ascontiguousarray(particle_id, np.int64)
+        nb = np.ascontiguousarray(nbound, np.int64)
+        no = None if nest_offset is None else np.ascontiguousarray(nest_offset, np.int64)
+        nl = None if nest_list is None else np.ascontiguousarray(nest_list, np.int32)
+        new_count = np.zeros(len(po) - 1, np.int64)
+        keep = np.full(max(int(po[-1]), 1), -1, np.int32)
+        self._check(self._lib.hbtu_mask_batch(self._ctx, *capi.mask_args(po, ids, no, nl, nb, new_count, keep)))
+        return new_count, keep
+
     # -- Subhalo_t::CalculateProfileProperties + CalculateShape (src/subhalo.cpp:242-398) --------------
     def profile_batch(self, epoch, part_offset, pos_mass, io) -> np.ndarray:
         """``io``: structured array (capi.PROFILEIO_DTYPE) with the [in]/[io] fields set; returns the updated copy."""

@@ -206,6 +206,23 @@ typedef struct hbtu_profile_io
 int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
                        const float *pos_mass, hbtu_profile_io *io);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Source preparation: exclusive particle ownership before unbinding,
+ *   void SubhaloSnapshot_t::MaskSubhalos()  + SubhaloMasker_t::Mask   src/subhalo_tracking.cpp:793-841
+ * Every ROOT of the nest forest (a host's central with the other heads appended to its list, :832-838) owns one
+ * exclusion set.  Its hierarchy is visited depth first, children before their parent, in list order; a subhalo keeps, in
+ * order, the particles whose Id no earlier visited subhalo (or earlier position of its own list) holds.  Subhaloes with
+ * nbound <= 1 (orphans) are skipped: they keep their list and exclude nothing (:806).
+ *
+ *  particle_id[N]       Particle_t::Id of every list entry (HOST memory; any 64-bit values)
+ *  nbound[nsub]         Subhalo_t::Nbound on entry (only "<= 1" matters)
+ *  new_count[nsub]      [out] particles subhalo s keeps
+ *  keep_index[N]        [out] subhalo s keeps the entries keep_index[part_offset[s] .. part_offset[s]+new_count[s])
+ *                       (indices into the batch arrays, ascending)                                              */
+int hbtu_mask_batch(hbtu_ctx *ctx, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id,
+                    const int64_t *nest_offset, const int32_t *nest_list, const int64_t *nbound, int64_t *new_count,
+                    int32_t *keep_index);
+
 /* Counters of the last hbtu_execute / hbtu_tree_potential (for bench.py's roofline and
  * gpu_launches fields). */
 typedef struct hbtu_stats
@@ -222,6 +239,7 @@ typedef struct hbtu_stats
   double h2d_ms, d2h_ms;       /* copies in hbtu_stage / hbtu_fetch                    */
   int64_t h2d_bytes, d2h_bytes;
   double execute_ms;           /* CUDA-event time of the whole hbtu_execute (host planning gaps included) */
+  int64_t tree_sources;        /* source particles over all tree builds (sum over rounds)                */
 } hbtu_stats;
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted

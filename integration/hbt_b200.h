@@ -13,3 +13,8 @@
 #pragma once
 #include "subhalo.h"
 void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch);
+
+// src/subhalo_tracking.cpp:531 of the reference reads `MaskSubhalos();` (inside SubhaloSnapshot_t::PrepareCentrals) and becomes
+//     HBT_B200_MaskSubhalos(*this);
+// (exclusive particle ownership on the device through hbtu_mask_batch; Subhalos / MemberTable are public members).
+void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap);

@@ -358,3 +358,55 @@ void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epo
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Source preparation.  SubhaloSnapshot_t::MaskSubhalos (src/subhalo_tracking.cpp:
+// 824-841, called from PrepareCentrals at :531) is a private member defined in a file that is NOT replaced; the maintainer
+// swaps that one call for
+//     HBT_B200_MaskSubhalos(*this);                          // declared in integration/hbt_b200.h
+// which sends every host's hierarchy (central + old nests + the other heads, exactly the temporary append of :832-838) with
+// the particle Ids to hbtu_mask_batch and shrinks the particle lists to the entries it keeps.
+void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap)
+{
+  SubhaloList_t &Subhalos = snap.Subhalos;
+  Batch b;
+  std::vector<std::vector<int32_t>> lists;
+  for (HBTInt haloid = 0; haloid < (HBTInt)snap.MemberTable.SubGroups.size(); haloid++)
+  {
+    auto &subgroup = snap.MemberTable.SubGroups[haloid];
+    if (subgroup.size() == 0) continue;
+    auto &heads = snap.MemberTable.SubGroupsOfHeads[haloid];
+    int64_t me = add_hierarchy(b, lists, Subhalos, Subhalos[subgroup[0]]);
+    for (size_t i = 1; i < heads.size(); i++) lists[me].push_back((int32_t)add_hierarchy(b, lists, Subhalos, Subhalos[heads[i]]));
+  }
+  close_nests(b, lists);
+  const int64_t nsub = b.subs.size();
+  if (nsub == 0) return;
+  std::vector<int64_t> part_offset(nsub + 1, 0), nbound(nsub), new_count(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    part_offset[s + 1] = part_offset[s] + (int64_t)b.subs[s]->Particles.size();
+    nbound[s] = b.subs[s]->Nbound;
+  }
+  std::vector<int64_t> ids(part_offset[nsub]);
+  std::vector<int32_t> keep(part_offset[nsub] > 0 ? part_offset[nsub] : 1);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t s = 0; s < nsub; s++)
+    for (size_t i = 0; i < b.subs[s]->Particles.size(); i++) ids[part_offset[s] + i] = b.subs[s]->Particles[i].Id;
+  hbtu_ctx *ctx = context();
+  int rc = hbtu_mask_batch(ctx, nsub, part_offset.data(), ids.data(), b.nest_offset.data(), b.nest_list.data(), nbound.data(),
+                           new_count.data(), keep.data());
+  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_mask_batch failed: ") + hbtu_last_error(ctx));
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t s = 0; s < nsub; s++)
+  { // keep is ascending: compact in place, like the reference's move loop (:809-820)
+    auto &P = b.subs[s]->Particles;
+    const int32_t *k = &keep[part_offset[s]];
+    for (int64_t i = 0; i < new_count[s]; i++)
+    {
+      const int64_t src = k[i] - part_offset[s];
+      if (src != i) P[i] = std::move(P[src]);
+    }
+    P.resize(new_count[s]);
+  }
+}

@@ -1171,3 +1171,83 @@ int hbto_profile_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64
   }
   return HBTU_OK;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Source preparation: SubhaloSnapshot_t::MaskSubhalos + SubhaloMasker_t::Mask,
+ * src/subhalo_tracking.cpp:793-841.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct
+{ /* unordered_set<HBTInt> ExclusionList (:795): open addressing, insert-only */
+  int64_t *key;
+  unsigned char *used;
+  uint64_t mask;
+} IdSet;
+
+static int idset_insert(IdSet *h, int64_t id)
+{ /* returns 1 when inserted (was absent), like unordered_set::insert(...).second (:812-813) */
+  uint64_t z = (uint64_t)id * 0x9E3779B97F4A7C15ULL;
+  uint64_t i = (z ^ (z >> 29)) & h->mask;
+  while (h->used[i])
+  {
+    if (h->key[i] == id) return 0;
+    i = (i + 1) & h->mask;
+  }
+  h->used[i] = 1;
+  h->key[i] = id;
+  return 1;
+}
+
+static void mask_recursive(int64_t s, const int64_t *part_offset, const int64_t *ids, const int64_t *nest_offset,
+                           const int32_t *nest_list, const int64_t *nbound, IdSet *h, int64_t *new_count, int32_t *keep_index)
+{ /* SubhaloMasker_t::Mask, :801-822 */
+  if (nest_offset)
+    for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++)
+      mask_recursive(nest_list[k], part_offset, ids, nest_offset, nest_list, nbound, h, new_count, keep_index);
+  const int64_t b = part_offset[s], e = part_offset[s + 1];
+  int64_t save = b;
+  if (nbound[s] <= 1)
+  { /* skip orphans (:806): list untouched, nothing excluded */
+    for (int64_t i = b; i < e; i++) keep_index[save++] = (int32_t)i;
+  }
+  else
+    for (int64_t i = b; i < e; i++)
+      if (idset_insert(h, ids[i])) keep_index[save++] = (int32_t)i;
+  new_count[s] = save - b;
+}
+
+static int64_t tree_particles(int64_t s, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list)
+{
+  int64_t n = part_offset[s + 1] - part_offset[s];
+  if (nest_offset)
+    for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++) n += tree_particles(nest_list[k], part_offset, nest_offset, nest_list);
+  return n;
+}
+
+int hbto_mask_batch(const hbtu_params *params, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id,
+                    const int64_t *nest_offset, const int32_t *nest_list, const int64_t *nbound, int64_t *new_count,
+                    int32_t *keep_index)
+{
+  (void)params;
+  char *is_child = calloc((size_t)(nsub > 0 ? nsub : 1), 1);
+  if (nest_offset)
+    for (int64_t k = 0; k < nest_offset[nsub]; k++)
+    {
+      if (nest_list[k] < 0 || nest_list[k] >= nsub || is_child[nest_list[k]]) { free(is_child); return HBTU_ERR_INVALID; }
+      is_child[nest_list[k]] = 1;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t s = 0; s < nsub; s++)
+  { /* one SubhaloMasker_t per host group = per root, :834 */
+    if (is_child[s]) continue;
+    int64_t n = tree_particles(s, part_offset, nest_offset, nest_list);
+    uint64_t cap = 16;
+    while (cap < 2 * (uint64_t)n + 2) cap <<= 1;
+    IdSet h = {malloc(sizeof(int64_t) * cap), calloc(cap, 1), cap - 1};
+    mask_recursive(s, part_offset, particle_id, nest_offset, nest_list, nbound, &h, new_count, keep_index);
+    free(h.key);
+    free(h.used);
+  }
+  free(is_child);
+  return HBTU_OK;
+}

@@ -33,6 +33,10 @@ def _bind(lib, prefix):
     if pb is not None:
         pb.argtypes = [C.POINTER(capi.Params)] + capi.PROFILE_ARGTYPES
         pb.restype = C.c_int
+    mb = getattr(lib, prefix + "_mask_batch", None)
+    if mb is not None:
+        mb.argtypes = [C.POINTER(capi.Params)] + capi.MASK_ARGTYPES
+        mb.restype = C.c_int
     getattr(lib, prefix + "_set_num_threads").argtypes = [C.c_int]
     getattr(lib, prefix + "_get_max_threads").restype = C.c_int
     return lib
@@ -163,3 +167,18 @@ def profile_batch(lib, prefix, params, epoch, part_offset, pos_mass, io):
     if rc != 0:
         raise RuntimeError(f"{prefix}_profile_batch failed: {rc}")
     return out
+
+
+def mask_batch(lib, prefix, params, part_offset, particle_id, nest_offset, nest_list, nbound):
+    """SubhaloSnapshot_t::MaskSubhalos on the CPU checker `lib` (same contract as hbtu_mask_batch)."""
+    po = np.ascontiguousarray(part_offset, np.int64)
+    ids = np.ascontiguousarray(particle_id, np.int64)
+    nb = np.ascontiguousarray(nbound, np.int64)
+    no = None if nest_offset is None else np.ascontiguousarray(nest_offset, np.int64)
+    nl = None if nest_list is None else np.ascontiguousarray(nest_list, np.int32)
+    new_count = np.zeros(len(po) - 1, np.int64)
+    keep = np.full(max(int(po[-1]), 1), -1, np.int32)
+    rc = getattr(lib, prefix + "_mask_batch")(C.byref(params), *capi.mask_args(po, ids, no, nl, nb, new_count, keep))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_mask_batch failed: {rc}")
+    return new_count, keep

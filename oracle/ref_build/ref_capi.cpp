@@ -18,15 +18,28 @@
 #include <vector>
 #include <stdexcept>
 
+#include <unordered_set>
+#include <unordered_map>
+#include <string>
+#include <sstream>
+#include <fstream>
+#include <algorithm>
+#include <memory>
+
 #include "datatypes.h"
 #include "config_parser.h"
 #include "snapshot.h"
+/* SubhaloSnapshot_t::MaskSubhalos is a private member (src/subhalo.h:207); the harness calls the unmodified
+ * member, so the access specifier is lifted for this translation unit only (layout is unaffected). */
+#define private public
 #include "subhalo.h"
+#undef private
 #include "gravity_tree.h"
 
 #include "hbt_unbind.h"
 
 /* defined by integration/subhalo_unbind_b200.cpp in the drop-in build only */
+void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap) __attribute__((weak));
 void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch) __attribute__((weak));
 
 /* the real body lives in src/io/subhalo_io.cpp, which needs libhdf5 (absent) */
@@ -433,6 +446,76 @@ int hbtref_profile_batch(const hbtu_params *params, const hbtu_epoch *epoch, int
       o.inertial_tensor[j] = sub.InertialTensor[j];
       o.inertial_tensor_weighted[j] = sub.InertialTensorWeighted[j];
     }
+  }
+  return HBTU_OK;
+}
+
+/* SubhaloSnapshot_t::MaskSubhalos of the reference (src/subhalo_tracking.cpp:824-841) on an explicit nest forest; same
+ * contract as hbtu_mask_batch.  Every root becomes the central (and only head) of its own host halo, so that the
+ * reference's loop over MemberTable.SubGroups visits exactly the given hierarchies.  In the drop-in build the shim's
+ * HBT_B200_MaskSubhalos (-> hbtu_mask_batch) is used instead of the member. */
+int hbtref_mask_batch(const hbtu_params *params, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id,
+                      const int64_t *nest_offset, const int32_t *nest_list, const int64_t *nbound, int64_t *new_count,
+                      int32_t *keep_index)
+{
+  apply_params(params);
+  omp_set_max_active_levels(1);
+  SubhaloSnapshot_t snap;
+  snap.Subhalos.resize(nsub);
+  std::vector<int32_t> root(nsub, -1);
+  std::vector<char> is_child(nsub, 0);
+  if (nest_offset)
+    for (int64_t k = 0; k < nest_offset[nsub]; k++) is_child[nest_list[k]] = 1;
+  int32_t nhalos = 0;
+  std::vector<int64_t> stack;
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    if (is_child[s]) continue;
+    stack.assign(1, s);
+    while (!stack.empty())
+    {
+      int64_t q = stack.back();
+      stack.pop_back();
+      root[q] = nhalos;
+      if (nest_offset)
+        for (int64_t k = nest_offset[q]; k < nest_offset[q + 1]; k++) stack.push_back(nest_list[k]);
+    }
+    nhalos++;
+  }
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalo_t &sub = snap.Subhalos[s];
+    const int64_t b = part_offset[s], n = part_offset[s + 1] - b;
+    sub.Particles.resize(n);
+    for (int64_t i = 0; i < n; i++) sub.Particles[i].Id = (HBTInt)particle_id[b + i];
+    sub.Nbound = (HBTInt)nbound[s];
+    sub.Mbound = is_child[s] ? 1.f : 1e30f; /* the root sorts first in its group: it is the central */
+    sub.HostHaloId = root[s];
+    sub.TrackId = (HBTInt)s;
+    sub.Rank = 0;
+    if (nest_offset)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++) sub.NestedSubhalos.push_back(nest_list[k]);
+  }
+#pragma omp parallel
+  snap.MemberTable.Build(nhalos, snap.Subhalos, true);
+  snap.MemberTable.SubGroupsOfHeads.assign(nhalos, std::vector<HBTInt>());
+  for (HBTInt h = 0; h < nhalos; h++) snap.MemberTable.SubGroupsOfHeads[h].push_back(snap.MemberTable.SubGroups[h][0]);
+  if (HBT_B200_MaskSubhalos)
+    HBT_B200_MaskSubhalos(snap);
+  else
+    snap.MaskSubhalos();
+  for (int64_t s = 0; s < nsub; s++)
+  { /* the kept list is a subsequence of the input list: recover the positions */
+    const Subhalo_t &sub = snap.Subhalos[s];
+    const int64_t b = part_offset[s], e = part_offset[s + 1];
+    int64_t i = b, save = b;
+    for (const auto &p : sub.Particles)
+    {
+      while (i < e && (HBTInt)particle_id[i] != p.Id) i++;
+      if (i >= e) return HBTU_ERR_INVALID;
+      keep_index[save++] = (int32_t)i++;
+    }
+    new_count[s] = save - b;
   }
   return HBTU_OK;
 }

@@ -122,3 +122,43 @@ def profile_inputs(snap, res, last_vmax=None, seed=0):
 
 PROFILE_FIELDS = ["rmax_comoving", "vmax_physical", "last_max_vmax_physical", "snapshot_index_of_last_max_vmax", "r2sigma_comoving",
                   "rhalf_comoving", "bound_r200crit_comoving", "bound_m200crit", "inertial_tensor", "inertial_tensor_weighted"]
+
+
+def case_mask(seed=41, nroots=6, scale=1.0):
+    """Particle-Id lists with the overlaps MaskSubhalos exists for: every hierarchy draws its Ids from a shared pool, a
+    child shares part of its parent's particles, siblings overlap, some Ids repeat inside one list, some subhaloes are
+    orphans (Nbound <= 1) or empty, and different hierarchies reuse the same Ids (they must not exclude each other)."""
+    rng = np.random.default_rng(seed)
+    sizes, parent = [], []
+    for r in range(nroots):
+        root = len(sizes)
+        sizes.append(int(scale * rng.integers(200, 3000)))
+        parent.append(-1)
+        for _ in range(int(rng.integers(0, 6))):
+            par = int(rng.integers(root, len(sizes)))
+            sizes.append(int(scale * rng.integers(0, 400)))
+            parent.append(par)
+    sizes[-1] = 0
+    nsub = len(sizes)
+    part_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ids = np.zeros(part_offset[-1], np.int64)
+    pool = (rng.integers(1, 2**62, 5000, dtype=np.int64))  # 64-bit Ids, shared by ALL hierarchies
+    for s in range(nsub):
+        n = sizes[s]
+        own = pool[rng.integers(0, len(pool), n)]
+        if parent[s] >= 0 and n:
+            pb, pe = part_offset[parent[s]], part_offset[parent[s] + 1]
+            if pe > pb:
+                share = rng.random(n) < 0.4
+                own[share] = ids[pb:pe][rng.integers(0, pe - pb, int(share.sum()))]
+        ids[part_offset[s]:part_offset[s + 1]] = own
+    nbound = np.array([max(2, n // 2) for n in sizes], np.int64)
+    nbound[rng.random(nsub) < 0.15] = 1  # orphans
+    nbound[np.array(sizes) == 0] = 0
+    children = [[] for _ in range(nsub)]
+    for s, p_ in enumerate(parent):
+        if p_ >= 0:
+            children[p_].append(s)
+    nest_offset = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int64)
+    nest_list = np.array([c for cs in children for c in cs], np.int32)
+    return part_offset, ids, nest_offset, nest_list, nbound

@@ -79,7 +79,22 @@ def variants():
         print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "nbound", out["full_io"]["nbound"])
 
 
+def mask():
+    """SubhaloSnapshot_t::MaskSubhalos of the unmodified reference on cases.case_mask()."""
+    ref = po.load_ref()
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    part_offset, ids, nest_offset, nest_list, nbound = cases.case_mask()
+    new_count, keep = po.mask_batch(ref, "hbtref", p, part_offset, ids, nest_offset, nest_list, nbound)
+    path = os.path.join(HERE, "mask.npz")
+    np.savez_compressed(path, part_offset=part_offset, ids=ids, nest_offset=nest_offset, nest_list=nest_list, nbound=nbound,
+                        new_count=new_count, keep=keep)
+    print("mask ->", path, os.path.getsize(path) // 1024, "KiB", "kept", int(new_count.sum()), "of", int(part_offset[-1]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mask":
+        mask()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         variants()
         sys.exit(0)

@@ -76,3 +76,23 @@ def test_profile_properties_drop_in(variant):
     from test_gpu_profile import check_profile
     check_profile(got, want)
     assert (want["nbound"] > 1).sum() >= 5
+
+
+@pytest.mark.parametrize("variant", ["v32", "v64"])
+def test_mask_subhalos_drop_in(variant):
+    """SURVEY.md 8(f) next-1 through the reference-facing side: the harness builds a SubhaloSnapshot_t + MemberTable and calls
+    either the reference's private SubhaloSnapshot_t::MaskSubhalos (libhbtref) or the shim's HBT_B200_MaskSubhalos
+    (libhbtdropin -> hbtu_mask_batch), which shrinks the same vector<Particle_t> lists."""
+    if not po.have_dropin(variant):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    part_offset, ids, nest_offset, nest_list, nbound = cases.case_mask(seed=11, nroots=12)
+    if variant == "v32":
+        ids = ids % (2**31 - 1)  # HBTInt = int
+    want = po.mask_batch(ref, "hbtref", p, part_offset, ids, nest_offset, nest_list, nbound)
+    got = po.mask_batch(drop, "hbtref", p, part_offset, ids, nest_offset, nest_list, nbound)
+    assert np.array_equal(got[0], want[0]) and 0 < want[0].sum() < part_offset[-1]
+    for s in range(len(nbound)):
+        b = part_offset[s]
+        assert np.array_equal(got[1][b:b + got[0][s]], want[1][b:b + want[0][s]]), s

@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself: the plain-C restatement against the golden fixtures (generated from the
 unmodified reference), against the reference library where it is present, and against analytic answers."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -234,3 +235,33 @@ def test_oracle_variant_matches_golden(oracle_lib, name, trunc):
     else:  # the internal energy unbinds particles that the plain run keeps
         plain = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=trunc)
         assert plain.io["nbound"].sum() > g["nbound"].sum() and g["nbound"][0] > 1000
+
+
+# ---- source preparation: SubhaloSnapshot_t::MaskSubhalos ------------------------------------------
+def kept_lists(part_offset, new_count, keep):
+    return [keep[part_offset[s]:part_offset[s] + new_count[s]] for s in range(len(new_count))]
+
+
+def test_oracle_mask_matches_golden(oracle_lib):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mask.npz"))
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    new_count, keep = po.mask_batch(oracle_lib, "hbto", p, z["part_offset"], z["ids"], z["nest_offset"], z["nest_list"], z["nbound"])
+    assert np.array_equal(new_count, z["new_count"])
+    for a, b in zip(kept_lists(z["part_offset"], new_count, keep), kept_lists(z["part_offset"], z["new_count"], z["keep"])):
+        assert np.array_equal(a, b)
+    # the point of the exercise: inside a hierarchy every Id survives exactly once (orphans aside) ...
+    po_, ids, nb = z["part_offset"], z["ids"], z["nbound"]
+    assert 0 < new_count.sum() < po_[-1]
+    orphan = nb <= 1
+    assert np.array_equal(new_count[orphan], np.diff(po_)[orphan])
+
+
+def test_oracle_mask_matches_reference_random(oracle_lib, ref_lib):
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    for seed in (1, 2, 3):
+        part_offset, ids, nest_offset, nest_list, nbound = cases.case_mask(seed=seed, nroots=9)
+        a = po.mask_batch(oracle_lib, "hbto", p, part_offset, ids, nest_offset, nest_list, nbound)
+        b = po.mask_batch(ref_lib, "hbtref", p, part_offset, ids, nest_offset, nest_list, nbound)
+        assert np.array_equal(a[0], b[0])
+        for x, y in zip(kept_lists(part_offset, a[0], a[1]), kept_lists(part_offset, b[0], b[1])):
+            assert np.array_equal(x, y)
