@@ -317,7 +317,7 @@ def order_capacity(part_offset: np.ndarray, nest_offset, nest_list) -> int:
 
 def load_library(path: str | None = None) -> C.CDLL:
     """Load the CUDA product library.  Fails loudly when it has not been built."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("HBTU_LIB_PATH") or LIB_PATH  # HBTU_LIB_PATH: A/B builds of the same library (profiles/)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

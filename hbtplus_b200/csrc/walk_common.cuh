@@ -39,6 +39,66 @@ __device__ __forceinline__ float rsqrt_raw(float x)
   return y;
 }
 
+// Packed fp32x2 arithmetic (sm_100a: FADD2 / FMUL2 / FFMA2, one issue slot for two targets).  Each half is an IEEE
+// round-to-nearest operation, so results are bit-identical to the scalar FADD / FMUL / FFMA sequence.
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b)
+{
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b)
+{
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c)
+{
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)), "l"(*reinterpret_cast<unsigned long long *>(&c)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+
+// squared distances of node n to the T targets of a lane: (dx*dx + dy*dy) + dz*dz as FMUL, FFMA, FFMA - two targets per
+// instruction where the layout allows it (non-periodic, even T; the sign of dx is irrelevant)
+template <int T, bool PERIODIC>
+__device__ __forceinline__ void pair_r2(const float4 &n, const float (&px)[T], const float (&py)[T], const float (&pz)[T], const DevConfig &cfg,
+                                        float (&r2)[T])
+{
+  if constexpr (!PERIODIC && (T % 2 == 0))
+  {
+    const float2 nx = make_float2(-n.x, -n.x), ny = make_float2(-n.y, -n.y), nz = make_float2(-n.z, -n.z);
+#pragma unroll
+    for (int k = 0; k < T; k += 2)
+    {
+      const float2 dx = f2_add(make_float2(px[k], px[k + 1]), nx);
+      const float2 dy = f2_add(make_float2(py[k], py[k + 1]), ny);
+      const float2 dz = f2_add(make_float2(pz[k], pz[k + 1]), nz);
+      const float2 r = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      r2[k] = r.x;
+      r2[k + 1] = r.y;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < T; k++)
+    {
+      float dx = n.x - px[k], dy = n.y - py[k], dz = n.z - pz[k];
+      if (PERIODIC)
+      {
+        dx = nearest_f(dx, cfg.box_size, cfg.box_half);
+        dy = nearest_f(dy, cfg.box_size, cfg.box_half);
+        dz = nearest_f(dz, cfg.box_size, cfg.box_half);
+      }
+      r2[k] = dx * dx + dy * dy + dz * dz;
+    }
+  }
+}
+
 // One pass over the staged tile [tile_base, tile_lim) starting at node `no`, for the T targets of every lane.
 //   CAREFUL=false: every accepted source is added as -m/r and the smallest accepted r^2 is tracked; the caller
 //                  redoes the tile with CAREFUL=true if any lane met r < 2.8 eps (spline-softened pair, or r = 0).
@@ -56,17 +116,12 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
     const float lenq = nd->lenq;
     const int nend = nd->end;
     bool any_open = false;
+    float r2s[T];
+    pair_r2<T, PERIODIC>(n, px, py, pz, cfg, r2s);
 #pragma unroll
     for (int k = 0; k < T; k++)
     {
-      float dx = n.x - px[k], dy = n.y - py[k], dz = n.z - pz[k];
-      if (PERIODIC)
-      {
-        dx = nearest_f(dx, cfg.box_size, cfg.box_half);
-        dy = nearest_f(dy, cfg.box_size, cfg.box_half);
-        dz = nearest_f(dz, cfg.box_size, cfg.box_half);
-      }
-      const float r2 = dx * dx + dy * dy + dz * dz;
+      const float r2 = r2s[k];
       const bool active = no >= skip[k];
       const bool open = active && (lenq > r2); // reference criterion, per target (src/gravity_tree.cpp:135)
       const bool acc = active && !(lenq > r2);

@@ -29,6 +29,9 @@ namespace hbt
 {
 
 static constexpr int kGW = 4;      // warps per CTA (warps are independent)
+#ifndef HBT_GROUP_MINBLOCKS
+#define HBT_GROUP_MINBLOCKS 7 // resident CTAs per SM the register allocation must allow (measured, profiles/r01_walk_notes.md)
+#endif
 static constexpr int kWork = 768;  // ints per warp: chain stack (bottom) + MIXED list (top, grows down), both (node, end) pairs
 
 struct GroupSmem
@@ -53,28 +56,36 @@ __device__ __forceinline__ unsigned lanemask_lt()
   return m;
 }
 
-// dense evaluation of `cnt` FAR nodes for all targets of the warp: the roofline's 8 issue slots per pair
+// dense evaluation of `cnt` FAR nodes for all targets of the warp: the pair kernel and nothing else
 template <int T>
 __device__ __forceinline__ void eval_far(const float4 *__restrict__ ring, int base, int cnt, const float (&px)[T], const float (&py)[T],
                                          const float (&pz)[T], double (&accd)[T])
 {
-  float accf[T];
+  // two targets per FADD2 / FMUL2 / FFMA2: 7 packed + 2 MUFU.RSQ per pair of interactions
+  float2 accf[T / 2];
 #pragma unroll
-  for (int k = 0; k < T; k++) accf[k] = 0.f;
+  for (int k = 0; k < T / 2; k++) accf[k] = make_float2(0.f, 0.f);
 #pragma unroll 2
   for (int i = 0; i < cnt; i++)
   {
     const float4 nd = ring[(base + i) & 63];
+    const float2 nx = make_float2(-nd.x, -nd.x), ny = make_float2(-nd.y, -nd.y), nz = make_float2(-nd.z, -nd.z), nw = make_float2(-nd.w, -nd.w);
 #pragma unroll
-    for (int k = 0; k < T; k++)
+    for (int k = 0; k < T; k += 2)
     {
-      const float dx = nd.x - px[k], dy = nd.y - py[k], dz = nd.z - pz[k];
-      const float r2 = dx * dx + dy * dy + dz * dz;
-      accf[k] = fmaf(-nd.w, rsqrt_raw(r2), accf[k]);
+      const float2 dx = f2_add(make_float2(px[k], px[k + 1]), nx);
+      const float2 dy = f2_add(make_float2(py[k], py[k + 1]), ny);
+      const float2 dz = f2_add(make_float2(pz[k], pz[k + 1]), nz);
+      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      accf[k / 2] = f2_fma(nw, make_float2(rsqrt_raw(r2.x), rsqrt_raw(r2.y)), accf[k / 2]);
     }
   }
 #pragma unroll
-  for (int k = 0; k < T; k++) accd[k] += (double)accf[k];
+  for (int k = 0; k < T; k += 2)
+  {
+    accd[k] += (double)accf[k / 2].x;
+    accd[k + 1] += (double)accf[k / 2].y;
+  }
 }
 
 // NEAR nodes: particles accepted by every target, but the pair may be softened (r < 2.8 eps, incl. the self pair
@@ -118,7 +129,7 @@ __device__ __forceinline__ void eval_near(const float4 *__restrict__ ring, int b
 }
 
 template <int T, bool PERIODIC, bool COUNT>
-__global__ void __launch_bounds__(kGW * 32) walk_group_kernel(const WalkArgs a, const DevConfig cfg)
+__global__ void __launch_bounds__(kGW * 32, HBT_GROUP_MINBLOCKS) walk_group_kernel(const WalkArgs a, const DevConfig cfg)
 {
   __shared__ GroupSmem s_all[kGW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
