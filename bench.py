@@ -195,6 +195,42 @@ def bench_mask_row(ctx, snap, csnap, peaks):
     return row
 
 
+def bench_idtable_row(ctx, n, n_cpu, peaks):
+    """SURVEY.md 8(f) next-4, measured beside the headline: MappedIndexTable_t::Fill + GetIndices (src/hash.tpp:18-32,
+    src/hash_remote.tpp:9-88) for a snapshot of n particle Ids and n queries (half present, half absent)."""
+    from oracle import pyoracle as po
+
+    def make(m, seed):
+        rng = np.random.default_rng(seed)
+        ids = rng.permutation(m).astype(np.int64) * 7 + 3
+        q = np.concatenate([ids[rng.integers(0, m, m // 2)], rng.integers(0, 7 * m, m - m // 2, dtype=np.int64) * 7 + 4])
+        return ids, q
+
+    ids, q = make(n, 11)
+    tb, tq, eb, eq = [], [], [], []
+    for _ in range(2):
+        t0 = time.perf_counter(); ctx.idtable_build(ids); eb.append(time.perf_counter() - t0); tb.append(ctx.stats().execute_ms * 1e-3)
+        t0 = time.perf_counter(); out = ctx.idtable_query(q); eq.append(time.perf_counter() - t0); tq.append(ctx.stats().execute_ms * 1e-3)
+    assert int((out >= 0).sum()) == n // 2
+    # algorithmic bytes: build 8 R + 12 W (keys) + 12 R + 12 W (one sort pass); query 8 R + 8 W + 8 probe
+    bbytes, qbytes = 44, 24
+    k = float(np.min(tb)) + float(np.min(tq))
+    row = {"table_entries": int(n), "queries": int(len(q)), "build_kernel_ms": float(np.min(tb)) * 1e3, "query_kernel_ms": float(np.min(tq)) * 1e3,
+           "build_e2e_ms": float(np.min(eb)) * 1e3, "query_e2e_ms": float(np.min(eq)) * 1e3, "value": len(q) / k, "unit": "queries/s (build + query kernels)",
+           "roofline": {"bound": "hbm", "achieved": (bbytes * n + qbytes * len(q)) / k / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                        "frac": (bbytes * n + qbytes * len(q)) / k / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
+    if po.have_ref():
+        ref = po.load_ref()
+        ref.hbtref_set_num_threads(os.cpu_count() or 1)
+        cids, cq = make(n_cpu, 12)
+        t0 = time.perf_counter()
+        po.idtable_query(ref, "hbtref", params_for(), cids, cq)
+        dt = time.perf_counter() - t0
+        row["cpu_baseline"] = {"value": len(cq) / dt, "unit": "queries/s (Fill + sort queries + GetIndices)", "cores": os.cpu_count() or 1, "kind": "reference",
+                               "sample": f"{n_cpu} table entries, {len(cq)} queries", "seconds": dt}
+    return row
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -413,7 +449,8 @@ def main():
             dt, kind, ncpu, _ = run_cpu(csnap)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
             out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
-                                          "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks)}
+                                          "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks),
+                                          "particle_query": bench_idtable_row(ctx, snap.npart, csnap.npart, peaks)}
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:

@@ -285,6 +285,9 @@ EXPORTS = [
     "hbtu_tree_potential",
     "hbtu_profile_batch",
     "hbtu_mask_batch",
+    "hbtu_idtable_build",
+    "hbtu_idtable_query",
+    "hbtu_idtable_clear",
     "hbtu_get_stats",
     "hbtu_set_counting",
 ]
@@ -347,6 +350,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hbtu_profile_batch.restype = C.c_int
     lib.hbtu_mask_batch.argtypes = [C.c_void_p] + MASK_ARGTYPES
     lib.hbtu_mask_batch.restype = C.c_int
+    lib.hbtu_idtable_build.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.hbtu_idtable_build.restype = C.c_int
+    lib.hbtu_idtable_query.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.hbtu_idtable_query.restype = C.c_int
+    lib.hbtu_idtable_clear.argtypes = [C.c_void_p]
+    lib.hbtu_idtable_clear.restype = C.c_int
     lib.hbtu_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.hbtu_get_stats.restype = C.c_int
     return lib

@@ -405,6 +405,7 @@ void hbtu_destroy(hbtu_ctx *ctx)
   cudaFree(c.d_ids_orig);
   cudaFree(c.d_E);
   cudaFree(c.d_rho);
+  idtable_clear(c);
   cudaFree(c.d_subs);
   cudaFree(c.d_part_offset);
   cudaFree(c.d_slot_base);
@@ -478,6 +479,19 @@ int hbtu_mask_batch(hbtu_ctx *ctx, int64_t nsub, const int64_t *part_offset, con
                     const int32_t *nest_list, const int64_t *nbound, int64_t *new_count, int32_t *keep_index)
 {
   return guarded(ctx, [&](Context &c) { mask_batch(c, nsub, part_offset, particle_id, nest_offset, nest_list, nbound, new_count, keep_index); });
+}
+
+int hbtu_idtable_build(hbtu_ctx *ctx, int64_t n, const int64_t *particle_id)
+{
+  return guarded(ctx, [&](Context &c) { idtable_build(c, n, particle_id); });
+}
+int hbtu_idtable_query(hbtu_ctx *ctx, int64_t nq, const int64_t *query_id, int64_t *index_out)
+{
+  return guarded(ctx, [&](Context &c) { idtable_query(c, nq, query_id, index_out); });
+}
+int hbtu_idtable_clear(hbtu_ctx *ctx)
+{
+  return guarded(ctx, [&](Context &c) { idtable_clear(c); });
 }
 
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out)

@@ -47,6 +47,9 @@ struct Context
   SubState *d_subs = nullptr;
   int64_t *d_part_offset = nullptr, *d_slot_base = nullptr;
   int64_t cap_subs = 0;
+  uint64_t *d_idt_key = nullptr; // idtable.cu: sorted (order-preserving) particle Ids of the last hbtu_idtable_build
+  int *d_idt_val = nullptr;      // and their indices
+  int64_t idt_n = 0;
   unsigned long long *d_counters = nullptr;
   bool count_interactions = false;
 
@@ -61,6 +64,10 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
 // mask.cu: SubhaloSnapshot_t::MaskSubhalos for a forest of particle-Id lists
 void mask_batch(Context &c, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id, const int64_t *nest_offset,
                 const int32_t *nest_list, const int64_t *nbound, int64_t *new_count, int32_t *keep_index);
+// idtable.cu: MappedIndexTable_t::Fill / GetIndices
+void idtable_build(Context &c, int64_t n, const int64_t *particle_id);
+void idtable_query(Context &c, int64_t nq, const int64_t *query_id, int64_t *index_out);
+void idtable_clear(Context &c);
 void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out);
 
 } // namespace hbt

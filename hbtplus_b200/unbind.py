@@ -111,6 +111,18 @@ class UnbindContext:
         self._check(rc)
         return BatchResult(io, order_offset, order, energy)
 
+    # -- MappedIndexTable_t::Fill / GetIndices (src/hash.tpp:18-32, src/hash_remote.tpp:9-88) ----------------
+    def idtable_build(self, particle_id):
+        ids = np.ascontiguousarray(particle_id, np.int64)
+        self._check(self._lib.hbtu_idtable_build(self._ctx, len(ids), capi._ptr(ids, C.c_int64)))
+
+    def idtable_query(self, query_id) -> np.ndarray:
+        """Index of every queried Id in the array given to idtable_build, -1 (NullParticleId) when absent."""
+        q = np.ascontiguousarray(query_id, np.int64)
+        out = np.empty(len(q), np.int64)
+        self._check(self._lib.hbtu_idtable_query(self._ctx, len(q), capi._ptr(q, C.c_int64), capi._ptr(out, C.c_int64)))
+        return out
+
     # -- SubhaloSnapshot_t::MaskSubhalos (src/subhalo_tracking.cpp:793-841) -----------------------------
     def mask_batch(self, part_offset, particle_id, nest_offset, nest_list, nbound):
         """Exclusive particle ownership inside every hierarchy of the nest forest.  Returns (new_count[nsub], keep_index[N]):

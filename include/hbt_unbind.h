@@ -223,6 +223,18 @@ int hbtu_mask_batch(hbtu_ctx *ctx, int64_t nsub, const int64_t *part_offset, con
                     const int64_t *nest_offset, const int32_t *nest_list, const int64_t *nbound, int64_t *new_count,
                     int32_t *keep_index);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Particle query, the on-node part: Id -> index of the snapshot's particle, as
+ *   MappedIndexTable_t::Fill        src/hash.tpp:18-32    (sort the (Id, index) pairs)
+ *   MappedIndexTable_t::GetIndices  src/hash_remote.tpp:9-88  (batch binary search; what ParticleSnapshot_t::GetIndices,
+ *                                   :98-105, runs for ParticleExchanger_t::QueryParticles, src/particle_exchanger.h:196-211)
+ * The table lives in the context until the next build / clear / hbtu_destroy.  Ids are 64-bit (HBTInt = int builds widen).
+ *  index_out[nq]  index into the build array, or -1 (SpecialConst::NullParticleId, src/datatypes.h:87) when absent.
+ *  Ids are expected to be unique; of equal Ids the lowest index answers.                                         */
+int hbtu_idtable_build(hbtu_ctx *ctx, int64_t n, const int64_t *particle_id);
+int hbtu_idtable_query(hbtu_ctx *ctx, int64_t nq, const int64_t *query_id, int64_t *index_out);
+int hbtu_idtable_clear(hbtu_ctx *ctx);
+
 /* Counters of the last hbtu_execute / hbtu_tree_potential (for bench.py's roofline and
  * gpu_launches fields). */
 typedef struct hbtu_stats

@@ -1251,3 +1251,47 @@ int hbto_mask_batch(const hbtu_params *params, int64_t nsub, const int64_t *part
   free(is_child);
   return HBTU_OK;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Particle query: MappedIndexTable_t::Fill (src/hash.tpp:18-32) +
+ * MappedIndexTable_t::GetIndices (src/hash_remote.tpp:9-88).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct
+{ /* IndexedKey_t, src/hash.h */
+  int64_t Key, Index;
+} IdPair;
+
+static int comp_pair(const void *a, const void *b)
+{ /* CompPair, src/hash.tpp:13-17; the index breaks ties so that the answer for duplicated Ids is defined */
+  const IdPair *x = (const IdPair *)a, *y = (const IdPair *)b;
+  if (x->Key != y->Key) return (x->Key > y->Key) - (x->Key < y->Key);
+  return (x->Index > y->Index) - (x->Index < y->Index);
+}
+
+int hbto_idtable_query(const hbtu_params *params, int64_t n, const int64_t *particle_id, int64_t nq, const int64_t *query_id,
+                       int64_t *index_out)
+{
+  (void)params;
+  IdPair *Map = malloc(sizeof(IdPair) * (size_t)(n > 0 ? n : 1));
+  for (int64_t i = 0; i < n; i++)
+  {
+    Map[i].Key = particle_id[i];
+    Map[i].Index = i;
+  }
+  qsort(Map, (size_t)n, sizeof(IdPair), comp_pair); /* Fill, :29 */
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < nq; q++)
+  { /* lower_bound + equality test, src/hash_remote.tpp:76-83 */
+    const int64_t key = query_id[q];
+    int64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+      int64_t mid = lo + ((hi - lo) >> 1);
+      if (Map[mid].Key < key) lo = mid + 1; else hi = mid;
+    }
+    index_out[q] = (lo < n && Map[lo].Key == key) ? Map[lo].Index : -1;
+  }
+  free(Map);
+  return HBTU_OK;
+}

@@ -182,3 +182,17 @@ def mask_batch(lib, prefix, params, part_offset, particle_id, nest_offset, nest_
     if rc != 0:
         raise RuntimeError(f"{prefix}_mask_batch failed: {rc}")
     return new_count, keep
+
+
+def idtable_query(lib, prefix, params, particle_id, query_id):
+    """MappedIndexTable_t::Fill + GetIndices on the CPU checker `lib` (same contract as hbtu_idtable_build + _query)."""
+    ids = np.ascontiguousarray(particle_id, np.int64)
+    q = np.ascontiguousarray(query_id, np.int64)
+    out = np.empty(len(q), np.int64)
+    f = getattr(lib, prefix + "_idtable_query")
+    f.argtypes = [C.POINTER(capi.Params), C.c_int64, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    f.restype = C.c_int
+    rc = f(C.byref(params), len(ids), capi._ptr(ids, C.c_int64), len(q), capi._ptr(q, C.c_int64), capi._ptr(out, C.c_int64))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_idtable_query failed: {rc}")
+    return out

@@ -35,6 +35,8 @@
 #include "subhalo.h"
 #undef private
 #include "gravity_tree.h"
+#include "hash.h"
+#include "hash_remote.tpp"
 
 #include "hbt_unbind.h"
 
@@ -517,6 +519,46 @@ int hbtref_mask_batch(const hbtu_params *params, int64_t nsub, const int64_t *pa
     }
     new_count[s] = save - b;
   }
+  return HBTU_OK;
+}
+
+/* MappedIndexTable_t<HBTInt,HBTInt>::Fill + GetIndices of the reference (src/hash.tpp:18-32, src/hash_remote.tpp:9-88),
+ * queried the way ParticleExchanger_t::QueryParticles does (src/particle_exchanger.h:196-211): queries sorted by Id, batch
+ * binary search, original order restored.  Same contract as hbtu_idtable_build + hbtu_idtable_query. */
+namespace
+{
+struct IdList_t : public KeyList_t<HBTInt, HBTInt>
+{
+  const int64_t *ids;
+  int64_t n;
+  IdList_t(const int64_t *p, int64_t m) : ids(p), n(m) {}
+  HBTInt GetKey(const HBTInt i) const { return (HBTInt)ids[i]; }
+  HBTInt GetIndex(const HBTInt i) const { return i; }
+  HBTInt size() const { return (HBTInt)n; }
+};
+struct QueryItem_t
+{
+  HBTInt Id;
+  int64_t Order;
+};
+} // namespace
+
+int hbtref_idtable_query(const hbtu_params *params, int64_t n, const int64_t *particle_id, int64_t nq, const int64_t *query_id,
+                         int64_t *index_out)
+{
+  (void)params;
+  MappedIndexTable_t<HBTInt, HBTInt> table;
+  IdList_t keys(particle_id, n);
+  table.Fill(keys, SpecialConst::NullParticleId);
+  std::vector<QueryItem_t> q(nq);
+  for (int64_t i = 0; i < nq; i++)
+  {
+    q[i].Id = (HBTInt)query_id[i];
+    q[i].Order = i;
+  }
+  std::sort(q.begin(), q.end(), [](const QueryItem_t &a, const QueryItem_t &b) { return a.Id < b.Id; });
+  table.GetIndices(q);
+  for (const auto &x : q) index_out[x.Order] = x.Id;
   return HBTU_OK;
 }
 

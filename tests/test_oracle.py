@@ -265,3 +265,28 @@ def test_oracle_mask_matches_reference_random(oracle_lib, ref_lib):
         assert np.array_equal(a[0], b[0])
         for x, y in zip(kept_lists(part_offset, a[0], a[1]), kept_lists(part_offset, b[0], b[1])):
             assert np.array_equal(x, y)
+
+
+# ---- particle query: MappedIndexTable_t::Fill / GetIndices ----------------------------------------
+def idtable_case(seed, n, nq, wide):
+    rng = np.random.default_rng(seed)
+    hi = 2**62 if wide else 2**31 - 2
+    ids = rng.choice(hi, n, replace=False).astype(np.int64) if not wide else np.unique(rng.integers(-2**62, 2**62, n, dtype=np.int64))
+    rng.shuffle(ids)
+    hit = ids[rng.integers(0, len(ids), nq // 2)]
+    miss = rng.integers(-5 if wide else 0, hi, nq - len(hit), dtype=np.int64)
+    q = np.concatenate([hit, miss, [-1]])
+    rng.shuffle(q)
+    return ids, q
+
+
+def test_oracle_idtable_matches_reference(oracle_lib, ref_lib):
+    p = capi.make_params(box_size=62.5, softening=5e-3)
+    for seed in (1, 2):
+        ids, q = idtable_case(seed, 20000, 30000, wide=False)  # the V32 reference holds HBTInt = int
+        a = po.idtable_query(oracle_lib, "hbto", p, ids, q)
+        b = po.idtable_query(ref_lib, "hbtref", p, ids, q)
+        assert np.array_equal(a, b)
+        found = a >= 0
+        assert found.sum() >= len(q) // 2 and np.array_equal(ids[a[found]], q[found]) and a[q == -1].max() == -1
+    assert np.array_equal(po.idtable_query(oracle_lib, "hbto", p, np.zeros(0, np.int64), np.array([3, 4])), [-1, -1])
