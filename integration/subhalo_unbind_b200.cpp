@@ -13,10 +13,13 @@
 //
 // Build:  g++ -std=c++11 -O2 -fopenmp $(HBT_DEFS) -I$(HBT)/src -I<repo>/include -c subhalo_unbind_b200.cpp
 // Link :  replace subhalo_unbind.o by subhalo_unbind_b200.o and add -L<repo>/hbtplus_b200/csrc -lhbtunbind
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "datatypes.h"
@@ -29,7 +32,6 @@ static_assert(sizeof(HBTReal) == 4, "only the HBTReal=float ABI variant of libhb
 
 namespace
 {
-hbtu_ctx *g_ctx = nullptr;
 hbtu_params g_params;
 
 void fill_params(hbtu_params &p)
@@ -59,24 +61,49 @@ void fill_params(hbtu_params &p)
   p.shuffle_seed = seed ? atoll(seed) : 20240001;
 }
 
-hbtu_ctx *context()
-{ // one context per process (= per MPI rank); re-created if the configuration changed
+// Devices this process drives.  Default: one (HBT_UNBIND_DEVICE, the usual one-MPI-rank-per-GPU launch).  With
+// HBT_UNBIND_DEVICES=0,1,2,3 one rank shards its hierarchies over several GPUs of the box (whole
+// hierarchies, cost-weighted longest-processing-time-first, no data-path collective; see run_sharded below).
+std::vector<hbtu_ctx *> g_ctxs;
+std::string g_devices;
+
+std::vector<hbtu_ctx *> &contexts()
+{ // one context per device; re-created if the configuration or the device list changed
   hbtu_params p;
   fill_params(p);
-  if (g_ctx && std::memcmp(&p, &g_params, sizeof(p)) == 0) return g_ctx;
-  if (g_ctx) hbtu_destroy(g_ctx);
-  g_ctx = nullptr;
-  int rc = hbtu_create(&p, &g_ctx);
-  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_create failed: ") + hbtu_last_error(nullptr));
+  const char *list = getenv("HBT_UNBIND_DEVICES");
+  const std::string devs = list ? list : std::to_string(p.device);
+  if (!g_ctxs.empty() && devs == g_devices && std::memcmp(&p, &g_params, sizeof(p)) == 0) return g_ctxs;
+  for (auto *c : g_ctxs) hbtu_destroy(c);
+  g_ctxs.clear();
+  size_t pos = 0;
+  while (pos <= devs.size())
+  {
+    size_t comma = devs.find(',', pos);
+    if (comma == std::string::npos) comma = devs.size();
+    if (comma > pos)
+    {
+      hbtu_params q = p;
+      q.device = atoi(devs.substr(pos, comma - pos).c_str());
+      hbtu_ctx *c = nullptr;
+      int rc = hbtu_create(&q, &c);
+      if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_create failed: ") + hbtu_last_error(nullptr));
+      g_ctxs.push_back(c);
+    }
+    pos = comma + 1;
+  }
+  if (g_ctxs.empty()) throw std::runtime_error("HBT_UNBIND_DEVICES names no device");
   g_params = p;
+  g_devices = devs;
   static bool registered = false;
   if (!registered)
   {
-    atexit([] { if (g_ctx) hbtu_destroy(g_ctx); g_ctx = nullptr; });
+    atexit([] { for (auto *c : g_ctxs) hbtu_destroy(c); g_ctxs.clear(); });
     registered = true;
   }
-  return g_ctx;
+  return g_ctxs;
 }
+hbtu_ctx *context() { return contexts()[0]; }
 
 struct Batch
 { // pack -> call -> unpack of a set of subhaloes given by index into `Subhalos`
@@ -84,10 +111,11 @@ struct Batch
   std::vector<int64_t> part_offset, nest_offset;
   std::vector<int32_t> nest_list;
 
-  void run(const Snapshot_t &epoch, int32_t flags)
+  void run(const Snapshot_t &epoch, int32_t flags, hbtu_ctx *ctx = nullptr)
   {
     const int64_t nsub = subs.size();
     if (nsub == 0) return;
+    if (!ctx) ctx = context();
     // the caller's compile-time physics variant travels as batch flags
 #ifdef NO_STRIPPING
     flags |= HBTU_FLAG_NO_STRIPPING;
@@ -154,7 +182,6 @@ struct Batch
 #else
     float *pe = nullptr;
 #endif
-    hbtu_ctx *ctx = context();
     int rc = hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), no, nl, io.data(), flags, cap,
                                order_offset.data(), order.data(), pe);
     if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_unbind_batch failed: ") + hbtu_last_error(ctx));
@@ -204,6 +231,75 @@ int64_t add_hierarchy(Batch &b, std::vector<std::vector<int32_t>> &lists, Subhal
   }
   return me;
 }
+void close_nests(Batch &b, const std::vector<std::vector<int32_t>> &lists);
+
+// Multi-GPU inside one process.  The batch is cut at hierarchy boundaries (add_hierarchy appends a root and
+// everything nested in it contiguously, so a unit is the index range up to the next root), the units are dealt to the
+// devices longest-processing-time-first with cost sum n*log2(n) per unit, and every device runs its sub-batch on its own
+// host thread and context.  Results do not depend on the split: hierarchies never interact.
+void run_sharded(Batch &b, const std::vector<std::vector<int32_t>> &lists, const Snapshot_t &epoch, int32_t flags)
+{
+  std::vector<hbtu_ctx *> &ctxs = contexts();
+  const int64_t nsub = b.subs.size();
+  const int G = (int)ctxs.size();
+  if (G == 1 || nsub < 2)
+  {
+    b.run(epoch, flags, ctxs[0]);
+    return;
+  }
+  std::vector<char> is_child(nsub, 0);
+  for (auto &l : lists)
+    for (int32_t ch : l) is_child[ch] = 1;
+  struct Unit { int64_t first, last; double cost; };
+  std::vector<Unit> units;
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    const double n = (double)b.subs[s]->Particles.size();
+    const double c = n * std::log2(n + 2.0);
+    if (!is_child[s]) units.push_back(Unit{s, s + 1, c});
+    else { units.back().last = s + 1; units.back().cost += c; }
+  }
+  std::vector<size_t> by_cost(units.size());
+  for (size_t i = 0; i < units.size(); i++) by_cost[i] = i;
+  std::stable_sort(by_cost.begin(), by_cost.end(), [&](size_t x, size_t y) { return units[x].cost > units[y].cost; });
+  std::vector<double> load(G, 0.0);
+  std::vector<std::vector<size_t>> mine(G);
+  for (size_t u : by_cost)
+  {
+    int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    load[g] += units[u].cost;
+    mine[g].push_back(u);
+  }
+  std::vector<Batch> parts(G);
+  std::vector<std::vector<std::vector<int32_t>>> part_lists(G);
+  for (int g = 0; g < G; g++)
+  {
+    std::sort(mine[g].begin(), mine[g].end()); // keep the reference's visiting order inside a device
+    std::vector<int32_t> remap(nsub, -1);
+    for (size_t u : mine[g])
+      for (int64_t s = units[u].first; s < units[u].last; s++)
+      {
+        remap[s] = (int32_t)parts[g].subs.size();
+        parts[g].subs.push_back(b.subs[s]);
+      }
+    part_lists[g].resize(parts[g].subs.size());
+    for (size_t u : mine[g])
+      for (int64_t s = units[u].first; s < units[u].last; s++)
+        for (int32_t ch : lists[s]) part_lists[g][remap[s]].push_back(remap[ch]);
+    close_nests(parts[g], part_lists[g]);
+  }
+  std::vector<std::thread> workers;
+  std::vector<std::string> errors(G);
+  for (int g = 0; g < G; g++)
+    workers.emplace_back([&, g] {
+      try { parts[g].run(epoch, flags, ctxs[g]); }
+      catch (const std::exception &ex) { errors[g] = ex.what(); }
+    });
+  for (auto &w : workers) w.join();
+  for (auto &e : errors)
+    if (!e.empty()) throw std::runtime_error(e);
+}
+
 void close_nests(Batch &b, const std::vector<std::vector<int32_t>> &lists)
 {
   b.nest_offset.assign(lists.size() + 1, 0);
@@ -282,7 +378,7 @@ void SubhaloSnapshot_t::RefineParticles()
   }
 #endif
   close_nests(b, lists);
-  b.run(*this, HBTU_FLAG_TRUNCATE_SOURCE);
+  run_sharded(b, lists, *this, HBTU_FLAG_TRUNCATE_SOURCE);
   // subhaloes the reference's loops never unbind (members of a host whose nest is not reachable from a head) are
   // still truncated by its last loop (subhalo_unbind.cpp:511-513)
   for (size_t i = 0; i < Subhalos.size(); i++)

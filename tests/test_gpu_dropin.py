@@ -96,3 +96,24 @@ def test_mask_subhalos_drop_in(variant):
     for s in range(len(nbound)):
         b = part_offset[s]
         assert np.array_equal(got[1][b:b + got[0][s]], want[1][b:b + want[0][s]]), s
+
+
+def test_refine_particles_sharded_over_devices(monkeypatch):
+    """SURVEY.md 8(e) at the shim: with HBT_UNBIND_DEVICES the rank's hierarchies are dealt to several contexts (here three
+    contexts on device 0, so that one GPU suffices), each on its own host thread; the result must not depend on the split."""
+    if not po.have_dropin("v32"):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    drop = po.load_dropin("v32")
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True)
+    e = capi.make_epoch(0.9, snapshot_index=15)
+    snap, host, n_old, nhalos, mb = snapshot_with_hosts(21, True)
+    monkeypatch.delenv("HBT_UNBIND_DEVICES", raising=False)
+    one = po.refine_particles(drop, p, e, snap, host, n_old, nhalos, mb)
+    monkeypatch.setenv("HBT_UNBIND_DEVICES", "0,0,0")
+    three = po.refine_particles(drop, p, e, snap, host, n_old, nhalos, mb)
+    for f in one.io.dtype.names:
+        assert np.array_equal(one.io[f], three.io[f]), f
+    assert np.array_equal(one.order_offset, three.order_offset)
+    from conftest import orders_equal_modulo_ties
+    for s in range(snap.nsub):  # the same lists; entries whose energies agree to round-off may swap (DESIGN.md section 7)
+        assert orders_equal_modulo_ties(three.particles(s), one.particles(s), one.energy[one.order_offset[s]:][:len(one.particles(s))], int(one.io["nbound"][s])), s
