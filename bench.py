@@ -142,7 +142,16 @@ def bench_profile_row(ctx, e, snap, res, csnap, peaks):
     # algorithmic bytes per bound particle: radius/shape 16 B read + 12 B key/index write; sort 12 + 12;
     # cumulative mass 12 + 4 (mass gather) read + 8 write; select 8 + 8 read
     bytes_per = 16 + 12 + 24 + 24 + 16
+    # fused with the resident unbinding batch (hbtu_profile_executed): only the per-subhalo records cross PCIe
+    ctx.stage(e, snap, capi.HBTU_FLAG_TRUNCATE_SOURCE)
+    ctx.execute()
+    t_fused = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.profile_executed(io)
+        t_fused.append(time.perf_counter() - t0)
     row = {"bound_particles": nb, "subhaloes": int(snap.nsub), "kernel_ms": float(np.min(t_k)) * 1e3, "e2e_ms": float(np.min(t_e2e)) * 1e3,
+           "e2e_resident_ms": float(np.min(t_fused)) * 1e3,
            "value": nb / float(np.min(t_k)), "e2e_value": nb / float(np.min(t_e2e)), "unit": "bound particles/s",
            "roofline": {"bound": "hbm", "achieved": bytes_per * nb / float(np.min(t_k)) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
                         "frac": bytes_per * nb / float(np.min(t_k)) / 1e9 / peaks.get("hbm_gbs", 6650.0), "bytes_per_particle": bytes_per}}

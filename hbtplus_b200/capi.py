@@ -284,6 +284,7 @@ EXPORTS = [
     "hbtu_fetch",
     "hbtu_tree_potential",
     "hbtu_profile_batch",
+    "hbtu_profile_executed",
     "hbtu_mask_batch",
     "hbtu_idtable_build",
     "hbtu_idtable_query",
@@ -348,6 +349,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hbtu_tree_potential.restype = C.c_int
     lib.hbtu_profile_batch.argtypes = [C.c_void_p] + PROFILE_ARGTYPES
     lib.hbtu_profile_batch.restype = C.c_int
+    lib.hbtu_profile_executed.argtypes = [C.c_void_p, C.POINTER(ProfileIO)]
+    lib.hbtu_profile_executed.restype = C.c_int
     lib.hbtu_mask_batch.argtypes = [C.c_void_p] + MASK_ARGTYPES
     lib.hbtu_mask_batch.restype = C.c_int
     lib.hbtu_idtable_build.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]

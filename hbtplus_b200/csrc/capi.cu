@@ -475,6 +475,11 @@ int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, con
   return guarded(ctx, [&](Context &c) { profile_batch(c, epoch, nsub, part_offset, pos_mass, io); });
 }
 
+int hbtu_profile_executed(hbtu_ctx *ctx, hbtu_profile_io *io)
+{
+  return guarded(ctx, [&](Context &c) { profile_executed(c, io); });
+}
+
 int hbtu_mask_batch(hbtu_ctx *ctx, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id, const int64_t *nest_offset,
                     const int32_t *nest_list, const int64_t *nbound, int64_t *new_count, int32_t *keep_index)
 {

@@ -61,6 +61,7 @@ struct Context
 void execute_batch(Context &c);
 // profile.cu: Subhalo_t::CalculateProfileProperties + CalculateShape for a batch of particle lists
 void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io);
+void profile_executed(Context &c, hbtu_profile_io *io);
 // mask.cu: SubhaloSnapshot_t::MaskSubhalos for a forest of particle-Id lists
 void mask_batch(Context &c, int64_t nsub, const int64_t *part_offset, const int64_t *particle_id, const int64_t *nest_offset,
                 const int32_t *nest_list, const int64_t *nbound, int64_t *new_count, int32_t *keep_index);

@@ -67,8 +67,8 @@ __device__ __forceinline__ double pwarp_sum(double v)
 // K1: radius to the most-bound position (sort key) and the inertia-tensor terms.  Elements of a block mostly belong to
 // one subhalo: then the 12 sums are reduced in the block and issue 12 atomics; mixed blocks reduce per warp / lane.
 __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *__restrict__ subs, int nsub, int64_t B,
-                                                                 const float4 *__restrict__ pos, DevConfig cfg, uint64_t *__restrict__ key,
-                                                                 int *__restrict__ val, ProfScratch *__restrict__ scr)
+                                                                 const float4 *__restrict__ pos, const int *__restrict__ ids, DevConfig cfg,
+                                                                 uint64_t *__restrict__ key, int *__restrict__ val, ProfScratch *__restrict__ scr)
 {
   __shared__ double red[12][kPB / 32];
   const int64_t e = (int64_t)blockIdx.x * kPB + threadIdx.x;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *_
     s = block_uniform ? s_first : prof_find(subs, nsub, e);
     const ProfSub sb = subs[s];
     const int64_t i = e - sb.bound_off;
-    const float4 p = pos[sb.part_off + i];
+    const float4 p = ids ? pos[ids[sb.part_off + i]] : pos[sb.part_off + i]; // ids: the Elist of a resident unbinding batch
     float dx = __fsub_rn(p.x, sb.cx), dy = __fsub_rn(p.y, sb.cy), dz = __fsub_rn(p.z, sb.cz);
     // the reference takes cen - pos for the radius and pos - cen for the tensor: the squares and the pair products agree
     if (cfg.periodic)
@@ -160,10 +160,12 @@ struct SortedMass
   const int *val;
   const ProfSub *subs;
   const float4 *pos;
+  const int *ids;
   __device__ double operator()(int64_t k) const
   {
     const ProfSub &sb = subs[(int)(key[k] >> 32)];
-    return (double)pos[sb.part_off + val[k]].w;
+    const int64_t e = sb.part_off + val[k];
+    return (double)pos[ids ? ids[e] : e].w;
   }
 };
 struct KeySeg
@@ -259,22 +261,20 @@ __global__ void prof_finalize_kernel(const ProfSub *__restrict__ subs, int nsub,
   }
 }
 
-void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io)
+// common core.  Particle list of subhalo s = `list_off[s]` + i, read through `d_ids` when given (indices into d_pos),
+// else directly.  host_pos != nullptr: the positions are uploaded first (N_host particles).
+static void profile_core(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *list_off, const int64_t *list_len, const float *host_pos,
+                         int64_t N_host, const float4 *resident_pos, const int *d_ids, hbtu_profile_io *io)
 {
-  if (!epoch || nsub < 0 || !part_offset || !io) throw CudaError{HBTU_ERR_INVALID, "bad argument"};
-  if (nsub == 0) return;
-  if (nsub > 0x7fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
-  const int64_t N = part_offset[nsub];
-  if (N > 0 && !pos_mass) throw CudaError{HBTU_ERR_INVALID, "null particle array"};
   std::vector<ProfSub> subs(nsub);
   int64_t B = 0;
   for (int64_t s = 0; s < nsub; s++)
   {
-    const int64_t n = part_offset[s + 1] - part_offset[s];
-    if (n < 0 || io[s].nbound < 0 || io[s].nbound > n) throw CudaError{HBTU_ERR_INVALID, "nbound exceeds the particle list of a subhalo"};
+    if (list_len[s] < 0 || io[s].nbound < 0 || io[s].nbound > list_len[s])
+      throw CudaError{HBTU_ERR_INVALID, "nbound exceeds the particle list of a subhalo"};
     if (io[s].nbound > 0x7fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "subhalo larger than 2^31 particles"};
     ProfSub &sb = subs[s];
-    sb.part_off = part_offset[s];
+    sb.part_off = list_off[s];
     sb.bound_off = B;
     sb.nb = io[s].nbound > 1 ? (int)io[s].nbound : 0;
     sb.cx = (float)io[s].mostbound_pos[0];
@@ -283,7 +283,6 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
     sb.mbound = io[s].mbound;
     B += sb.nb;
   }
-  c.staged = c.executed = false; // the arena is shared with a staged batch's rounds
   DevConfig cfg = c.cfg;
   cfg.scale_factor = (float)epoch->scale_factor;
   cfg.hz = (float)epoch->hz;
@@ -295,10 +294,15 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
   cudaStream_t st = c.stream;
   Arena &ar = c.arena;
   ar.reset();
-  ar.reserve(N * 16 + B * 56 + nsub * (int64_t)(sizeof(ProfSub) + sizeof(ProfScratch) + sizeof(hbtu_profile_io)) + (64 << 20));
+  ar.reserve(N_host * 16 + B * 56 + nsub * (int64_t)(sizeof(ProfSub) + sizeof(ProfScratch) + sizeof(hbtu_profile_io)) + (64 << 20));
   c.ls.launches = 0;
-  float4 *d_pos = ar.alloc<float4>(N);
-  if (N > 0) HBT_CUDA(cudaMemcpyAsync(d_pos, pos_mass, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
+  const float4 *d_pos = resident_pos;
+  if (host_pos)
+  {
+    float4 *up = ar.alloc<float4>(N_host);
+    if (N_host > 0) HBT_CUDA(cudaMemcpyAsync(up, host_pos, sizeof(float4) * (size_t)N_host, cudaMemcpyHostToDevice, st));
+    d_pos = up;
+  }
   ProfSub *d_subs = ar.alloc<ProfSub>(nsub);
   HBT_CUDA(cudaMemcpyAsync(d_subs, subs.data(), sizeof(ProfSub) * (size_t)nsub, cudaMemcpyHostToDevice, st));
   hbtu_profile_io *d_io = ar.alloc<hbtu_profile_io>(nsub);
@@ -312,7 +316,7 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st)); // kernels only: the H2D copies above are queued before it
   if (B > 0)
   {
-    prof_radius_shape_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, (int)nsub, B, d_pos, cfg, key_a, val_a, d_scr);
+    prof_radius_shape_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, (int)nsub, B, d_pos, d_ids, cfg, key_a, val_a, d_scr);
     HBT_CHECK_LAUNCH();
     int bits = 32;
     while ((1ll << (bits - 32)) < nsub) bits++;
@@ -324,7 +328,7 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
     HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, B, 0, bits, st));
     skey = dk.Current();
     auto kin = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), KeySeg{skey});
-    auto vin = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), SortedMass{skey, dv.Current(), d_subs, d_pos});
+    auto vin = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), SortedMass{skey, dv.Current(), d_subs, d_pos, d_ids});
     size_t sb2 = 0;
     HBT_CUDA(cub::DeviceScan::InclusiveSumByKey(nullptr, sb2, kin, vin, mcum, B, cub::Equality(), st));
     void *tmp2 = ar.alloc<char>((int64_t)sb2);
@@ -340,17 +344,52 @@ void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int6
   HBT_CUDA(cudaEventRecord(c.ev_exec[1], st));
   HBT_CUDA(cudaMemcpyAsync(io, d_io, sizeof(hbtu_profile_io) * (size_t)nsub, cudaMemcpyDeviceToHost, st));
   HBT_CUDA(cudaStreamSynchronize(st));
-  std::memset(&c.stats, 0, sizeof(c.stats));
+  hbtu_stats stats;
+  std::memset(&stats, 0, sizeof(stats));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
+  stats.execute_ms = ms; // radius/shape + sort + scan + select + finalize
+  stats.other_ms = ms;
+  stats.walk_targets = B;
+  stats.kernel_launches = c.ls.launches;
+  stats.h2d_bytes = N_host * 16 + nsub * (int64_t)(sizeof(ProfSub) + sizeof(hbtu_profile_io));
+  stats.d2h_bytes = nsub * (int64_t)sizeof(hbtu_profile_io);
+  c.stats = stats;
+}
+
+void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io)
+{
+  if (!epoch || nsub < 0 || !part_offset || !io) throw CudaError{HBTU_ERR_INVALID, "bad argument"};
+  if (nsub == 0) return;
+  if (nsub > 0x7fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
+  const int64_t N = part_offset[nsub];
+  if (N > 0 && !pos_mass) throw CudaError{HBTU_ERR_INVALID, "null particle array"};
+  std::vector<int64_t> len(nsub);
+  for (int64_t s = 0; s < nsub; s++) len[s] = part_offset[s + 1] - part_offset[s];
+  c.staged = c.executed = false; // the arena is shared with a staged batch's rounds
+  profile_core(c, epoch, nsub, part_offset, len.data(), pos_mass, N, nullptr, nullptr, io);
+}
+
+// The same on the batch that hbtu_execute left in HBM: the particle lists are the Elists (new order, bound first) of the
+// subhaloes, read through d_ids from the resident positions - nothing but the per-subhalo records crosses PCIe.
+void profile_executed(Context &c, hbtu_profile_io *io)
+{
+  if (!io) throw CudaError{HBTU_ERR_INVALID, "bad argument"};
+  if (!c.staged || !c.executed) throw CudaError{HBTU_ERR_INVALID, "hbtu_profile_executed needs an executed batch (hbtu_stage + hbtu_execute)"};
+  const int64_t nsub = c.nsub;
+  if (nsub == 0) return;
+  std::vector<int64_t> off(nsub), len(nsub);
+  for (int64_t s = 0; s < nsub; s++)
   {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
-    c.stats.execute_ms = ms; // radius/shape + sort + scan + select + finalize
-    c.stats.other_ms = ms;
-    c.stats.walk_targets = B;
+    off[s] = c.subs[s].slot_base;
+    len[s] = c.subs[s].n_src; // Particles.size() after unbinding, before truncation: the bound part is its head
   }
-  c.stats.kernel_launches = c.ls.launches;
-  c.stats.h2d_bytes = N * 16 + nsub * (int64_t)(sizeof(ProfSub) + sizeof(hbtu_profile_io));
-  c.stats.d2h_bytes = nsub * (int64_t)sizeof(hbtu_profile_io);
+  hbtu_epoch e;
+  e.scale_factor = c.cfg.scale_factor;
+  e.hz = c.cfg.hz;
+  e.snapshot_index = c.cfg.snapshot_index;
+  e.reserved = 0;
+  profile_core(c, &e, nsub, off.data(), len.data(), nullptr, 0, c.d_pos, c.d_ids, io);
 }
 
 } // namespace hbt

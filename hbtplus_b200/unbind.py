@@ -149,6 +149,12 @@ class UnbindContext:
         self._check(rc)
         return out
 
+    def profile_executed(self, io) -> np.ndarray:
+        """profile_batch on the batch hbtu_execute left resident in HBM (stage + execute first): no particle upload."""
+        out = np.ascontiguousarray(io, capi.PROFILEIO_DTYPE).copy()
+        self._check(self._lib.hbtu_profile_executed(self._ctx, out.ctypes.data_as(C.POINTER(capi.ProfileIO))))
+        return out
+
     # -- GravityTree_t::Build + EvaluatePotential / BindingEnergy -------------------------------------
     def tree_potential(self, epoch, src_pos_mass, tgt_pos, self_mass=None, tgt_vel=None, ref_pos=None, ref_vel=None) -> np.ndarray:
         src = np.ascontiguousarray(src_pos_mass, np.float32)

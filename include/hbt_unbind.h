@@ -205,6 +205,10 @@ typedef struct hbtu_profile_io
  *  pos_mass[4*N]        x,y,z (comoving), mass (HOST memory)                                                  */
 int hbtu_profile_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
                        const float *pos_mass, hbtu_profile_io *io);
+/* The same for the batch that hbtu_execute left resident in HBM (after hbtu_stage + hbtu_execute, before the next stage):
+ * the particle lists are the new orders the unbinding just produced, the epoch is the staged one, io[s] belongs to
+ * subhalo s of that batch; only the per-subhalo records cross PCIe. */
+int hbtu_profile_executed(hbtu_ctx *ctx, hbtu_profile_io *io);
 
 /* ---------------------------------------------------------------------------------------------------
  * Source preparation: exclusive particle ownership before unbinding,

@@ -35,14 +35,16 @@ def test_ctypes_structs_match_the_header(tmp_path):
     prog = tmp_path / "sz.c"
     prog.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "hbt_unbind.h"\n'
-        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hbtu_params), sizeof(hbtu_epoch), sizeof(hbtu_sub_io),'
-        " sizeof(hbtu_stats), offsetof(hbtu_sub_io, mbound), offsetof(hbtu_sub_io, nsource_full), offsetof(hbtu_params, G));return 0;}\n"
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hbtu_params), sizeof(hbtu_epoch), sizeof(hbtu_sub_io),'
+        " sizeof(hbtu_stats), offsetof(hbtu_sub_io, mbound), offsetof(hbtu_sub_io, nsource_full), offsetof(hbtu_params, G),"
+        " sizeof(hbtu_profile_io), offsetof(hbtu_profile_io, inertial_tensor));return 0;}\n"
     )
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(capi.Params), C.sizeof(capi.Epoch), C.sizeof(capi.SubIO), C.sizeof(capi.Stats),
-            capi.SubIO.mbound.offset, capi.SubIO.nsource_full.offset, capi.Params.G.offset]
+            capi.SubIO.mbound.offset, capi.SubIO.nsource_full.offset, capi.Params.G.offset,
+            C.sizeof(capi.ProfileIO), capi.ProfileIO.inertial_tensor.offset]
     assert got == want
     assert capi.SUBIO_DTYPE.itemsize == C.sizeof(capi.SubIO)
     for name in capi.SUBIO_DTYPE.names:

@@ -59,6 +59,19 @@ def test_profile_after_unbind_vs_oracle(make_ctx, oracle_lib, periodic):
     check_profile(got, want)
     st = ctx.stats()
     assert 8 <= st.kernel_launches <= 20  # one batched pass, not one launch per subhalo
+    # the fused form: the batch is still resident after stage + execute, only the records travel
+    ctx.stage(e, snap, capi.HBTU_FLAG_TRUNCATE_SOURCE)
+    ctx.execute()
+    res2 = ctx.fetch()
+    _, _, io2 = cases.profile_inputs(snap, res2, seed=5)
+    fused = ctx.profile_executed(io2)
+    st = ctx.stats()
+    assert st.h2d_bytes < 200 * snap.nsub
+    for f in cases.PROFILE_FIELDS:
+        assert np.array_equal(fused[f], got[f], equal_nan=True), f
+    with pytest.raises(Exception):  # nothing resident any more after another kind of call
+        ctx.profile_batch(e, part_offset, pm, io)
+        ctx.profile_executed(io2)
 
 
 def test_profile_edge_cases(make_ctx, oracle_lib):
