@@ -8,7 +8,8 @@
 //   PeriodicDistance                       src/config_parser.h:143-156
 // as segmented, batched passes over the concatenated bound particles of all subhaloes (B = sum Nbound):
 //
-//   radius + shape (K1)   16 B read per particle, 12 B key/index write; fp64 block reductions for the tensors   HBM
+//   radius + shape (K1)   16 B read per particle, 12 B key/index write; fp64 sums of the tensor terms with a fixed
+//                         summation tree (seg_reduce.cuh)                                                          HBM
 //   CUB radix sort        (subhalo, radius bits) 64-bit key + 32-bit index                                       HBM
 //   CUB scan-by-key       cumulative mass in double (the reference's serial double sum; exact for equal masses)  HBM
 //   select (K3)           v^2 = M(<r)/max(r,eps): first maximum, last radius with M > 200 rho_crit (4/3 pi) r^3  HBM
@@ -23,6 +24,8 @@
 #include <vector>
 
 #include "context.cuh"
+#include "seg_reduce.cuh"
+#include "det_scan.cuh"
 
 namespace hbt
 {
@@ -58,33 +61,45 @@ __device__ __forceinline__ int prof_find(const ProfSub *__restrict__ subs, int n
   return lo;
 }
 
-__device__ __forceinline__ double pwarp_sum(double v)
+struct ProfDone
 {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+  ProfScratch *scr;
+  __device__ void operator()(int s, const double (&x)[12]) const
+  {
+#pragma unroll
+    for (int j = 0; j < 12; j++) scr[s].sums[j] = x[j];
+  }
+};
+struct ProfRange
+{
+  const ProfSub *subs;
+  __device__ void operator()(int s, int64_t &begin, int64_t &end) const
+  {
+    begin = subs[s].bound_off;
+    end = begin + subs[s].nb;
+  }
+};
 
 // K1: radius to the most-bound position (sort key) and the inertia-tensor terms.  Elements of a block mostly belong to
 // one subhalo: then the 12 sums are reduced in the block and issue 12 atomics; mixed blocks reduce per warp / lane.
 __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *__restrict__ subs, int nsub, int64_t B,
                                                                  const float4 *__restrict__ pos, const int *__restrict__ ids, DevConfig cfg,
-                                                                 uint64_t *__restrict__ key, int *__restrict__ val, ProfScratch *__restrict__ scr)
+                                                                 uint64_t *__restrict__ key, int *__restrict__ val, ProfScratch *__restrict__ scr,
+                                                                 SegPartials<12> part)
 {
-  __shared__ double red[12][kPB / 32];
   const int64_t e = (int64_t)blockIdx.x * kPB + threadIdx.x;
   const bool valid = e < B;
-  const int64_t e_first = (int64_t)blockIdx.x * kPB, e_last = min(e_first + kPB, B) - 1;
-  const int s_first = prof_find(subs, nsub, e_first), s_last = prof_find(subs, nsub, e_last);
-  const bool block_uniform = (s_first == s_last) && (e_last == e_first + kPB - 1);
   int s = -1;
+  int64_t seg_begin = 0, seg_end = 0;
   double v[12];
 #pragma unroll
   for (int j = 0; j < 12; j++) v[j] = 0.0;
-  bool contributes = false;
   if (valid)
   {
-    s = block_uniform ? s_first : prof_find(subs, nsub, e);
+    s = prof_find(subs, nsub, e);
     const ProfSub sb = subs[s];
+    seg_begin = sb.bound_off;
+    seg_end = seg_begin + sb.nb;
     const int64_t i = e - sb.bound_off;
     const float4 p = ids ? pos[ids[sb.part_off + i]] : pos[sb.part_off + i]; // ids: the Elist of a resident unbinding batch
     float dx = __fsub_rn(p.x, sb.cx), dy = __fsub_rn(p.y, sb.cy), dz = __fsub_rn(p.z, sb.cz);
@@ -101,7 +116,6 @@ __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *_
     val[e] = (int)(e - sb.bound_off);
     if (i >= 1)
     { // src/subhalo.cpp:354-386: HBTReal products, double accumulation
-      contributes = true;
       const float m = p.w;
       v[0] = (double)__fmul_rn(dx2, m);
       v[1] = (double)__fmul_rn(__fmul_rn(dx, dy), m);
@@ -119,39 +133,16 @@ __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *_
       v[11] = (double)__fdiv_rn(dz2, dr2);
     }
   }
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (block_uniform)
-  {
-#pragma unroll
-    for (int j = 0; j < 12; j++)
-    {
-      const double x = pwarp_sum(v[j]);
-      if (lane == 0) red[j][w] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12)
-    {
-      double x = 0.0;
-      for (int q = 0; q < kPB / 32; q++) x += red[threadIdx.x][q];
-      atomicAdd(&scr[s_first].sums[threadIdx.x], x);
-    }
-    return;
-  }
-  const int s0 = __shfl_sync(0xffffffffu, s, 0);
-  if (__all_sync(0xffffffffu, s == s0) && s0 >= 0)
-  {
-#pragma unroll
-    for (int j = 0; j < 12; j++)
-    {
-      const double x = pwarp_sum(v[j]);
-      if (lane == 0) atomicAdd(&scr[s0].sums[j], x);
-    }
-  }
-  else if (contributes)
-  {
-#pragma unroll
-    for (int j = 0; j < 12; j++) atomicAdd(&scr[s].sums[j], v[j]);
-  }
+  // fixed summation tree (seg_reduce.cuh): the same lists give the same tensors bit for bit
+  seg_reduce_block<12>(v, valid, s, seg_begin, seg_end, B, part, ProfDone{scr});
+}
+
+__global__ void __launch_bounds__(kPB) prof_finish_kernel(const ProfSub *__restrict__ subs, int nsub, int64_t B, SegPartials<12> part,
+                                                           ProfScratch *__restrict__ scr)
+{
+  const int a = blockIdx.x;
+  if (a >= nsub) return;
+  seg_reduce_finish_block<12>(a, B, part, ProfRange{subs}, ProfDone{scr});
 }
 
 struct SortedMass
@@ -167,6 +158,10 @@ struct SortedMass
     const int64_t e = sb.part_off + val[k];
     return (double)pos[ids ? ids[e] : e].w;
   }
+};
+struct PlusD
+{
+  __device__ double operator()(double a, double b) const { return a + b; }
 };
 struct KeySeg
 {
@@ -316,7 +311,11 @@ static void profile_core(Context &c, const hbtu_epoch *epoch, int64_t nsub, cons
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st)); // kernels only: the H2D copies above are queued before it
   if (B > 0)
   {
-    prof_radius_shape_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, (int)nsub, B, d_pos, d_ids, cfg, key_a, val_a, d_scr);
+    static_assert(kPB == kSegBlock, "seg_reduce.cuh blocks");
+    SegPartials<12> part{ar.alloc<double>((int64_t)pgrid(B) * 12), ar.alloc<double>((int64_t)pgrid(B) * 12)};
+    prof_radius_shape_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, (int)nsub, B, d_pos, d_ids, cfg, key_a, val_a, d_scr, part);
+    HBT_CHECK_LAUNCH();
+    prof_finish_kernel<<<(unsigned)nsub, kPB, 0, st>>>(d_subs, (int)nsub, B, part, d_scr);
     HBT_CHECK_LAUNCH();
     int bits = 32;
     while ((1ll << (bits - 32)) < nsub) bits++;
@@ -327,15 +326,11 @@ static void profile_core(Context &c, const hbtu_epoch *epoch, int64_t nsub, cons
     void *tmp = ar.alloc<char>((int64_t)tb);
     HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, B, 0, bits, st));
     skey = dk.Current();
-    auto kin = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), KeySeg{skey});
-    auto vin = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), SortedMass{skey, dv.Current(), d_subs, d_pos, d_ids});
-    size_t sb2 = 0;
-    HBT_CUDA(cub::DeviceScan::InclusiveSumByKey(nullptr, sb2, kin, vin, mcum, B, cub::Equality(), st));
-    void *tmp2 = ar.alloc<char>((int64_t)sb2);
-    HBT_CUDA(cub::DeviceScan::InclusiveSumByKey(tmp2, sb2, kin, vin, mcum, B, cub::Equality(), st));
+    // cumulative mass in double with a fixed combination tree (det_scan.cuh; exact anyway for equal masses)
+    det_inclusive_scan_by_key<double, PlusD>(ar, st, B, SortedMass{skey, dv.Current(), d_subs, d_pos, d_ids}, KeySeg{skey}, 0.0, mcum, c.ls.launches);
     prof_select_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, B, skey, mcum, cfg.softening, rho_virial, d_scr);
     HBT_CHECK_LAUNCH();
-    c.ls.launches += 4 + 1 + (bits + 7) / 8;
+    c.ls.launches += 3 + 1 + (bits + 7) / 8;
   }
   prof_finalize_kernel<<<pgrid(nsub), kPB, 0, st>>>(d_subs, (int)nsub, skey, mcum, d_scr, cfg.softening, velocity_unit, rho_virial,
                                                     cfg.snapshot_index, d_io);

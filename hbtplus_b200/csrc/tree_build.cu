@@ -8,7 +8,7 @@
 //   keys (K1)      63-bit octal key by the reference's own double-precision descent            HBM
 //   sort (K2)      CUB radix sort by key, then stable by segment                               HBM
 //   cells (K3)     one thread per adjacent pair: gallop+bisect for the cell range              latency/L2
-//   scans          cell counts (int) and segmented moment prefix sums (double4)                HBM
+//   scans          cell counts (int, CUB) and segmented moment prefix sums (double4, det_scan.cuh)  HBM
 //   emit (K3/K4)   pre-order node array: particles and cells with mass, CoM, len^2/theta^2, end HBM
 //
 // Every pass is a streaming, coalesced read of 4..32 B per source particle; grids are sized in
@@ -18,6 +18,7 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include "device_tree.cuh"
+#include "det_scan.cuh"
 
 namespace hbt
 {
@@ -225,13 +226,18 @@ struct MomentOp
   const float4 *spos;
   const int *ts_seg;
   const SegRoot *roots;
-  __device__ double4s operator()(int k) const
+  __device__ double4s operator()(int64_t k) const
   {
     float4 p = spos[k];
     const SegRoot &r = roots[ts_seg[k]];
     double m = (double)p.w;
     return double4s{m, m * ((double)p.x - r.cx), m * ((double)p.y - r.cy), m * ((double)p.z - r.cz)};
   }
+};
+struct SegKeyOp
+{
+  const int *ts_seg;
+  __device__ int operator()(int64_t k) const { return ts_seg[k]; }
 };
 struct Double4Plus
 {
@@ -353,13 +359,10 @@ void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t
     ls.launches += 2;
   }
   t.msum = arena.alloc<double4s>(S);
-  {
-    auto in = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), MomentOp{t.spos, t.ts_seg, t.roots});
-    size_t b = 0;
-    HBT_CUDA(cub::DeviceScan::InclusiveScanByKey(nullptr, b, t.ts_seg, in, t.msum, Double4Plus(), S, cub::Equality(), stream));
-    void *tm = arena.alloc<char>((int64_t)b);
-    HBT_CUDA(cub::DeviceScan::InclusiveScanByKey(tm, b, t.ts_seg, in, t.msum, Double4Plus(), S, cub::Equality(), stream));
-    ls.launches += 2;
+  { // segmented prefix sums of m, m*(x - centre) in double with a FIXED combination tree (det_scan.cuh): the node masses and
+    // centres of mass - and with them every potential - are the same bits on every run
+    det_inclusive_scan_by_key<double4s, Double4Plus>(arena, stream, (int64_t)S, MomentOp{t.spos, t.ts_seg, t.roots}, SegKeyOp{t.ts_seg},
+                                                     double4s{0., 0., 0., 0.}, t.msum, ls.launches);
   }
   // nodes ---------------------------------------------------------------------------------------------
   t.node_xm = arena.alloc<float4>(2 * (int64_t)S + 64); // +pad: the walk stages 32 nodes without a bounds check

@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "context.cuh"
+#include "seg_reduce.cuh"
 
 namespace hbt
 {
@@ -517,75 +518,60 @@ __device__ __forceinline__ double warp_sum_d(double v)
   return v;
 }
 
-// accumulate NV doubles per target into subs[sub].sums.  tgt_seg is non-decreasing, so a block whose first and
-// last target share a segment reduces in shared memory and issues NV atomics per BLOCK (the 1e8-particle
-// central would otherwise serialise millions of same-address fp64 atomics); mixed blocks fall back to
-// warp-level aggregation, mixed warps to per-lane atomics.
+// NV fp64 sums per target into subs[sub].sums with a fixed summation tree (seg_reduce.cuh): pass A inside the producing
+// kernel, pass B = seg_finish_kernel.  The same input therefore gives the same bits on every run.
 template <int NV>
-__device__ __forceinline__ void seg_accumulate(const double (&v)[NV], bool contributes, int a, int sub, SubState *subs, bool block_uniform)
+struct SumsDone
 {
-  __shared__ double red[NV][kBlock / 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (block_uniform)
+  const Segment *segs;
+  SubState *subs;
+  __device__ void operator()(int a, const double (&s)[NV]) const
   {
+    SubState &st = subs[segs[a].sub];
 #pragma unroll
-    for (int i = 0; i < NV; i++)
-    {
-      double s = warp_sum_d(contributes ? v[i] : 0.0);
-      if (lane == 0) red[i][w] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV)
-    {
-      double s = 0.0;
-      for (int k = 0; k < kBlock / 32; k++) s += red[threadIdx.x][k];
-      int sub0 = __shfl_sync((1u << NV) - 1u, sub, 0);
-      if (sub0 >= 0 && s != 0.0) atomicAdd(&subs[sub0].sums[threadIdx.x], s);
-    }
-    return;
+    for (int i = 0; i < NV; i++) st.sums[i] = s[i];
   }
-  int a0 = __shfl_sync(0xffffffffu, a, 0);
-  int sub0 = __shfl_sync(0xffffffffu, sub, 0);
-  if (__all_sync(0xffffffffu, a == a0))
+};
+struct TargetRange
+{
+  const Segment *segs;
+  __device__ void operator()(int a, int64_t &begin, int64_t &end) const
   {
-    if (a0 < 0) return;
-    if (!__any_sync(0xffffffffu, contributes)) return;
-#pragma unroll
-    for (int i = 0; i < NV; i++)
-    {
-      double s = warp_sum_d(contributes ? v[i] : 0.0);
-      if (lane == 0) atomicAdd(&subs[sub0].sums[i], s);
-    }
+    begin = segs[a].tgt_off;
+    end = begin + segs[a].tgt_n;
   }
-  else if (contributes)
-  {
-#pragma unroll
-    for (int i = 0; i < NV; i++) atomicAdd(&subs[sub].sums[i], v[i]);
-  }
+};
+template <int NV>
+__global__ void __launch_bounds__(kBlock) seg_finish_kernel(const Segment *__restrict__ segs, int nseg, int64_t T, SegPartials<NV> part,
+                                                             SubState *__restrict__ subs)
+{
+  const int a = blockIdx.x;
+  if (a >= nseg) return;
+  seg_reduce_finish_block<NV>(a, T, part, TargetRange{segs}, SumsDone<NV>{segs, subs});
 }
 
 // EnergySnapshot_t::AverageVelocity / AveragePosition over the first Nbound (src/subhalo_unbind.cpp:108-188)
 __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
                                                                const int *__restrict__ ids, const float4 *__restrict__ pos,
-                                                               const float4 *__restrict__ vel, SubState *__restrict__ subs, DevConfig cfg)
+                                                               const float4 *__restrict__ vel, SubState *__restrict__ subs, DevConfig cfg,
+                                                               SegPartials<7> part)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < T;
   int a = valid ? tgt_seg[t] : -1;
-  const int tb0 = blockIdx.x * blockDim.x, tb1 = min(tb0 + (int)blockDim.x, T) - 1;
-  const bool block_uniform = (tb1 == tb0 + (int)blockDim.x - 1) && tgt_seg[tb0] == tgt_seg[tb1];
   int sub = -1;
-  bool contributes = false;
+  int64_t seg_begin = 0, seg_end = 0;
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
   if (valid)
   {
     const Segment sg = segs[a];
     sub = sg.sub;
+    seg_begin = sg.tgt_off;
+    seg_end = seg_begin + sg.tgt_n;
     const SubState &st = subs[sub];
     int j = t - sg.tgt_off;
     if (st.status != kDisrupted && j < st.nbound)
     {
-      contributes = true;
       int id = ids[sg.slot_base + j];
       float4 x = pos[id], u = vel[id];
       float m = x.w;
@@ -608,7 +594,7 @@ __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__r
       }
     }
   }
-  seg_accumulate<7>(v, contributes, a, sub, subs, block_uniform);
+  seg_reduce_block<7>(v, valid, a, seg_begin, seg_end, (int64_t)T, part, SumsDone<7>{segs, subs});
 }
 
 __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
@@ -647,25 +633,24 @@ __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubSta
 __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
                                                              const int *__restrict__ ids, const float *__restrict__ E,
                                                              const float4 *__restrict__ pos, const float4 *__restrict__ vel,
-                                                             SubState *__restrict__ subs, DevConfig cfg)
+                                                             SubState *__restrict__ subs, DevConfig cfg, SegPartials<6> part)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < T;
   int a = valid ? tgt_seg[t] : -1;
-  const int tb0 = blockIdx.x * blockDim.x, tb1 = min(tb0 + (int)blockDim.x, T) - 1;
-  const bool block_uniform = (tb1 == tb0 + (int)blockDim.x - 1) && tgt_seg[tb0] == tgt_seg[tb1];
   int sub = -1;
-  bool contributes = false;
+  int64_t seg_begin = 0, seg_end = 0;
   double v[6] = {0, 0, 0, 0, 0, 0};
   if (valid)
   {
     const Segment sg = segs[a];
     sub = sg.sub;
+    seg_begin = sg.tgt_off;
+    seg_end = seg_begin + sg.tgt_n;
     const SubState &st = subs[sub];
     int j = t - sg.tgt_off;
     if (st.status == kConverged && j < st.nbound)
     {
-      contributes = true;
       int64_t slot = sg.slot_base + j;
       int id = ids[slot];
       float4 x = pos[id], u = vel[id];
@@ -688,7 +673,7 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
       v[5] = (double)m;
     }
   }
-  seg_accumulate<6>(v, contributes, a, sub, subs, block_uniform);
+  seg_reduce_block<6>(v, valid, a, seg_begin, seg_end, (int64_t)T, part, SumsDone<6>{segs, subs});
 }
 
 struct RoundResult
@@ -954,12 +939,21 @@ static void run_round(Context &c, std::vector<int> &active)
     HBT_CHECK_LAUNCH();
     c.ls.launches += 2;
   }
-  frame_reduce_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_pos, c.d_vel, c.d_subs, c.cfg);
+  static_assert(kBlock == kSegBlock, "seg_reduce.cuh blocks");
+  const int64_t nblk = grid_for(T);
+  SegPartials<7> part7{ar.alloc<double>(nblk * 7), ar.alloc<double>(nblk * 7)};
+  SegPartials<6> part6{part7.head, part7.tail}; // reused after state2 has consumed the frame sums
+  frame_reduce_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_pos, c.d_vel, c.d_subs, c.cfg, part7);
+  HBT_CHECK_LAUNCH();
+  seg_finish_kernel<7><<<nseg, kBlock, 0, st>>>(d_segs, nseg, T, part7, c.d_subs);
   HBT_CHECK_LAUNCH();
   state2_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, c.cfg);
   HBT_CHECK_LAUNCH();
-  kinematics_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg);
+  kinematics_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg, part6);
   HBT_CHECK_LAUNCH();
+  seg_finish_kernel<6><<<nseg, kBlock, 0, st>>>(d_segs, nseg, T, part6, c.d_subs);
+  HBT_CHECK_LAUNCH();
+  c.ls.launches += 2;
   RoundResult *d_res = ar.alloc<RoundResult>(nseg);
   finalize_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, d_res);
   HBT_CHECK_LAUNCH();
