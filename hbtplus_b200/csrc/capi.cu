@@ -239,6 +239,7 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
   tr.S = S;
   tr.nseg = 1;
   tr.tree_off = d_tree_off;
+  tr.h_tree_off = tree_off.data();
   tr.tpos = ar.alloc<float4>(S);
   tr.ts_seg = ar.alloc<int>(S);
   tr.bbox = ar.alloc<uint32_t>(6);

@@ -1,15 +1,20 @@
-// det_scan.cuh - run-to-run deterministic inclusive scan-by-key for floating-point values (sm_100a).
+// det_scan.cuh - deterministic, composition-invariant inclusive prefix sums inside segments (sm_100a).
 //
 // cub::DeviceScan::*ByKey is a single-pass scan with decoupled look-back: how the partial sums of earlier tiles are
 // grouped depends on the order in which tiles happen to publish them, so for fp64 addition (not associative) the last
 // bit of a prefix can change from run to run.  The node moments of the octree and the cumulative masses of the density
-// profiles must not: this is the classic three-kernel reduce-then-scan with a fixed combination tree,
-//   K1  tile summaries   (segmented aggregate of every 1024-element tile, cub::BlockScan: fixed order)
-//   K2  one block scans the tile summaries in order (running carry) -> carry-in of every tile
-//   K3  every tile scans its elements starting from its carry-in and writes the prefixes.
+// profiles must not - and they must not depend on WHERE in a batch a subhalo sits either (another sharding over GPUs has
+// to give the same catalogue).  So the combination tree is fixed and aligned to each segment:
+//   K1  tile sums        every segment is cut into 1024-element tiles counted from ITS first element; cub::BlockReduce
+//   K2  one block per segment scans that segment's tile sums in order (running carry) -> carry-in of every tile
+//   K3  every tile scans its elements (cub::BlockScan) starting from its carry-in and writes the prefixes.
+// The tile table (tile_off[a] = number of tiles of the segments before a) comes from the host: O(nseg).
 // Reads the input twice (values come from a functor, typically 20-24 B per element) and writes it once.
 #pragma once
+#include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,125 +23,122 @@ namespace hbt
 
 constexpr int kScanThreads = 256, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
 
-template <class V>
-struct SegVal
-{ // segmented-scan element: `head` = a segment starts at (or inside) this partial result
-  V v;
-  int head;
-};
-template <class V, class Plus>
-struct SegOp
+// largest a in [0,n) with off[a] <= k (off non-decreasing; empty segments share their successor's offset and are skipped)
+__device__ __forceinline__ int scan_find(const int *__restrict__ off, int n, int k)
 {
-  Plus plus;
-  __device__ __forceinline__ SegVal<V> operator()(const SegVal<V> &a, const SegVal<V> &b) const
+  int lo = 0, hi = n;
+  while (hi - lo > 1)
   {
-    SegVal<V> r;
-    r.head = a.head | b.head;
-    r.v = b.head ? b.v : plus(a.v, b.v);
-    return r;
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= k) lo = mid; else hi = mid;
   }
-};
+  return lo;
+}
 
-template <class V, class ValFn, class KeyFn>
-__device__ __forceinline__ void scan_load(int64_t base, int64_t n, ValFn val, KeyFn key, V zero, SegVal<V> (&x)[kScanItems])
+template <class V, class ValFn>
+__device__ __forceinline__ void scan_load(int64_t first, int64_t seg_end, ValFn val, V zero, V (&x)[kScanItems])
 {
-  const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+  const int64_t i0 = first + (int64_t)threadIdx.x * kScanItems;
 #pragma unroll
-  for (int j = 0; j < kScanItems; j++)
-  {
-    const int64_t i = i0 + j;
-    if (i < n)
-    {
-      x[j].v = val(i);
-      x[j].head = (i == 0 || key(i) != key(i - 1)) ? 1 : 0;
-    }
-    else
-    { // padding behaves like a new, empty segment
-      x[j].v = zero;
-      x[j].head = 1;
-    }
-  }
+  for (int j = 0; j < kScanItems; j++) x[j] = (i0 + j < seg_end) ? val(i0 + j) : zero;
 }
 
-template <class V, class Plus, class ValFn, class KeyFn>
-__global__ void __launch_bounds__(kScanThreads) det_scan_summary_kernel(int64_t n, ValFn val, KeyFn key, V zero, SegVal<V> *__restrict__ summary)
+template <class V, class Plus, class ValFn>
+__global__ void __launch_bounds__(kScanThreads) det_scan_sums_kernel(const int *__restrict__ seg_off, const int *__restrict__ tile_off, int nseg, ValFn val,
+                                                                      V zero, V *__restrict__ tile_sum)
 {
-  using BlockScan = cub::BlockScan<SegVal<V>, kScanThreads>;
-  __shared__ typename BlockScan::TempStorage tmp;
-  SegVal<V> x[kScanItems];
-  scan_load<V>((int64_t)blockIdx.x * kScanTile, n, val, key, zero, x);
-  SegVal<V> agg;
-  BlockScan(tmp).InclusiveScan(x, x, SegOp<V, Plus>(), agg);
-  if (threadIdx.x == 0) summary[blockIdx.x] = agg;
+  using BlockReduce = cub::BlockReduce<V, kScanThreads>;
+  __shared__ typename BlockReduce::TempStorage tmp;
+  const int a = scan_find(tile_off, nseg, (int)blockIdx.x);
+  const int64_t first = (int64_t)seg_off[a] + (int64_t)((int)blockIdx.x - tile_off[a]) * kScanTile;
+  V x[kScanItems];
+  scan_load<V>(first, seg_off[a + 1], val, zero, x);
+  const V s = BlockReduce(tmp).Reduce(x, Plus());
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
 }
 
-// one block: carry[t] = summaries 0..t-1 combined in order
+// one block per segment: carry[t] = sum of the segment's tile sums before tile t, combined in order
 template <class V, class Plus>
-__global__ void __launch_bounds__(kScanThreads) det_scan_carry_kernel(int64_t ntiles, const SegVal<V> *__restrict__ summary, V zero,
-                                                                       SegVal<V> *__restrict__ carry)
+__global__ void __launch_bounds__(kScanThreads) det_scan_carry_kernel(const int *__restrict__ tile_off, V zero, const V *__restrict__ tile_sum,
+                                                                       V *__restrict__ carry)
 {
-  using BlockScan = cub::BlockScan<SegVal<V>, kScanThreads>;
+  using BlockScan = cub::BlockScan<V, kScanThreads>;
   __shared__ typename BlockScan::TempStorage tmp;
-  __shared__ SegVal<V> running;
-  if (threadIdx.x == 0)
+  __shared__ V running;
+  const int t0 = tile_off[blockIdx.x], t1 = tile_off[blockIdx.x + 1];
+  if (t1 - t0 <= 1)
   {
-    running.v = zero;
-    running.head = 1;
+    if (t1 - t0 == 1 && threadIdx.x == 0) carry[t0] = zero;
+    return;
   }
+  if (threadIdx.x == 0) running = zero;
   __syncthreads();
-  SegOp<V, Plus> op{};
-  for (int64_t base = 0; base < ntiles; base += kScanTile)
+  Plus plus{};
+  for (int base = t0; base < t1; base += kScanTile)
   {
-    SegVal<V> x[kScanItems];
-    const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+    V x[kScanItems];
+    const int i0 = base + (int)threadIdx.x * kScanItems;
 #pragma unroll
-    for (int j = 0; j < kScanItems; j++)
-    {
-      if (i0 + j < ntiles) x[j] = summary[i0 + j];
-      else { x[j].v = zero; x[j].head = 1; }
-    }
-    SegVal<V> agg;
-    BlockScan(tmp).ExclusiveScan(x, x, op, agg); // x[j] = combination of this chunk's summaries before i0+j (undefined for the first)
-    const SegVal<V> run = running;
+    for (int j = 0; j < kScanItems; j++) x[j] = (i0 + j < t1) ? tile_sum[i0 + j] : zero;
+    V agg;
+    BlockScan(tmp).ExclusiveScan(x, x, zero, plus, agg);
+    const V run = running;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kScanItems; j++)
-      if (i0 + j < ntiles) carry[i0 + j] = (threadIdx.x == 0 && j == 0) ? run : op(run, x[j]);
-    if (threadIdx.x == 0) running = op(run, agg);
+      if (i0 + j < t1) carry[i0 + j] = plus(run, x[j]);
+    if (threadIdx.x == 0) running = plus(run, agg);
     __syncthreads();
   }
 }
 
-template <class V, class Plus, class ValFn, class KeyFn>
-__global__ void __launch_bounds__(kScanThreads) det_scan_apply_kernel(int64_t n, ValFn val, KeyFn key, V zero, const SegVal<V> *__restrict__ carry,
-                                                                       V *__restrict__ out)
+template <class V, class Plus, class ValFn>
+__global__ void __launch_bounds__(kScanThreads) det_scan_apply_kernel(const int *__restrict__ seg_off, const int *__restrict__ tile_off, int nseg, ValFn val,
+                                                                       V zero, const V *__restrict__ carry, V *__restrict__ out)
 {
-  using BlockScan = cub::BlockScan<SegVal<V>, kScanThreads>;
+  using BlockScan = cub::BlockScan<V, kScanThreads>;
   __shared__ typename BlockScan::TempStorage tmp;
-  SegVal<V> x[kScanItems];
-  const int64_t base = (int64_t)blockIdx.x * kScanTile;
-  scan_load<V>(base, n, val, key, zero, x);
-  SegOp<V, Plus> op{};
-  BlockScan(tmp).InclusiveScan(x, x, op);
-  const SegVal<V> c = carry[blockIdx.x];
-  const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+  const int a = scan_find(tile_off, nseg, (int)blockIdx.x);
+  const int64_t first = (int64_t)seg_off[a] + (int64_t)((int)blockIdx.x - tile_off[a]) * kScanTile;
+  const int64_t seg_end = seg_off[a + 1];
+  V x[kScanItems];
+  scan_load<V>(first, seg_end, val, zero, x);
+  Plus plus{};
+  BlockScan(tmp).InclusiveScan(x, x, plus);
+  const V c = carry[blockIdx.x];
+  const int64_t i0 = first + (int64_t)threadIdx.x * kScanItems;
 #pragma unroll
   for (int j = 0; j < kScanItems; j++)
-    if (i0 + j < n) out[i0 + j] = op(c, x[j]).v;
+    if (i0 + j < seg_end) out[i0 + j] = plus(c, x[j]);
 }
 
-// out[i] = plus-combination of val(j) over the j <= i with key(j) == key(i) (keys are grouped), in a fixed order
-template <class V, class Plus, class ValFn, class KeyFn>
-inline void det_inclusive_scan_by_key(Arena &arena, cudaStream_t stream, int64_t n, ValFn val, KeyFn key, V zero, V *out, int64_t &launches)
+// host: tile table of segments given by element offsets seg_off[0..nseg]
+inline int scan_tile_table(const int *seg_off, int nseg, std::vector<int> &tile_off)
 {
-  if (n <= 0) return;
-  const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  SegVal<V> *summary = arena.alloc<SegVal<V>>(ntiles), *carry = arena.alloc<SegVal<V>>(ntiles);
-  det_scan_summary_kernel<V, Plus><<<(unsigned)ntiles, kScanThreads, 0, stream>>>(n, val, key, zero, summary);
+  tile_off.resize((size_t)nseg + 1);
+  int t = 0;
+  for (int a = 0; a < nseg; a++)
+  {
+    tile_off[a] = t;
+    t += (seg_off[a + 1] - seg_off[a] + kScanTile - 1) / kScanTile;
+  }
+  tile_off[nseg] = t;
+  return t;
+}
+
+// out[i] = val(first element of i's segment) + ... + val(i), combined in a fixed order that depends only on the segment
+//   d_seg_off / d_tile_off: device copies of the element offsets and of scan_tile_table(); ntiles = tile_off[nseg]
+template <class V, class Plus, class ValFn>
+inline void det_inclusive_scan_segments(Arena &arena, cudaStream_t stream, const int *d_seg_off, const int *d_tile_off, int nseg, int ntiles, ValFn val,
+                                        V zero, V *out, int64_t &launches)
+{
+  if (ntiles <= 0 || nseg <= 0) return;
+  V *tile_sum = arena.alloc<V>(ntiles), *carry = arena.alloc<V>(ntiles);
+  det_scan_sums_kernel<V, Plus><<<(unsigned)ntiles, kScanThreads, 0, stream>>>(d_seg_off, d_tile_off, nseg, val, zero, tile_sum);
   HBT_CHECK_LAUNCH();
-  det_scan_carry_kernel<V, Plus><<<1, kScanThreads, 0, stream>>>(ntiles, summary, zero, carry);
+  det_scan_carry_kernel<V, Plus><<<(unsigned)nseg, kScanThreads, 0, stream>>>(d_tile_off, zero, tile_sum, carry);
   HBT_CHECK_LAUNCH();
-  det_scan_apply_kernel<V, Plus><<<(unsigned)ntiles, kScanThreads, 0, stream>>>(n, val, key, zero, carry, out);
+  det_scan_apply_kernel<V, Plus><<<(unsigned)ntiles, kScanThreads, 0, stream>>>(d_seg_off, d_tile_off, nseg, val, zero, carry, out);
   HBT_CHECK_LAUNCH();
   launches += 3;
 }

@@ -108,6 +108,7 @@ struct TreeArrays
   SegRoot *roots = nullptr;
   uint32_t *bbox = nullptr; // 6 ordered-uint per segment
   const int *tree_off = nullptr; // [nseg+1] device
+  const int *h_tree_off = nullptr; // the same on the host (tile table of the deterministic moment scan)
 };
 
 struct LaunchStats

@@ -70,37 +70,24 @@ struct ProfDone
     for (int j = 0; j < 12; j++) scr[s].sums[j] = x[j];
   }
 };
-struct ProfRange
-{
-  const ProfSub *subs;
-  __device__ void operator()(int s, int64_t &begin, int64_t &end) const
-  {
-    begin = subs[s].bound_off;
-    end = begin + subs[s].nb;
-  }
-};
 
-// K1: radius to the most-bound position (sort key) and the inertia-tensor terms.  Elements of a block mostly belong to
-// one subhalo: then the 12 sums are reduced in the block and issue 12 atomics; mixed blocks reduce per warp / lane.
-__global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *__restrict__ subs, int nsub, int64_t B,
+// K1: radius to the most-bound position (sort key) and the inertia-tensor terms.  Block b works on one 256-particle chunk
+// of one subhalo's bound list (chunk table, seg_reduce.cuh), so the tensor sums have a summation tree that depends on the
+// subhalo alone.
+__global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *__restrict__ subs, int nsub, const int *__restrict__ chunk_off,
                                                                  const float4 *__restrict__ pos, const int *__restrict__ ids, DevConfig cfg,
-                                                                 uint64_t *__restrict__ key, int *__restrict__ val, ProfScratch *__restrict__ scr,
-                                                                 SegPartials<12> part)
+                                                                 uint64_t *__restrict__ key, int *__restrict__ val, double *__restrict__ partial)
 {
-  const int64_t e = (int64_t)blockIdx.x * kPB + threadIdx.x;
-  const bool valid = e < B;
-  int s = -1;
-  int64_t seg_begin = 0, seg_end = 0;
+  int s, c;
+  seg_chunk_of_block(chunk_off, nsub, blockIdx.x, s, c);
+  const ProfSub sb = subs[s];
+  const int i = c * kPB + threadIdx.x;
   double v[12];
 #pragma unroll
   for (int j = 0; j < 12; j++) v[j] = 0.0;
-  if (valid)
+  if (i < sb.nb)
   {
-    s = prof_find(subs, nsub, e);
-    const ProfSub sb = subs[s];
-    seg_begin = sb.bound_off;
-    seg_end = seg_begin + sb.nb;
-    const int64_t i = e - sb.bound_off;
+    const int64_t e = sb.bound_off + i;
     const float4 p = ids ? pos[ids[sb.part_off + i]] : pos[sb.part_off + i]; // ids: the Elist of a resident unbinding batch
     float dx = __fsub_rn(p.x, sb.cx), dy = __fsub_rn(p.y, sb.cy), dz = __fsub_rn(p.z, sb.cz);
     // the reference takes cen - pos for the radius and pos - cen for the tensor: the squares and the pair products agree
@@ -113,7 +100,7 @@ __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *_
     const float dx2 = __fmul_rn(dx, dx), dy2 = __fmul_rn(dy, dy), dz2 = __fmul_rn(dz, dz);
     const float r = __fsqrt_rn(__fadd_rn(__fadd_rn(dx2, dy2), dz2)); // PeriodicDistance
     key[e] = ((uint64_t)(uint32_t)s << 32) | __float_as_uint(r);
-    val[e] = (int)(e - sb.bound_off);
+    val[e] = i;
     if (i >= 1)
     { // src/subhalo.cpp:354-386: HBTReal products, double accumulation
       const float m = p.w;
@@ -133,16 +120,15 @@ __global__ void __launch_bounds__(kPB) prof_radius_shape_kernel(const ProfSub *_
       v[11] = (double)__fdiv_rn(dz2, dr2);
     }
   }
-  // fixed summation tree (seg_reduce.cuh): the same lists give the same tensors bit for bit
-  seg_reduce_block<12>(v, valid, s, seg_begin, seg_end, B, part, ProfDone{scr});
+  seg_reduce_chunk<12>(v, partial);
 }
 
-__global__ void __launch_bounds__(kPB) prof_finish_kernel(const ProfSub *__restrict__ subs, int nsub, int64_t B, SegPartials<12> part,
+__global__ void __launch_bounds__(kPB) prof_finish_kernel(int nsub, const int *__restrict__ chunk_off, const double *__restrict__ partial,
                                                            ProfScratch *__restrict__ scr)
 {
   const int a = blockIdx.x;
   if (a >= nsub) return;
-  seg_reduce_finish_block<12>(a, B, part, ProfRange{subs}, ProfDone{scr});
+  seg_reduce_finish_block<12>(a, chunk_off, partial, ProfDone{scr});
 }
 
 struct SortedMass
@@ -162,11 +148,6 @@ struct SortedMass
 struct PlusD
 {
   __device__ double operator()(double a, double b) const { return a + b; }
-};
-struct KeySeg
-{
-  const uint64_t *key;
-  __device__ int operator()(int64_t k) const { return (int)(key[k] >> 32); }
 };
 
 // K3: per sorted element: v^2 = M(<r)/max(r, eps) (src/subhalo.cpp:302-306), argmax, overdensity test (src/snapshot.cpp:272-280)
@@ -307,15 +288,25 @@ static void profile_core(Context &c, const hbtu_epoch *epoch, int64_t nsub, cons
   uint64_t *key_a = ar.alloc<uint64_t>(B), *key_b = ar.alloc<uint64_t>(B);
   int *val_a = ar.alloc<int>(B), *val_b = ar.alloc<int>(B);
   double *mcum = ar.alloc<double>(B);
+  if (B > 0x7fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "more than 2^31 bound particles in one batch"};
   const uint64_t *skey = key_a;
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st)); // kernels only: the H2D copies above are queued before it
   if (B > 0)
   {
     static_assert(kPB == kSegBlock, "seg_reduce.cuh blocks");
-    SegPartials<12> part{ar.alloc<double>((int64_t)pgrid(B) * 12), ar.alloc<double>((int64_t)pgrid(B) * 12)};
-    prof_radius_shape_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, (int)nsub, B, d_pos, d_ids, cfg, key_a, val_a, d_scr, part);
+    std::vector<int> chunk_off, bound_off32((size_t)nsub + 1), tile_off;
+    const int nchunk = seg_chunk_table((int)nsub, [&](int a) { return subs[a].nb; }, chunk_off);
+    for (int64_t a = 0; a < nsub; a++) bound_off32[a] = (int)subs[a].bound_off;
+    bound_off32[nsub] = (int)B;
+    const int ntiles = scan_tile_table(bound_off32.data(), (int)nsub, tile_off);
+    int *d_chunk_off = ar.alloc<int>(nsub + 1), *d_bound_off = ar.alloc<int>(nsub + 1), *d_tile_off = ar.alloc<int>(nsub + 1);
+    HBT_CUDA(cudaMemcpyAsync(d_chunk_off, chunk_off.data(), sizeof(int) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
+    HBT_CUDA(cudaMemcpyAsync(d_bound_off, bound_off32.data(), sizeof(int) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
+    HBT_CUDA(cudaMemcpyAsync(d_tile_off, tile_off.data(), sizeof(int) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
+    double *partial = ar.alloc<double>((int64_t)nchunk * 12);
+    prof_radius_shape_kernel<<<nchunk, kPB, 0, st>>>(d_subs, (int)nsub, d_chunk_off, d_pos, d_ids, cfg, key_a, val_a, partial);
     HBT_CHECK_LAUNCH();
-    prof_finish_kernel<<<(unsigned)nsub, kPB, 0, st>>>(d_subs, (int)nsub, B, part, d_scr);
+    prof_finish_kernel<<<(unsigned)nsub, kPB, 0, st>>>((int)nsub, d_chunk_off, partial, d_scr);
     HBT_CHECK_LAUNCH();
     int bits = 32;
     while ((1ll << (bits - 32)) < nsub) bits++;
@@ -326,8 +317,11 @@ static void profile_core(Context &c, const hbtu_epoch *epoch, int64_t nsub, cons
     void *tmp = ar.alloc<char>((int64_t)tb);
     HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, B, 0, bits, st));
     skey = dk.Current();
-    // cumulative mass in double with a fixed combination tree (det_scan.cuh; exact anyway for equal masses)
-    det_inclusive_scan_by_key<double, PlusD>(ar, st, B, SortedMass{skey, dv.Current(), d_subs, d_pos, d_ids}, KeySeg{skey}, 0.0, mcum, c.ls.launches);
+    // cumulative mass in double with a fixed combination tree aligned to each subhalo (det_scan.cuh; exact anyway for equal
+    // masses).  The sorted array keeps every subhalo in its own range [bound_off, bound_off + nb).
+    det_inclusive_scan_segments<double, PlusD>(ar, st, d_bound_off, d_tile_off, (int)nsub, ntiles, SortedMass{skey, dv.Current(), d_subs, d_pos, d_ids},
+                                               0.0, mcum, c.ls.launches);
+    HBT_CUDA(cudaStreamSynchronize(st)); // the tables above are host temporaries
     prof_select_kernel<<<pgrid(B), kPB, 0, st>>>(d_subs, B, skey, mcum, cfg.softening, rho_virial, d_scr);
     HBT_CHECK_LAUNCH();
     c.ls.launches += 3 + 1 + (bits + 7) / 8;

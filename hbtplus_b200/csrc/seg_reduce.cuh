@@ -1,32 +1,54 @@
-// seg_reduce.cuh - deterministic segmented sums of NV doubles per element (sm_100a).
+// seg_reduce.cuh - deterministic, composition-invariant segmented sums of NV doubles per element (sm_100a).
 //
-// Elements 0..N-1 are grouped into contiguous segments (subhaloes).  fp64 addition is not associative, so sums that are
-// combined by atomics depend on the order in which blocks happen to finish; the reductions of the unbinding path
-// (frames, kinematics, inertia tensors) instead use a FIXED summation tree, so that the same input gives the same bits:
+// Elements are grouped into contiguous segments (subhaloes).  fp64 addition is not associative, so sums combined by
+// atomics depend on the order in which blocks happen to finish, and sums over blocks aligned to the batch depend on where
+// in the batch a subhalo sits.  The reductions of the unbinding path (frames, kinematics, inertia tensors) use a FIXED
+// summation tree aligned to each segment, so the same subhalo gives the same bits on every run and in every batch:
 //
-//   pass A (at the end of the producing kernel, one call per 256-thread block): the block's elements are cut into
-//           pieces by segment.  A block that lies inside one segment reduces with a fixed shuffle/shared-memory tree;
-//           a block that straddles segments lets NV threads walk its staged values in element order.  A piece that is a
-//           whole segment is final and handed to `done`; the piece of a segment that began in an earlier block goes to
-//           head[block], the piece of a segment that continues in a later block to tail[block].
-//   pass B (seg_reduce_finish_block, one block per segment that spans several blocks):
-//           total = tail[first block] + (head[] of the blocks in between, strided over the threads in a fixed order,
-//           fixed block tree) + head[last block].
+//   pass A (inside the producing kernel): every segment is cut into 256-element chunks counted from ITS first element;
+//           block b works on chunk (a, c) found through the chunk table, reduces its NV sums with a fixed shuffle /
+//           shared-memory tree and stores them in partial[b].
+//   pass B (seg_reduce_finish_block, one block per segment): thread j adds the segment's chunks j, j+256, .. in order,
+//           then the same fixed block tree.
+// The chunk table (chunk_off[a] = number of chunks of the segments before a) comes from the host: O(nseg).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace hbt
 {
 
-constexpr int kSegBlock = 256; // threads (= elements) per block of pass A
+constexpr int kSegBlock = 256; // threads (= elements) per chunk
 
-template <int NV>
-struct SegPartials
+// host: chunk table for segment lengths len[0..nseg)
+template <class LenFn>
+inline int seg_chunk_table(int nseg, LenFn len, std::vector<int> &chunk_off)
 {
-  double *head; // [nblocks][NV] piece of the segment that was already open when the block started
-  double *tail; // [nblocks][NV] piece of the segment that continues after the block (and did not start before it)
-};
+  chunk_off.resize((size_t)nseg + 1);
+  int64_t t = 0;
+  for (int a = 0; a < nseg; a++)
+  {
+    chunk_off[a] = (int)t;
+    t += ((int64_t)len(a) + kSegBlock - 1) / kSegBlock;
+  }
+  chunk_off[nseg] = (int)t;
+  return (int)t;
+}
+
+// device: segment and chunk of block b (largest a with chunk_off[a] <= b; empty segments are skipped)
+__device__ __forceinline__ void seg_chunk_of_block(const int *__restrict__ chunk_off, int nseg, int b, int &a, int &c)
+{
+  int lo = 0, hi = nseg;
+  while (hi - lo > 1)
+  {
+    int mid = (lo + hi) >> 1;
+    if (chunk_off[mid] <= b) lo = mid; else hi = mid;
+  }
+  a = lo;
+  c = b - chunk_off[lo];
+}
 
 __device__ __forceinline__ double seg_warp_sum(double v)
 {
@@ -34,119 +56,12 @@ __device__ __forceinline__ double seg_warp_sum(double v)
   return v;
 }
 
-// Pass A.  Every thread of the block calls it (also threads past the end, with valid = false).
-//   v                the thread's contribution (ignored when !valid)
-//   seg              segment of the thread's element; seg_begin/seg_end: element range of that segment
-//   done(seg, s)     called by ONE thread per finished segment with the NV sums
-template <int NV, class DoneFn>
-__device__ __forceinline__ void seg_reduce_block(const double (&v)[NV], bool valid, int seg, int64_t seg_begin, int64_t seg_end, int64_t n_total,
-                                                 const SegPartials<NV> &part, DoneFn done)
-{
-  __shared__ double s_val[kSegBlock][NV];
-  __shared__ int s_seg[kSegBlock];
-  __shared__ int64_t s_rng[kSegBlock][2];
-  __shared__ double s_red[NV][kSegBlock / 32];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int64_t block_begin = (int64_t)blockIdx.x * kSegBlock;
-  const int64_t block_end = block_begin + kSegBlock < n_total ? block_begin + kSegBlock : n_total;
-  const int nvalid = (int)(block_end - block_begin);
-  s_seg[tid] = valid ? seg : -1;
-  __syncthreads();
-  const bool uniform = nvalid > 0 && s_seg[0] == s_seg[nvalid - 1]; // segments are contiguous
-  if (uniform)
-  {
-#pragma unroll
-    for (int i = 0; i < NV; i++)
-    {
-      const double s = seg_warp_sum(valid ? v[i] : 0.0);
-      if (lane == 0) s_red[i][w] = s;
-    }
-    __syncthreads();
-    if (tid == 0)
-    {
-      double s[NV];
-#pragma unroll
-      for (int i = 0; i < NV; i++)
-      {
-        double x = 0.0;
-        for (int k = 0; k < kSegBlock / 32; k++) x += s_red[i][k];
-        s[i] = x;
-      }
-      const bool before = seg_begin < block_begin, after = seg_end > block_end;
-      if (!before && !after) done(seg, s);
-      else
-      {
-        double *dst = (before ? part.head : part.tail) + (int64_t)blockIdx.x * NV;
-#pragma unroll
-        for (int i = 0; i < NV; i++) dst[i] = s[i];
-      }
-    }
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < NV; i++) s_val[tid][i] = valid ? v[i] : 0.0;
-  s_rng[tid][0] = seg_begin;
-  s_rng[tid][1] = seg_end;
-  __syncthreads();
-  if (tid < NV)
-  { // component tid of every piece, in element order
-    int i = 0;
-    while (i < nvalid)
-    {
-      const int a = s_seg[i];
-      double x = 0.0;
-      int j = i;
-      for (; j < nvalid && s_seg[j] == a; j++) x += s_val[j][tid];
-      const bool before = s_rng[i][0] < block_begin, after = s_rng[i][1] > block_end;
-      if (before) part.head[(int64_t)blockIdx.x * NV + tid] = x;
-      else if (after) part.tail[(int64_t)blockIdx.x * NV + tid] = x;
-      else s_red[tid][0] = x; // whole segment inside the block: collected below
-      if (!before && !after)
-      {
-        // all NV components of this piece must reach `done` together: thread 0 gathers them
-        __syncwarp((1u << NV) - 1u);
-        if (tid == 0)
-        {
-          double s[NV];
-#pragma unroll
-          for (int c = 0; c < NV; c++) s[c] = s_red[c][0];
-          done(a, s);
-        }
-        __syncwarp((1u << NV) - 1u);
-      }
-      i = j;
-    }
-  }
-}
-
-// Pass B: one 256-thread block per segment (blockIdx.x = segment).  seg_range(a, begin, end) gives the element range;
-// done(a, s) as in pass A.  Thread j adds the middle blocks j, j+256, .. in order, then the fixed block tree.
-template <int NV, class RangeFn, class DoneFn>
-__device__ __forceinline__ void seg_reduce_finish_block(int a, int64_t n_total, const SegPartials<NV> &part, RangeFn seg_range, DoneFn done)
+// fixed block tree: xor-shuffle inside warps, then warp sums added in warp order by thread 0.  Result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void seg_block_sum(double (&s)[NV])
 {
   __shared__ double s_red[NV][kSegBlock / 32];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int64_t begin, end;
-  seg_range(a, begin, end);
-  if (end <= begin)
-  {
-    if (tid == 0)
-    {
-      double s[NV];
-#pragma unroll
-      for (int i = 0; i < NV; i++) s[i] = 0.0;
-      done(a, s);
-    }
-    return;
-  }
-  const int64_t b0 = begin / kSegBlock, b1 = (end - 1) / kSegBlock;
-  if (b0 == b1) return; // finished in pass A
-  double s[NV];
-#pragma unroll
-  for (int i = 0; i < NV; i++) s[i] = 0.0;
-  for (int64_t b = b0 + 1 + tid; b < b1; b += kSegBlock)
-#pragma unroll
-    for (int i = 0; i < NV; i++) s[i] += part.head[b * NV + i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NV; i++)
   {
@@ -154,17 +69,43 @@ __device__ __forceinline__ void seg_reduce_finish_block(int a, int64_t n_total, 
     if (lane == 0) s_red[i][w] = x;
   }
   __syncthreads();
-  if (tid == 0)
+  if (threadIdx.x == 0)
   {
 #pragma unroll
     for (int i = 0; i < NV; i++)
     {
       double x = 0.0;
       for (int k = 0; k < kSegBlock / 32; k++) x += s_red[i][k];
-      s[i] = (part.tail[b0 * NV + i] + x) + part.head[b1 * NV + i];
+      s[i] = x;
     }
-    done(a, s);
   }
+}
+
+// Pass A: every thread of the block calls it with its contribution (zeros when it has no element).
+template <int NV>
+__device__ __forceinline__ void seg_reduce_chunk(double (&v)[NV], double *__restrict__ partial)
+{
+  seg_block_sum<NV>(v);
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int i = 0; i < NV; i++) partial[(int64_t)blockIdx.x * NV + i] = v[i];
+  }
+}
+
+// Pass B: one 256-thread block per segment a; done(a, s) is called by thread 0 with the NV sums.
+template <int NV, class DoneFn>
+__device__ __forceinline__ void seg_reduce_finish_block(int a, const int *__restrict__ chunk_off, const double *__restrict__ partial, DoneFn done)
+{
+  const int c0 = chunk_off[a], c1 = chunk_off[a + 1];
+  double s[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) s[i] = 0.0;
+  for (int c = c0 + (int)threadIdx.x; c < c1; c += kSegBlock)
+#pragma unroll
+    for (int i = 0; i < NV; i++) s[i] += partial[(int64_t)c * NV + i];
+  seg_block_sum<NV>(s);
+  if (threadIdx.x == 0) done(a, s);
 }
 
 } // namespace hbt

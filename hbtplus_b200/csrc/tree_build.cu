@@ -234,11 +234,6 @@ struct MomentOp
     return double4s{m, m * ((double)p.x - r.cx), m * ((double)p.y - r.cy), m * ((double)p.z - r.cz)};
   }
 };
-struct SegKeyOp
-{
-  const int *ts_seg;
-  __device__ int operator()(int64_t k) const { return ts_seg[k]; }
-};
 struct Double4Plus
 {
   __host__ __device__ double4s operator()(const double4s &a, const double4s &b) const
@@ -359,10 +354,15 @@ void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t
     ls.launches += 2;
   }
   t.msum = arena.alloc<double4s>(S);
-  { // segmented prefix sums of m, m*(x - centre) in double with a FIXED combination tree (det_scan.cuh): the node masses and
-    // centres of mass - and with them every potential - are the same bits on every run
-    det_inclusive_scan_by_key<double4s, Double4Plus>(arena, stream, (int64_t)S, MomentOp{t.spos, t.ts_seg, t.roots}, SegKeyOp{t.ts_seg},
-                                                     double4s{0., 0., 0., 0.}, t.msum, ls.launches);
+  { // per-tree prefix sums of m, m*(x - centre) in double with a FIXED combination tree aligned to each tree (det_scan.cuh):
+    // node masses and centres of mass - and with them every potential - are the same bits on every run and in every batch
+    std::vector<int> tile_off;
+    const int ntiles = scan_tile_table(t.h_tree_off, nseg, tile_off);
+    int *d_tile_off = arena.alloc<int>(nseg + 1);
+    HBT_CUDA(cudaMemcpyAsync(d_tile_off, tile_off.data(), sizeof(int) * (size_t)(nseg + 1), cudaMemcpyHostToDevice, stream));
+    det_inclusive_scan_segments<double4s, Double4Plus>(arena, stream, t.tree_off, d_tile_off, nseg, ntiles, MomentOp{t.spos, t.ts_seg, t.roots},
+                                                       double4s{0., 0., 0., 0.}, t.msum, ls.launches);
+    HBT_CUDA(cudaStreamSynchronize(stream)); // tile_off is a host temporary
   }
   // nodes ---------------------------------------------------------------------------------------------
   t.node_xm = arena.alloc<float4>(2 * (int64_t)S + 64); // +pad: the walk stages 32 nodes without a bounds check

@@ -152,11 +152,14 @@ __global__ void __launch_bounds__(kBlock) restore_front_kernel(const CopyJob *__
 // subhaloes whose source is too small to iterate (src/subhalo_unbind.cpp:269-293 and the disruption
 // branch :361-379, which every source with 2 <= n < MinNumPartOfSub necessarily takes)
 __global__ void trivial_kernel(const int *__restrict__ list, int n, SubState *__restrict__ subs, const int *__restrict__ ids,
-                               const float4 *__restrict__ pos, DevConfig cfg)
+                               const float4 *__restrict__ pos, DevConfig cfg, float *__restrict__ E)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SubState &st = subs[list[i]];
+  // the one energy such a subhalo reports (Energies[0]): 0 as in the reference's n == 1 branch (:285-287); for 2 <= n <
+  // MinNumPartOfSub the reference reports the E of whatever its partition left in Elist[0], which is not Particles[0]
+  if ((st.is_orphan ? st.n_own : st.n_src) > 0) E[st.slot_base] = 0.f;
   const int nu = st.is_orphan ? st.n_own : st.n_src;
   if (nu < cfg.min_num_part && st.death == -1) st.death = cfg.snapshot_index;
   st.iterations = 0;
@@ -518,8 +521,9 @@ __device__ __forceinline__ double warp_sum_d(double v)
   return v;
 }
 
-// NV fp64 sums per target into subs[sub].sums with a fixed summation tree (seg_reduce.cuh): pass A inside the producing
-// kernel, pass B = seg_finish_kernel.  The same input therefore gives the same bits on every run.
+// NV fp64 sums per target into subs[sub].sums with a fixed summation tree aligned to each subhalo (seg_reduce.cuh): pass A
+// inside the producing kernel (block = one 256-target chunk of one segment), pass B = seg_finish_kernel.  The same subhalo
+// therefore gives the same bits on every run and in every batch.
 template <int NV>
 struct SumsDone
 {
@@ -532,44 +536,29 @@ struct SumsDone
     for (int i = 0; i < NV; i++) st.sums[i] = s[i];
   }
 };
-struct TargetRange
-{
-  const Segment *segs;
-  __device__ void operator()(int a, int64_t &begin, int64_t &end) const
-  {
-    begin = segs[a].tgt_off;
-    end = begin + segs[a].tgt_n;
-  }
-};
 template <int NV>
-__global__ void __launch_bounds__(kBlock) seg_finish_kernel(const Segment *__restrict__ segs, int nseg, int64_t T, SegPartials<NV> part,
-                                                             SubState *__restrict__ subs)
+__global__ void __launch_bounds__(kBlock) seg_finish_kernel(const Segment *__restrict__ segs, int nseg, const int *__restrict__ chunk_off,
+                                                             const double *__restrict__ partial, SubState *__restrict__ subs)
 {
   const int a = blockIdx.x;
   if (a >= nseg) return;
-  seg_reduce_finish_block<NV>(a, T, part, TargetRange{segs}, SumsDone<NV>{segs, subs});
+  seg_reduce_finish_block<NV>(a, chunk_off, partial, SumsDone<NV>{segs, subs});
 }
 
 // EnergySnapshot_t::AverageVelocity / AveragePosition over the first Nbound (src/subhalo_unbind.cpp:108-188)
-__global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+__global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__restrict__ segs, int nseg, const int *__restrict__ chunk_off,
                                                                const int *__restrict__ ids, const float4 *__restrict__ pos,
                                                                const float4 *__restrict__ vel, SubState *__restrict__ subs, DevConfig cfg,
-                                                               SegPartials<7> part)
+                                                               double *__restrict__ partial)
 {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = t < T;
-  int a = valid ? tgt_seg[t] : -1;
-  int sub = -1;
-  int64_t seg_begin = 0, seg_end = 0;
+  int a, c;
+  seg_chunk_of_block(chunk_off, nseg, blockIdx.x, a, c);
+  const Segment sg = segs[a];
+  const int j = c * kBlock + threadIdx.x; // Elist index inside the subhalo
   double v[7] = {0, 0, 0, 0, 0, 0, 0};
-  if (valid)
+  if (j < sg.tgt_n)
   {
-    const Segment sg = segs[a];
-    sub = sg.sub;
-    seg_begin = sg.tgt_off;
-    seg_end = seg_begin + sg.tgt_n;
-    const SubState &st = subs[sub];
-    int j = t - sg.tgt_off;
+    const SubState &st = subs[sg.sub];
     if (st.status != kDisrupted && j < st.nbound)
     {
       int id = ids[sg.slot_base + j];
@@ -594,7 +583,7 @@ __global__ void __launch_bounds__(kBlock) frame_reduce_kernel(const Segment *__r
       }
     }
   }
-  seg_reduce_block<7>(v, valid, a, seg_begin, seg_end, (int64_t)T, part, SumsDone<7>{segs, subs});
+  seg_reduce_chunk<7>(v, partial);
 }
 
 __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, const int *__restrict__ ids,
@@ -630,25 +619,19 @@ __global__ void state2_kernel(const Segment *__restrict__ segs, int nseg, SubSta
 }
 
 // EnergySnapshot_t::AverageKinematics (src/subhalo_unbind.cpp:189-232) for subhaloes that converged this round
-__global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
+__global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__restrict__ segs, int nseg, const int *__restrict__ chunk_off,
                                                              const int *__restrict__ ids, const float *__restrict__ E,
                                                              const float4 *__restrict__ pos, const float4 *__restrict__ vel,
-                                                             SubState *__restrict__ subs, DevConfig cfg, SegPartials<6> part)
+                                                             SubState *__restrict__ subs, DevConfig cfg, double *__restrict__ partial)
 {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = t < T;
-  int a = valid ? tgt_seg[t] : -1;
-  int sub = -1;
-  int64_t seg_begin = 0, seg_end = 0;
+  int a, c;
+  seg_chunk_of_block(chunk_off, nseg, blockIdx.x, a, c);
+  const Segment sg = segs[a];
+  const int j = c * kBlock + threadIdx.x;
   double v[6] = {0, 0, 0, 0, 0, 0};
-  if (valid)
+  if (j < sg.tgt_n)
   {
-    const Segment sg = segs[a];
-    sub = sg.sub;
-    seg_begin = sg.tgt_off;
-    seg_end = seg_begin + sg.tgt_n;
-    const SubState &st = subs[sub];
-    int j = t - sg.tgt_off;
+    const SubState &st = subs[sg.sub];
     if (st.status == kConverged && j < st.nbound)
     {
       int64_t slot = sg.slot_base + j;
@@ -657,13 +640,13 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
       float m = x.w;
       const float xs[3] = {x.x, x.y, x.z}, us[3] = {u.x, u.y, u.z};
       double dx[3], dv[3], K = 0.0;
-      for (int c = 0; c < 3; c++)
+      for (int q = 0; q < 3; q++)
       {
-        dx[c] = (double)__fsub_rn(xs[c], st.ref_pos[c]);
-        if (cfg.periodic) dx[c] = nearest_d(dx[c], (double)cfg.box_size, (double)cfg.box_half);
-        dx[c] *= (double)cfg.scale_factor;
-        dv[c] = (double)__fsub_rn(us[c], st.ref_vel[c]) + (double)cfg.hz * dx[c];
-        K += dv[c] * dv[c] * (double)m;
+        dx[q] = (double)__fsub_rn(xs[q], st.ref_pos[q]);
+        if (cfg.periodic) dx[q] = nearest_d(dx[q], (double)cfg.box_size, (double)cfg.box_half);
+        dx[q] *= (double)cfg.scale_factor;
+        dv[q] = (double)__fsub_rn(us[q], st.ref_vel[q]) + (double)cfg.hz * dx[q];
+        K += dv[q] * dv[q] * (double)m;
       }
       v[0] = (double)__fmul_rn(E[slot], m);
       v[1] = K;
@@ -673,7 +656,7 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
       v[5] = (double)m;
     }
   }
-  seg_reduce_block<6>(v, valid, a, seg_begin, seg_end, (int64_t)T, part, SumsDone<6>{segs, subs});
+  seg_reduce_chunk<6>(v, partial);
 }
 
 struct RoundResult
@@ -828,6 +811,7 @@ static void run_round(Context &c, std::vector<int> &active)
   tr.S = (int)S;
   tr.nseg = nseg;
   tr.tree_off = d_tree_off;
+  tr.h_tree_off = tree_off.data();
   tr.tpos = ar.alloc<float4>(S);
   tr.ts_seg = ar.alloc<int>(S);
   tr.bbox = ar.alloc<uint32_t>(6 * (int64_t)nseg);
@@ -940,18 +924,25 @@ static void run_round(Context &c, std::vector<int> &active)
     c.ls.launches += 2;
   }
   static_assert(kBlock == kSegBlock, "seg_reduce.cuh blocks");
-  const int64_t nblk = grid_for(T);
-  SegPartials<7> part7{ar.alloc<double>(nblk * 7), ar.alloc<double>(nblk * 7)};
-  SegPartials<6> part6{part7.head, part7.tail}; // reused after state2 has consumed the frame sums
-  frame_reduce_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_pos, c.d_vel, c.d_subs, c.cfg, part7);
-  HBT_CHECK_LAUNCH();
-  seg_finish_kernel<7><<<nseg, kBlock, 0, st>>>(d_segs, nseg, T, part7, c.d_subs);
+  std::vector<int> chunk_off;
+  const int nchunk = seg_chunk_table(nseg, [&](int a) { return segs[a].tgt_n; }, chunk_off);
+  int *d_chunk_off = upload(ar, chunk_off, st);
+  double *partial = ar.alloc<double>((int64_t)nchunk * 7);
+  if (nchunk > 0)
+  {
+    frame_reduce_kernel<<<nchunk, kBlock, 0, st>>>(d_segs, nseg, d_chunk_off, c.d_ids, c.d_pos, c.d_vel, c.d_subs, c.cfg, partial);
+    HBT_CHECK_LAUNCH();
+  }
+  seg_finish_kernel<7><<<nseg, kBlock, 0, st>>>(d_segs, nseg, d_chunk_off, partial, c.d_subs);
   HBT_CHECK_LAUNCH();
   state2_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, c.cfg);
   HBT_CHECK_LAUNCH();
-  kinematics_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, (int)T, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg, part6);
-  HBT_CHECK_LAUNCH();
-  seg_finish_kernel<6><<<nseg, kBlock, 0, st>>>(d_segs, nseg, T, part6, c.d_subs);
+  if (nchunk > 0)
+  { // `partial` is reused: state2 has consumed the frame sums
+    kinematics_kernel<<<nchunk, kBlock, 0, st>>>(d_segs, nseg, d_chunk_off, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg, partial);
+    HBT_CHECK_LAUNCH();
+  }
+  seg_finish_kernel<6><<<nseg, kBlock, 0, st>>>(d_segs, nseg, d_chunk_off, partial, c.d_subs);
   HBT_CHECK_LAUNCH();
   c.ls.launches += 2;
   RoundResult *d_res = ar.alloc<RoundResult>(nseg);
@@ -1052,6 +1043,7 @@ static void run_refine(Context &c, const std::vector<int> &list)
   tr.S = (int)S;
   tr.nseg = nseg;
   tr.tree_off = d_off;
+  tr.h_tree_off = off.data();
   tr.tpos = ar.alloc<float4>(S);
   tr.ts_seg = ar.alloc<int>(S);
   tr.bbox = ar.alloc<uint32_t>(6 * (int64_t)nseg);
@@ -1279,7 +1271,7 @@ void execute_batch(Context &c)
       int *d_list = nullptr;
       HBT_CUDA(cudaMalloc(&d_list, sizeof(int) * trivial.size()));
       HBT_CUDA(cudaMemcpyAsync(d_list, trivial.data(), sizeof(int) * trivial.size(), cudaMemcpyHostToDevice, st));
-      trivial_kernel<<<grid_for((int64_t)trivial.size()), kBlock, 0, st>>>(d_list, (int)trivial.size(), c.d_subs, c.d_ids, c.d_pos, c.cfg);
+      trivial_kernel<<<grid_for((int64_t)trivial.size()), kBlock, 0, st>>>(d_list, (int)trivial.size(), c.d_subs, c.d_ids, c.d_pos, c.cfg, c.d_E);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
       HBT_CUDA(cudaStreamSynchronize(st));
