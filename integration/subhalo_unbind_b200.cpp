@@ -28,7 +28,8 @@
 
 #include "hbt_unbind.h"
 
-static_assert(sizeof(HBTReal) == 4, "only the HBTReal=float ABI variant of libhbtunbind is built");
+// HBTReal = double builds (-DHBT_REAL8) are served too: the pack loops below narrow positions, velocities and masses to the
+// float4 arrays of the ABI (the device path computes in fp32 + fp64 sums either way), the records travel as double.
 
 namespace
 {
@@ -38,7 +39,7 @@ void fill_params(hbtu_params &p)
 {
   std::memset(&p, 0, sizeof(p));
   p.struct_size = sizeof(hbtu_params);
-  p.real_bytes = sizeof(HBTReal);
+  p.real_bytes = 4; // width of the particle arrays this shim hands over (see the note on HBT_REAL8 above)
   p.min_num_part_of_sub = HBTConfig.MinNumPartOfSub;
   p.periodic_boundary_on = HBTConfig.PeriodicBoundaryOn;
   p.refine_mostbound_particle = HBTConfig.RefineMostboundParticle;

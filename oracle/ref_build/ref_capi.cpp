@@ -235,7 +235,7 @@ int hbtref_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int6
                         hbtu_sub_io *io, int32_t flags, int64_t order_capacity, int64_t *order_offset,
                         int32_t *order_out, float *energy_out)
 {
-  if (params->real_bytes != (int)sizeof(HBTReal) || !variant_ok(flags)) return HBTU_ERR_UNSUPPORTED;
+  if ((params->real_bytes != 4 && params->real_bytes != (int)sizeof(HBTReal)) || !variant_ok(flags)) return HBTU_ERR_UNSUPPORTED;
   apply_params(params);
   Epoch_t snap;
   set_epoch(snap, epoch);
@@ -276,7 +276,7 @@ int hbtref_tree_potential(const hbtu_params *params, const hbtu_epoch *epoch, in
                           int64_t ntgt, const float *tgt_pos, const float *tgt_self_mass, const float *tgt_vel,
                           const double *ref_pos, const double *ref_vel, double *out)
 {
-  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  if ((params->real_bytes != 4 && params->real_bytes != (int)sizeof(HBTReal))) return HBTU_ERR_UNSUPPORTED;
   apply_params(params);
   Epoch_t snap;
   set_epoch(snap, epoch);
@@ -329,7 +329,7 @@ int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, 
                             const int32_t *host_halo_id, int64_t n_old, int32_t nhalos, const float *mbound_in, hbtu_sub_io *io,
                             int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
 {
-  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  if ((params->real_bytes != 4 && params->real_bytes != (int)sizeof(HBTReal))) return HBTU_ERR_UNSUPPORTED;
   apply_params(params);
   omp_set_max_active_levels(1);
   SubhaloSnapshot_t snap;
@@ -385,7 +385,7 @@ int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, 
 int hbtref_profile_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
                          const float *pos_mass, hbtu_profile_io *io)
 {
-  if (params->real_bytes != (int)sizeof(HBTReal)) return HBTU_ERR_UNSUPPORTED;
+  if ((params->real_bytes != 4 && params->real_bytes != (int)sizeof(HBTReal))) return HBTU_ERR_UNSUPPORTED;
   apply_params(params);
   Epoch_t snap;
   set_epoch(snap, epoch);

@@ -24,17 +24,19 @@ def snapshot_with_hosts(seed, periodic):
     return snap, np.asarray(host, np.int32), n_old, 2, mb
 
 
-@pytest.mark.parametrize("variant", ["v32", "v64", "v32ns", "v32th", "v32im"])
+@pytest.mark.parametrize("variant", ["v32", "v64", "v32ns", "v32th", "v32im", "v64r8"])
 @pytest.mark.parametrize("periodic", [False, True])
 def test_refine_particles_drop_in(periodic, variant):
     """v32 = -DDM_ONLY (HBTInt=int); v64 = -DHBT_INT8 (HBTInt=long, Particle_t with Type: the CMake default / EAGLE ABI);
     v32ns = -DNO_STRIPPING; v32th = -DUNBIND_WITH_THERMAL_ENERGY (Particle_t with InternalEnergy + Type);
-    v32im = -DINCLUSIVE_MASS (flat RefineParticles loop).  The CUDA library is the same binary for all of them; only the
+    v32im = -DINCLUSIVE_MASS (flat RefineParticles loop); v64r8 = -DHBT_INT8 -DHBT_REAL8 (HBTReal = double: the reference then
+    does its HBTReal arithmetic in double, the shim narrows the particle arrays to float4 - same gates).  The CUDA library is the same binary for all of them; only the
     shim is compiled with the caller's -D flags and passes the physics variant as batch flags."""
     if not po.have_dropin(variant):
         pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
     ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
-    assert ref.hbtref_sizeof_hbtint() == (8 if variant == "v64" else 4)
+    assert ref.hbtref_sizeof_hbtint() == (8 if variant in ("v64", "v64r8") else 4)
+    assert ref.hbtref_sizeof_hbtreal() == (8 if variant == "v64r8" else 4)
     ref.hbtref_set_num_threads(4)
     p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
     e = capi.make_epoch(0.9, snapshot_index=15)
@@ -57,7 +59,7 @@ def test_refine_particles_drop_in(periodic, variant):
     assert (want.io["nbound"][[0, 5]] > 1000).all()
 
 
-@pytest.mark.parametrize("variant", ["v32", "v64"])
+@pytest.mark.parametrize("variant", ["v32", "v64", "v64r8"])
 def test_profile_properties_drop_in(variant):
     """SURVEY.md 8(f) next-2 through the reference-facing side: the harness fills the reference's own Subhalo_t objects and
     calls either Subhalo_t::CalculateProfileProperties/CalculateShape (libhbtref) or the shim's batched replacement of the
@@ -74,7 +76,7 @@ def test_profile_properties_drop_in(variant):
     want = po.profile_batch(ref, "hbtref", p, e, part_offset, pm, io)
     got = po.profile_batch(drop, "hbtref", p, e, part_offset, pm, io)
     from test_gpu_profile import check_profile
-    check_profile(got, want)
+    check_profile(got, want, exact_mass=(variant != "v64r8"))  # HBTReal = double: the reference's radii are rounded once more
     assert (want["nbound"] > 1).sum() >= 5
 
 
