@@ -128,6 +128,25 @@ SUBIO_DTYPE = np.dtype(
 assert SUBIO_DTYPE.itemsize == C.sizeof(SubIO), (SUBIO_DTYPE.itemsize, C.sizeof(SubIO))
 
 
+class TrapIO(C.Structure):
+    _fields_ = [
+        ("mostbound_pos", C.c_double * 3),
+        ("mostbound_vel", C.c_double * 3),
+        ("nbound", C.c_int64),
+        ("sink_track_id", C.c_int64),
+        ("snapshot_index_of_sink", C.c_int32),
+        ("is_merged", C.c_int32),
+    ]
+
+
+#: numpy view of TrapIO (hbtu_trap_io: merger trap detection, src/subhalo_merge.cpp:29-172)
+TRAPIO_DTYPE = np.dtype([("mostbound_pos", "<f8", 3), ("mostbound_vel", "<f8", 3), ("nbound", "<i8"), ("sink_track_id", "<i8"),
+                         ("snapshot_index_of_sink", "<i4"), ("is_merged", "<i4")], align=True)
+assert TRAPIO_DTYPE.itemsize == C.sizeof(TrapIO)
+TRAP_ARGTYPES = [C.POINTER(Epoch), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
+                 C.POINTER(C.c_int32), C.POINTER(TrapIO)]
+
+
 class ProfileIO(C.Structure):
     _fields_ = [
         ("mostbound_pos", C.c_double * 3),
@@ -286,6 +305,7 @@ EXPORTS = [
     "hbtu_profile_batch",
     "hbtu_profile_executed",
     "hbtu_mask_batch",
+    "hbtu_detect_traps",
     "hbtu_idtable_build",
     "hbtu_idtable_query",
     "hbtu_idtable_clear",
@@ -351,6 +371,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.hbtu_profile_batch.restype = C.c_int
     lib.hbtu_profile_executed.argtypes = [C.c_void_p, C.POINTER(ProfileIO)]
     lib.hbtu_profile_executed.restype = C.c_int
+    lib.hbtu_detect_traps.argtypes = [C.c_void_p] + TRAP_ARGTYPES
+    lib.hbtu_detect_traps.restype = C.c_int
     lib.hbtu_mask_batch.argtypes = [C.c_void_p] + MASK_ARGTYPES
     lib.hbtu_mask_batch.restype = C.c_int
     lib.hbtu_idtable_build.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
@@ -388,3 +410,9 @@ def mask_args(part_offset, particle_id, nest_offset, nest_list, nbound, new_coun
     """Marshal numpy arrays into the positional tail of ``*_mask_batch``."""
     return (C.c_int64(len(part_offset) - 1), _ptr(part_offset, C.c_int64), _ptr(particle_id, C.c_int64), _ptr(nest_offset, C.c_int64),
             _ptr(nest_list, C.c_int32), _ptr(nbound, C.c_int64), _ptr(new_count, C.c_int64), _ptr(keep_index, C.c_int32))
+
+
+def trap_args(epoch, part_offset, pos_mass, vel, nest_offset, nest_list, io):
+    """Marshal numpy arrays into the positional tail of ``*_detect_traps``."""
+    return (C.byref(epoch), C.c_int64(len(part_offset) - 1), _ptr(part_offset, C.c_int64), _ptr(pos_mass, C.c_float), _ptr(vel, C.c_float),
+            _ptr(nest_offset, C.c_int64), _ptr(nest_list, C.c_int32), io.ctypes.data_as(C.POINTER(TrapIO)))

@@ -500,6 +500,12 @@ int hbtu_idtable_clear(hbtu_ctx *ctx)
   return guarded(ctx, [&](Context &c) { idtable_clear(c); });
 }
 
+int hbtu_detect_traps(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, const float *vel,
+                      const int64_t *nest_offset, const int32_t *nest_list, hbtu_trap_io *io)
+{
+  return guarded(ctx, [&](Context &c) { detect_traps(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io); });
+}
+
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out)
 {
   if (!ctx || !out) return HBTU_ERR_INVALID;

@@ -69,6 +69,9 @@ void mask_batch(Context &c, int64_t nsub, const int64_t *part_offset, const int6
 void idtable_build(Context &c, int64_t n, const int64_t *particle_id);
 void idtable_query(Context &c, int64_t nq, const int64_t *query_id, int64_t *index_out);
 void idtable_clear(Context &c);
+// trap.cu: detection part of SubhaloSnapshot_t::MergeSubhalos
+void detect_traps(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, const float *vel,
+                  const int64_t *nest_offset, const int32_t *nest_list, hbtu_trap_io *io);
 void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out);
 
 } // namespace hbt

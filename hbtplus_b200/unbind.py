@@ -123,6 +123,18 @@ class UnbindContext:
         self._check(self._lib.hbtu_idtable_query(self._ctx, len(q), capi._ptr(q, C.c_int64), capi._ptr(out, C.c_int64)))
         return out
 
+    # -- detection part of SubhaloSnapshot_t::MergeSubhalos (src/subhalo_merge.cpp:29-199) -----------------------
+    def detect_traps(self, epoch, part_offset, pos_mass, vel, nest_offset, nest_list, io) -> np.ndarray:
+        """``io``: structured array (capi.TRAPIO_DTYPE); returns the updated copy (sink ids, sink snapshot, is_merged)."""
+        out = np.ascontiguousarray(io, capi.TRAPIO_DTYPE).copy()
+        po = np.ascontiguousarray(part_offset, np.int64)
+        pm = np.ascontiguousarray(pos_mass, np.float32)
+        vv = np.ascontiguousarray(vel, np.float32)
+        no = None if nest_offset is None else np.ascontiguousarray(nest_offset, np.int64)
+        nl = None if nest_list is None else np.ascontiguousarray(nest_list, np.int32)
+        self._check(self._lib.hbtu_detect_traps(self._ctx, *capi.trap_args(epoch, po, pm, vv, no, nl, out)))
+        return out
+
     # -- SubhaloSnapshot_t::MaskSubhalos (src/subhalo_tracking.cpp:793-841) -----------------------------
     def mask_batch(self, part_offset, particle_id, nest_offset, nest_list, nbound):
         """Exclusive particle ownership inside every hierarchy of the nest forest.  Returns (new_count[nsub], keep_index[N]):

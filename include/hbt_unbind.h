@@ -239,6 +239,31 @@ int hbtu_idtable_build(hbtu_ctx *ctx, int64_t n, const int64_t *particle_id);
 int hbtu_idtable_query(hbtu_ctx *ctx, int64_t nq, const int64_t *query_id, int64_t *index_out);
 int hbtu_idtable_clear(hbtu_ctx *ctx);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Merger trap detection: the detection part of SubhaloSnapshot_t::MergeSubhalos,
+ *   SubHelper_t::BuildPosition / BuildVelocity   src/subhalo_merge.cpp:29-123   mass-weighted mean and dispersion of the
+ *                                                                              <= NumPartCoreMax = 20 most bound particles
+ *   SinkDistance                                 src/subhalo_merge.cpp:125-130 d/sigma_R + v/sigma_V to a host's core
+ *   FillHostTrackIds + DetectTraps               src/subhalo_merge.cpp:132-172 walk up the host chain, sink if delta < 2
+ * The host relation is the nest forest (with the other heads glued to the central's list, GlueHeadNests,
+ * src/subhalo_tracking.cpp:843-861).  Merging itself (MergeTo) and the re-unbinding of the hosts flagged in is_merged
+ * (src/subhalo_merge.cpp:201-214) stay with the caller: the latter is one more hbtu_unbind_batch. */
+typedef struct hbtu_trap_io
+{
+  double mostbound_pos[3];        /* [in]  ComovingMostBoundPosition                                            */
+  double mostbound_vel[3];        /* [in]  PhysicalMostBoundVelocity                                            */
+  int64_t nbound;                 /* [in]  Nbound                                                               */
+  int64_t sink_track_id;          /* [io]  SinkTrackId (batch-local index; >= 0 on entry: already trapped)      */
+  int32_t snapshot_index_of_sink; /* [io]  SnapshotIndexOfSink                                                  */
+  int32_t is_merged;              /* [out] SubHelper_t::IsMerged: a real subhalo (Nbound > 1) sank into this one */
+} hbtu_trap_io;
+
+/*  part_offset / pos_mass / vel   particle lists in bound order; only the first min(nbound, 20) of each are read, so a list
+ *                                 may be truncated to that                                                              */
+int hbtu_detect_traps(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset,
+                      const float *pos_mass, const float *vel, const int64_t *nest_offset,
+                      const int32_t *nest_list, hbtu_trap_io *io);
+
 /* Counters of the last hbtu_execute / hbtu_tree_potential (for bench.py's roofline and
  * gpu_launches fields). */
 typedef struct hbtu_stats

@@ -18,3 +18,8 @@ void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epo
 //     HBT_B200_MaskSubhalos(*this);
 // (exclusive particle ownership on the device through hbtu_mask_batch; Subhalos / MemberTable are public members).
 void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap);
+
+// src/subhalo_merge.cpp:193-198 of the reference (inside SubhaloSnapshot_t::MergeSubhalos): FillHelpers + DetectTraps become
+//     std::vector<char> merged; HBT_B200_DetectTraps(*this, merged);  for(i...) Helpers[i].IsMerged = merged[i];
+// (20-particle core moments, host chain walk and sink test on the device through hbtu_detect_traps).
+void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged);

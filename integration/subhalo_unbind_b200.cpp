@@ -507,3 +507,76 @@ void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap)
     P.resize(new_count[s]);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Merger trap detection.  SubhaloSnapshot_t::MergeSubhalos (src/subhalo_merge.cpp:187-221,
+// not replaced) opens with
+//     #pragma omp parallel
+//     { GlueHeadNests(); FillHelpers(Helpers, Subhalos); DetectTraps(Subhalos, Helpers, isnap); }
+// whose helpers are file-local.  The maintainer replaces FillHelpers + DetectTraps by
+//     HBT_B200_DetectTraps(*this, merged);   // then: Helpers[i].IsMerged = merged[i]
+// (called outside the parallel region; it builds the glued host relation itself from MemberTable, like RefineParticles does).
+void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged)
+{
+  SubhaloList_t &Subhalos = snap.Subhalos;
+  const int64_t nsub = Subhalos.size();
+  is_merged.assign(nsub, 0);
+  if (nsub == 0) return;
+  // host relation by subhalo index: NestedSubhalos + the other heads of every host halo under its central (GlueHeadNests)
+  std::vector<std::vector<int32_t>> lists(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+    for (auto ch : Subhalos[s].NestedSubhalos) lists[s].push_back((int32_t)ch);
+  for (HBTInt haloid = 0; haloid < (HBTInt)snap.MemberTable.SubGroups.size(); haloid++)
+  {
+    auto &subgroup = snap.MemberTable.SubGroups[haloid];
+    if (subgroup.size() == 0) continue;
+    auto &heads = snap.MemberTable.SubGroupsOfHeads[haloid];
+    for (size_t i = 1; i < heads.size(); i++) lists[subgroup[0]].push_back((int32_t)heads[i]);
+  }
+  std::vector<int64_t> nest_offset(nsub + 1, 0), part_offset(nsub + 1, 0);
+  std::vector<int32_t> nest_list;
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    nest_list.insert(nest_list.end(), lists[s].begin(), lists[s].end());
+    nest_offset[s + 1] = nest_list.size();
+    const int64_t nb = Subhalos[s].Nbound < 0 ? 0 : (int64_t)Subhalos[s].Nbound;
+    part_offset[s + 1] = part_offset[s] + (nb < 20 ? nb : 20); // only the <= NumPartCoreMax most bound particles are read
+  }
+  std::vector<float> pos_mass(4 * (size_t)part_offset[nsub]), vel(4 * (size_t)part_offset[nsub]);
+  std::vector<hbtu_trap_io> io(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    const Subhalo_t &sub = Subhalos[s];
+    for (int64_t i = 0; i < part_offset[s + 1] - part_offset[s]; i++)
+    {
+      const Particle_t &p = sub.Particles[i];
+      float *x = &pos_mass[4 * (part_offset[s] + i)], *v = &vel[4 * (part_offset[s] + i)];
+      x[0] = p.ComovingPosition[0]; x[1] = p.ComovingPosition[1]; x[2] = p.ComovingPosition[2]; x[3] = p.Mass;
+      v[0] = p.PhysicalVelocity[0]; v[1] = p.PhysicalVelocity[1]; v[2] = p.PhysicalVelocity[2]; v[3] = 0.f;
+    }
+    hbtu_trap_io &o = io[s];
+    for (int j = 0; j < 3; j++)
+    {
+      o.mostbound_pos[j] = sub.ComovingMostBoundPosition[j];
+      o.mostbound_vel[j] = sub.PhysicalMostBoundVelocity[j];
+    }
+    o.nbound = sub.Nbound < 0 ? 0 : (int64_t)sub.Nbound; // the list handed over holds min(Nbound, 20) particles
+    o.sink_track_id = sub.SinkTrackId;
+    o.snapshot_index_of_sink = sub.SnapshotIndexOfSink;
+    o.is_merged = 0;
+  }
+  hbtu_ctx *ctx = context();
+  hbtu_epoch e;
+  e.scale_factor = snap.Cosmology.ScaleFactor;
+  e.hz = snap.Cosmology.Hz;
+  e.snapshot_index = snap.GetSnapshotIndex();
+  e.reserved = 0;
+  int rc = hbtu_detect_traps(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), nest_offset.data(), nest_list.data(), io.data());
+  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_detect_traps failed: ") + hbtu_last_error(ctx));
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalos[s].SinkTrackId = (HBTInt)io[s].sink_track_id;
+    Subhalos[s].SnapshotIndexOfSink = io[s].snapshot_index_of_sink;
+    is_merged[s] = (char)io[s].is_merged;
+  }
+}

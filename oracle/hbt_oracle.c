@@ -1295,3 +1295,105 @@ int hbto_idtable_query(const hbtu_params *params, int64_t n, const int64_t *part
   free(Map);
   return HBTU_OK;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Merger trap detection: src/subhalo_merge.cpp:29-172.
+ * ------------------------------------------------------------------------------------------- */
+#define NUM_PART_CORE_MAX 20
+#define DELTA_CRIT 2.
+
+typedef struct
+{ /* SubHelper_t, src/subhalo_merge.cpp:14-27 */
+  int64_t HostTrackId;
+  int IsMerged;
+  HBTReal ComovingPosition[3], PhysicalVelocity[3];
+  float ComovingSigmaR, PhysicalSigmaV;
+} SubHelper;
+
+static void helper_build(const Config *c, SubHelper *h, int64_t nbound, const float *pm, const float *vel)
+{ /* BuildPosition :29-80, BuildVelocity :81-123 */
+  if (nbound == 0) { h->ComovingSigmaR = 0.f; h->PhysicalSigmaV = 0.f; return; }
+  if (nbound == 1)
+  {
+    h->ComovingSigmaR = 0.f; h->PhysicalSigmaV = 0.f;
+    for (int j = 0; j < 3; j++) { h->ComovingPosition[j] = pm[j]; h->PhysicalVelocity[j] = vel[j]; }
+    return;
+  }
+  const int64_t NumPart = nbound > NUM_PART_CORE_MAX ? NUM_PART_CORE_MAX : nbound;
+  double sx[3] = {0, 0, 0}, sx2[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sv2[3] = {0, 0, 0}, origin[3] = {0, 0, 0}, msum = 0.;
+  if (c->Periodic)
+    for (int j = 0; j < 3; j++) origin[j] = pm[j];
+  for (int64_t i = 0; i < NumPart; i++)
+  {
+    const HBTReal m = pm[4 * i + 3];
+    msum += m;
+    for (int j = 0; j < 3; j++)
+    {
+      double dx = c->Periodic ? nearest_d(c, pm[4 * i + j] - origin[j]) : pm[4 * i + j];
+      sx[j] += dx * m;
+      sx2[j] += dx * dx * m;
+      double dv = vel[4 * i + j];
+      sv[j] += dv * m;
+      sv2[j] += dv * dv * m;
+    }
+  }
+  for (int j = 0; j < 3; j++)
+  {
+    sx[j] /= msum; sx2[j] /= msum;
+    h->ComovingPosition[j] = (HBTReal)sx[j];
+    if (c->Periodic) h->ComovingPosition[j] += origin[j];
+    sx2[j] -= sx[j] * sx[j];
+    sv[j] /= msum; sv2[j] /= msum;
+    h->PhysicalVelocity[j] = (HBTReal)sv[j];
+    sv2[j] -= sv[j] * sv[j];
+  }
+  h->ComovingSigmaR = (float)sqrt(sx2[0] + sx2[1] + sx2[2]);
+  h->PhysicalSigmaV = (float)sqrt(sv2[0] + sv2[1] + sv2[2]);
+}
+
+static float sink_distance(const Config *c, const hbtu_trap_io *sat, const SubHelper *cen)
+{ /* SinkDistance, :125-130 */
+  const HBTReal sp[3] = {(HBTReal)sat->mostbound_pos[0], (HBTReal)sat->mostbound_pos[1], (HBTReal)sat->mostbound_pos[2]};
+  const HBTReal sv[3] = {(HBTReal)sat->mostbound_vel[0], (HBTReal)sat->mostbound_vel[1], (HBTReal)sat->mostbound_vel[2]};
+  float d = periodic_distance(c, cen->ComovingPosition, sp);
+  HBTReal dv[3] = {cen->PhysicalVelocity[0] - sv[0], cen->PhysicalVelocity[1] - sv[1], cen->PhysicalVelocity[2] - sv[2]};
+  float v = sqrtf(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+  return d / cen->ComovingSigmaR + v / cen->PhysicalSigmaV;
+}
+
+int hbto_detect_traps(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+                      const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_trap_io *io)
+{
+  Config c;
+  config_from(&c, params, epoch);
+  SubHelper *H = calloc((size_t)(nsub > 0 ? nsub : 1), sizeof(SubHelper));
+  for (int64_t i = 0; i < nsub; i++) H[i].HostTrackId = -1;
+  if (nest_offset) /* FillHostTrackIds, :163-172 */
+    for (int64_t i = 0; i < nsub; i++)
+      for (int64_t k = nest_offset[i]; k < nest_offset[i + 1]; k++) H[nest_list[k]].HostTrackId = i;
+  for (int64_t i = 0; i < nsub; i++) helper_build(&c, &H[i], io[i].nbound, &pos_mass[4 * part_offset[i]], &vel[4 * part_offset[i]]);
+  for (int64_t i = 0; i < nsub; i++)
+  { /* DetectTraps, :132-161 */
+    if (io[i].sink_track_id != -1) continue;
+    int64_t HostId = H[i].HostTrackId;
+    while (HostId >= 0)
+    {
+      if (io[HostId].nbound > 1)
+      {
+        float delta = sink_distance(&c, &io[i], &H[HostId]);
+        if (delta < DELTA_CRIT)
+        {
+          io[i].sink_track_id = HostId;
+          io[i].snapshot_index_of_sink = c.SnapshotIndex;
+          if (io[i].nbound > 1) H[HostId].IsMerged = 1;
+          break;
+        }
+      }
+      HostId = H[HostId].HostTrackId;
+    }
+  }
+  for (int64_t i = 0; i < nsub; i++) io[i].is_merged = H[i].IsMerged;
+  free(H);
+  return HBTU_OK;
+}

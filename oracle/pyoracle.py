@@ -196,3 +196,20 @@ def idtable_query(lib, prefix, params, particle_id, query_id):
     if rc != 0:
         raise RuntimeError(f"{prefix}_idtable_query failed: {rc}")
     return out
+
+
+def detect_traps(lib, prefix, params, epoch, part_offset, pos_mass, vel, nest_offset, nest_list, io):
+    """Detection part of SubhaloSnapshot_t::MergeSubhalos on the CPU checker `lib` (same contract as hbtu_detect_traps)."""
+    out = np.ascontiguousarray(io, capi.TRAPIO_DTYPE).copy()
+    po = np.ascontiguousarray(part_offset, np.int64)
+    pm = np.ascontiguousarray(pos_mass, np.float32)
+    vv = np.ascontiguousarray(vel, np.float32)
+    no = None if nest_offset is None else np.ascontiguousarray(nest_offset, np.int64)
+    nl = None if nest_list is None else np.ascontiguousarray(nest_list, np.int32)
+    f = getattr(lib, prefix + "_detect_traps")
+    f.argtypes = [C.POINTER(capi.Params)] + capi.TRAP_ARGTYPES
+    f.restype = C.c_int
+    rc = f(C.byref(params), *capi.trap_args(epoch, po, pm, vv, no, nl, out))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}_detect_traps failed: {rc}")
+    return out

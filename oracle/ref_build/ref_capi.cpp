@@ -42,6 +42,7 @@
 
 /* defined by integration/subhalo_unbind_b200.cpp in the drop-in build only */
 void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap) __attribute__((weak));
+void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged) __attribute__((weak));
 void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch) __attribute__((weak));
 
 /* the real body lives in src/io/subhalo_io.cpp, which needs libhdf5 (absent) */
@@ -559,6 +560,95 @@ int hbtref_idtable_query(const hbtu_params *params, int64_t n, const int64_t *pa
   std::sort(q.begin(), q.end(), [](const QueryItem_t &a, const QueryItem_t &b) { return a.Id < b.Id; });
   table.GetIndices(q);
   for (const auto &x : q) index_out[x.Order] = x.Id;
+  return HBTU_OK;
+}
+
+/* The detection part of SubhaloSnapshot_t::MergeSubhalos of the reference (src/subhalo_merge.cpp:187-199, with
+ * HBTConfig.MergeTrappedSubhalos = false so that nothing is merged or re-unbound) on an explicit nest forest; same contract
+ * as hbtu_detect_traps.  In the drop-in build the shim's HBT_B200_DetectTraps (-> hbtu_detect_traps) is used instead. */
+int hbtref_detect_traps(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+                        const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_trap_io *io)
+{
+  apply_params(params);
+  HBTConfig.MergeTrappedSubhalos = false;
+  omp_set_max_active_levels(1);
+  SubhaloSnapshot_t snap;
+  set_epoch(snap, epoch);
+  snap.Subhalos.resize(nsub);
+  std::vector<int32_t> root(nsub, -1);
+  std::vector<char> is_child(nsub, 0);
+  if (nest_offset)
+    for (int64_t k = 0; k < nest_offset[nsub]; k++) is_child[nest_list[k]] = 1;
+  int32_t nhalos = 0;
+  std::vector<int64_t> stack;
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    if (is_child[s]) continue;
+    stack.assign(1, s);
+    while (!stack.empty())
+    {
+      int64_t q = stack.back();
+      stack.pop_back();
+      root[q] = nhalos;
+      if (nest_offset)
+        for (int64_t k = nest_offset[q]; k < nest_offset[q + 1]; k++) stack.push_back(nest_list[k]);
+    }
+    nhalos++;
+  }
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalo_t &sub = snap.Subhalos[s];
+    const int64_t b = part_offset[s], n = part_offset[s + 1] - b;
+    sub.Particles.resize(n);
+    for (int64_t i = 0; i < n; i++)
+    {
+      Particle_t &p = sub.Particles[i];
+      p.Id = (HBTInt)(b + i);
+      for (int j = 0; j < 3; j++)
+      {
+        p.ComovingPosition[j] = pos_mass[4 * (b + i) + j];
+        p.PhysicalVelocity[j] = vel[4 * (b + i) + j];
+      }
+      p.Mass = pos_mass[4 * (b + i) + 3];
+    }
+    sub.Nbound = (HBTInt)io[s].nbound;
+    sub.Mbound = is_child[s] ? 1.f : 1e30f;
+    sub.HostHaloId = root[s];
+    sub.TrackId = (HBTInt)s;
+    sub.Rank = 0;
+    sub.SinkTrackId = (HBTInt)io[s].sink_track_id;
+    sub.SnapshotIndexOfSink = io[s].snapshot_index_of_sink;
+    for (int j = 0; j < 3; j++)
+    {
+      sub.ComovingMostBoundPosition[j] = io[s].mostbound_pos[j];
+      sub.PhysicalMostBoundVelocity[j] = io[s].mostbound_vel[j];
+    }
+    if (nest_offset)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++) sub.NestedSubhalos.push_back(nest_list[k]);
+  }
+#pragma omp parallel
+  snap.MemberTable.Build(nhalos, snap.Subhalos, true);
+  snap.MemberTable.SubGroupsOfHeads.assign(nhalos, std::vector<HBTInt>());
+  for (HBTInt h = 0; h < nhalos; h++) snap.MemberTable.SubGroupsOfHeads[h].push_back(snap.MemberTable.SubGroups[h][0]);
+  std::vector<char> merged(nsub, 0);
+  std::vector<int64_t> sink_before(nsub);
+  for (int64_t s = 0; s < nsub; s++) sink_before[s] = io[s].sink_track_id;
+  if (HBT_B200_DetectTraps)
+    HBT_B200_DetectTraps(snap, merged);
+  else
+  {
+    snap.MergeSubhalos();
+    /* SubHelper_t::IsMerged is local to MergeSubhalos: it is set exactly for the sinks of real subhaloes trapped now (:152-153) */
+    for (int64_t s = 0; s < nsub; s++)
+      if (sink_before[s] == -1 && snap.Subhalos[s].SinkTrackId != SpecialConst::NullTrackId && snap.Subhalos[s].Nbound > 1)
+        merged[snap.Subhalos[s].SinkTrackId] = 1;
+  }
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    io[s].sink_track_id = snap.Subhalos[s].SinkTrackId;
+    io[s].snapshot_index_of_sink = snap.Subhalos[s].SnapshotIndexOfSink;
+    io[s].is_merged = merged[s];
+  }
   return HBTU_OK;
 }
 

@@ -162,3 +162,55 @@ def case_mask(seed=41, nroots=6, scale=1.0):
     nest_offset = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int64)
     nest_list = np.array([c for cs in children for c in cs], np.int32)
     return part_offset, ids, nest_offset, nest_list, nbound
+
+
+def case_traps(seed=51, periodic=True):
+    """Nested subhaloes some of which sit inside their host's core in phase space (-> trapped), some do not, orphans as
+    satellites and as hosts (skipped as hosts), an already trapped one, depth-3 chains where the first real host is two
+    levels up, and a host straddling the box face."""
+    rng = np.random.default_rng(seed)
+    sizes = [5000, 800, 300, 60, 45, 1, 200, 0, 120, 3000, 500, 90, 30]
+    parent = [-1, 0, 0, 1, 3, 1, 5, 0, 2, -1, 9, 10, 11]
+    snap = synth.make_snapshot(sizes, seed=seed, wrap=periodic, parent=parent, centre=[0.03, 31.0, 62.47] if periodic else None, f_contam=0.0)
+    nsub = snap.nsub
+    io = np.zeros(nsub, capi.TRAPIO_DTYPE)
+    io["sink_track_id"] = -1
+    io["snapshot_index_of_sink"] = -1
+    nbound = np.array(sizes, np.int64)
+    nbound[5] = 1
+    io["nbound"] = nbound
+    # cores: mean of the first 20 particles; put half of the satellites right on their host's core, the others far in velocity
+    for s in range(nsub):
+        b, e = snap.part_offset[s], snap.part_offset[s + 1]
+        if e > b:
+            io["mostbound_pos"][s] = snap.pos_mass[b, :3]
+            io["mostbound_vel"][s] = snap.vel[b, :3]
+    for s in range(nsub):
+        p_ = parent[s]
+        if p_ < 0 or sizes[s] == 0:
+            continue
+        host = p_
+        while host >= 0 and nbound[host] <= 1:
+            host = parent[host]
+        hb = snap.part_offset[host]
+        hp = snap.pos_mass[hb:hb + 20, :3].astype(np.float64)
+        hv = snap.vel[hb:hb + 20, :3].astype(np.float64)
+        d0 = hp - hp[0]
+        if periodic:
+            d0 -= 62.5 * np.round(d0 / 62.5)
+        cpos, cvel = hp[0] + d0.mean(0), hv.mean(0)
+        sr, sv = np.sqrt(d0.var(0).sum()), np.sqrt(hv.var(0).sum())
+        if s % 2 == 0:   # inside: 0.4 sigma in position, 0.5 sigma in velocity -> delta ~ 0.9
+            io["mostbound_pos"][s] = np.mod(cpos + 0.4 * sr * np.array([1.0, 0, 0]), 62.5) if periodic else cpos + 0.4 * sr * np.array([1.0, 0, 0])
+            io["mostbound_vel"][s] = cvel + 0.5 * sv * np.array([0, 1.0, 0])
+        else:            # outside: 3 sigma in velocity
+            io["mostbound_vel"][s] = cvel + 3.0 * sv * np.array([0, 0, 1.0])
+    io["sink_track_id"][8] = 0  # already trapped: left alone
+    io["snapshot_index_of_sink"][8] = 4
+    children = [[] for _ in range(nsub)]
+    for s, p_ in enumerate(parent):
+        if p_ >= 0:
+            children[p_].append(s)
+    nest_offset = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int64)
+    nest_list = np.array([c for cs in children for c in cs], np.int32)
+    return snap, nest_offset, nest_list, io

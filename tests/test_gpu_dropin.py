@@ -121,3 +121,20 @@ def test_refine_particles_sharded_over_devices(monkeypatch):
     assert np.array_equal(one.order[:ntot], three.order[:ntot])
     bad = np.nonzero(one.energy[:ntot] != three.energy[:ntot])[0]
     assert len(bad) == 0, (bad[:10], one.energy[bad[:10]], three.energy[bad[:10]], np.searchsorted(one.order_offset, bad[:10], side='right') - 1, one.io['nbound'], one.io['nsource'])
+
+
+@pytest.mark.parametrize("variant", ["v32", "v64"])
+def test_detect_traps_drop_in(variant):
+    """SURVEY.md 8(f) next-3 through the reference-facing side: SubhaloSnapshot_t::MergeSubhalos' detection (libhbtref, with
+    MergeTrappedSubhalos off) against the shim's HBT_B200_DetectTraps (libhbtdropin -> hbtu_detect_traps)."""
+    if not po.have_dropin(variant):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True)
+    e = capi.make_epoch(0.8, snapshot_index=23)
+    snap, no, nl, io = cases.case_traps(periodic=True)
+    want = po.detect_traps(ref, "hbtref", p, e, snap.part_offset, snap.pos_mass, snap.vel, no, nl, io)
+    got = po.detect_traps(drop, "hbtref", p, e, snap.part_offset, snap.pos_mass, snap.vel, no, nl, io)
+    for f in ("sink_track_id", "snapshot_index_of_sink", "is_merged"):
+        assert np.array_equal(got[f], want[f]), f
+    assert (want["sink_track_id"] >= 0).sum() >= 4

@@ -290,3 +290,19 @@ def test_oracle_idtable_matches_reference(oracle_lib, ref_lib):
         found = a >= 0
         assert found.sum() >= len(q) // 2 and np.array_equal(ids[a[found]], q[found]) and a[q == -1].max() == -1
     assert np.array_equal(po.idtable_query(oracle_lib, "hbto", p, np.zeros(0, np.int64), np.array([3, 4])), [-1, -1])
+
+
+# ---- merger trap detection: SubHelper_t / SinkDistance / DetectTraps -------------------------------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_oracle_traps_match_reference(oracle_lib, ref_lib, periodic):
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
+    e = capi.make_epoch(0.8, snapshot_index=23)
+    snap, no, nl, io = cases.case_traps(periodic=periodic)
+    a = po.detect_traps(oracle_lib, "hbto", p, e, snap.part_offset, snap.pos_mass, snap.vel, no, nl, io)
+    b = po.detect_traps(ref_lib, "hbtref", p, e, snap.part_offset, snap.pos_mass, snap.vel, no, nl, io)
+    for f in ("sink_track_id", "snapshot_index_of_sink", "is_merged"):
+        assert np.array_equal(a[f], b[f]), f
+    trapped = (a["sink_track_id"] >= 0) & (io["sink_track_id"] < 0)
+    assert trapped.sum() >= 3 and (a["sink_track_id"][(io["sink_track_id"] < 0)] < 0).sum() >= 3  # both outcomes occur
+    assert a["sink_track_id"][8] == 0 and a["snapshot_index_of_sink"][8] == 4  # already trapped: untouched
+    assert np.all(a["snapshot_index_of_sink"][trapped] == 23) and a["is_merged"].sum() >= 1
