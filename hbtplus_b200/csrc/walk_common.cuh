@@ -115,7 +115,6 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
     const float4 n = nd->xm;
     const float lenq = nd->lenq;
     const int nend = nd->end;
-    bool any_open = false;
     float r2s[T];
     pair_r2<T, PERIODIC>(n, px, py, pz, cfg, r2s);
 #pragma unroll
@@ -123,10 +122,8 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
     {
       const float r2 = r2s[k];
       const bool active = no >= skip[k];
-      const bool open = active && (lenq > r2); // reference criterion, per target (src/gravity_tree.cpp:135)
-      const bool acc = active && !(lenq > r2);
+      const bool acc = active && !(lenq > r2); // reference criterion, per target (src/gravity_tree.cpp:135); else the node is opened
       const float rinv = rsqrt_raw(r2);
-      any_open |= open;
       if (CAREFUL)
       {
         if (__any_sync(kFull, acc && (r2 < h2)))
@@ -153,10 +150,7 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
           accf[k] = fmaf(-n.w, rinv, accf[k]);
       }
       else if (acc)
-      {
         accf[k] = fmaf(-n.w, rinv, accf[k]);
-        minr2 = fminf(minr2, r2);
-      }
       if (acc)
       {
         skip[k] = nend; // resume after this subtree (a particle's end is no+1)
@@ -164,7 +158,20 @@ __device__ __forceinline__ int walk_tile(const TileNode *__restrict__ tile, int 
       }
     }
     if (COUNT) n_vis++;
-    no = __any_sync(kFull, any_open) ? no + 1 : nend;
+    if (!CAREFUL)
+    { // closest pair of the step whether accepted or not (FMNMX3): a conservative trigger for the exact redo of the tile
+      float m = r2s[0];
+#pragma unroll
+      for (int k = 1; k < T; k++) m = fminf(m, r2s[k]);
+      minr2 = fminf(minr2, m);
+    }
+    // A target that opened this node still has skip <= no; one that accepted it resumes at nend; the others resume at or
+    // after nend.  The warp goes on at the first node some target still needs (one VIMNMX3 tree + one CREDUX.MIN instead
+    // of T compares + a vote, and runs of nodes nobody needs are jumped over in one step).
+    int ms = skip[0];
+#pragma unroll
+    for (int k = 1; k < T; k++) ms = min(ms, skip[k]);
+    no = max(no + 1, __reduce_min_sync(kFull, ms));
   } while (no < tile_lim);
   return no;
 }
