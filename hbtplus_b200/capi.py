@@ -100,6 +100,7 @@ class Stats(C.Structure):
         ("d2h_bytes", C.c_int64),
         ("execute_ms", C.c_double),
         ("tree_sources", C.c_int64),
+        ("walk_fallbacks", C.c_int64),
     ]
 
 

@@ -274,7 +274,7 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
     HBT_CHECK_LAUNCH();
     double *d_sorted = ar.alloc<double>(T), *d_out = ar.alloc<double>(T);
     c.ls.launches += 12;
-    HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
+    HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, kWalkCounters * sizeof(unsigned long long), st));
     WalkArgs wa{};
     wa.node_xm = tr.node_xm;
     wa.node_aux = tr.node_aux;
@@ -308,10 +308,11 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
     c.stats.walk_ms = ms;
     if (c.count_interactions)
     {
-      unsigned long long cnt[2];
+      unsigned long long cnt[kWalkCounters];
       HBT_CUDA(cudaMemcpy(cnt, c.d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
       c.stats.pair_interactions = (int64_t)cnt[0];
       c.stats.nodes_visited = (int64_t)cnt[1];
+      c.stats.walk_fallbacks = (int64_t)cnt[2];
     }
   }
   HBT_CUDA(cudaStreamSynchronize(st));
@@ -381,7 +382,7 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
     HBT_CUDA(cudaStreamCreateWithFlags(&cc.stream, cudaStreamNonBlocking));
     for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
     for (auto &ev : cc.ev_exec) HBT_CUDA(cudaEventCreate(&ev));
-    HBT_CUDA(cudaMalloc(&cc.d_counters, 2 * sizeof(unsigned long long)));
+    HBT_CUDA(cudaMalloc(&cc.d_counters, kWalkCounters * sizeof(unsigned long long)));
   });
   if (rc != HBTU_OK)
   {

@@ -144,8 +144,9 @@ struct WalkArgs
   double *out;           // kWalkPotential / kWalkBindingEnergy
   float *out_f;          // kWalkRefine: per target
   float ref_pos[3], ref_vel[3]; // kWalkBindingEnergy frame
-  unsigned long long *counters; // [2]: accepted interactions, warp node visits (nullptr = do not count)
+  unsigned long long *counters; // [kWalkCounters]: accepted interactions, warp node visits, groups redone per lane (nullptr = do not count)
 };
+constexpr int kWalkCounters = 4;
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 // Walk classes.  A segment belongs to one class; every class has its own warp numbering (warp_off) and launch.
 constexpr int kWalkGroup4 = 104, kWalkGroup8 = 108; // group walk with 128 / 256 targets per warp

@@ -1111,7 +1111,7 @@ void execute_batch(Context &c)
   c.ls.launches = 0;
   std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms));
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
-  if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(unsigned long long), st));
+  if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, kWalkCounters * sizeof(unsigned long long), st));
 
   // (re)initialise per-subhalo state from the staged inputs
   std::vector<SubState> init(nsub);
@@ -1315,10 +1315,11 @@ void execute_batch(Context &c)
   }
   if (c.count_interactions)
   {
-    unsigned long long cnt[2];
+    unsigned long long cnt[kWalkCounters];
     HBT_CUDA(cudaMemcpy(cnt, c.d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
     c.stats.pair_interactions = (int64_t)cnt[0];
     c.stats.nodes_visited = (int64_t)cnt[1];
+    c.stats.walk_fallbacks = (int64_t)cnt[2];
   }
   HBT_CUDA(cudaEventRecord(c.ev_exec[1], st));
   HBT_CUDA(cudaEventSynchronize(c.ev_exec[1]));

@@ -256,7 +256,7 @@ namespace
 {
 struct WalkPolicy
 {
-  int forced, big4, big2, group_min, group_t;
+  int forced, big4, big2, group_min, group_t, masked;
   WalkPolicy()
   {
     auto env = [](const char *n, int d) { const char *e = getenv(n); return e ? atoi(e) : d; };
@@ -265,6 +265,7 @@ struct WalkPolicy
     big2 = env("HBTU_WALK_BIG2", 1 << 19);
     group_min = env("HBTU_WALK_GROUP_MIN", 1 << 13); // segments with at least this many targets use the group walk (0 = never)
     group_t = env("HBTU_WALK_GROUP_T", 4) == 8 ? 8 : 4;
+    masked = env("HBTU_WALK_MASKED", 0); // 1: 128-target groups use the masked group walk (walk_masked.cu) instead of walk_group.cu
   }
 };
 const WalkPolicy &policy()
@@ -279,7 +280,8 @@ void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, L
   if (a.nwarps <= 0) return;
   if (a.targets_per_lane == kWalkGroup4 || a.targets_per_lane == kWalkGroup8)
   {
-    launch_walk_group(a, cfg, stream, ls);
+    if (a.targets_per_lane == kWalkGroup4 && policy().masked) launch_walk_masked(a, cfg, stream, ls);
+    else launch_walk_group(a, cfg, stream, ls);
     return;
   }
   if (a.targets_per_lane == 4) launch_t<4>(a, cfg, stream);

@@ -297,5 +297,7 @@ __device__ __forceinline__ int segment_of_warp(const int *__restrict__ warp_off,
 
 // walk_group.cu
 void launch_walk_group(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
+// walk_masked.cu
+void launch_walk_masked(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 
 } // namespace hbt

@@ -281,6 +281,7 @@ typedef struct hbtu_stats
   int64_t h2d_bytes, d2h_bytes;
   double execute_ms;           /* CUDA-event time of the whole hbtu_execute (host planning gaps included) */
   int64_t tree_sources;        /* source particles over all tree builds (sum over rounds)                */
+  int64_t walk_fallbacks;      /* counting on: groups of the masked walk redone per lane (chain stack exhausted) */
 } hbtu_stats;
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted

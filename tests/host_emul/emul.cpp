@@ -1,81 +1,17 @@
 // emul.cpp - CPU emulation of the device octree index arithmetic (tree_core.cuh) + a scalar fp32
 // walk over the pre-order node array.  TEST-ONLY: built by tests/test_tree_core.py with g++ to
 // unit-test hbtplus_b200/csrc/tree_core.cuh without a GPU.  Never linked into the product library.
-#include <algorithm>
-#include <cmath>
-#include <cstdint>
-#include <cstring>
-#include <vector>
-#include "tree_core.cuh"
-#include "hbt_unbind.h"
+#include "emul_tree.h"
 using namespace hbt;
-
-struct Node { float x, y, z, m, lenq; int end; };
 
 extern "C" int emul_tree_potential(const hbtu_params *p, const hbtu_epoch *e, int64_t n, const float *src, int64_t ntgt,
                                    const float *tgt, const float *self_mass, double *out, int64_t *accepted, int64_t *visited,
                                    int64_t *ncells_out)
 {
-  // bbox -> root (oct_tree.tpp:30-51)
-  float mn[3], mx[3];
-  for (int j = 0; j < 3; j++) mn[j] = mx[j] = src[j];
-  for (int64_t i = 1; i < n; i++)
-    for (int j = 0; j < 3; j++) { mn[j] = std::min(mn[j], src[4 * i + j]); mx[j] = std::max(mx[j], src[4 * i + j]); }
-  SegRoot root;
-  double len = (double)mx[0] - mn[0];
-  for (int j = 1; j < 3; j++) len = std::max(len, (double)mx[j] - mn[j]);
-  root.cx = 0.5 * ((double)mx[0] + mn[0]); root.cy = 0.5 * ((double)mx[1] + mn[1]); root.cz = 0.5 * ((double)mx[2] + mn[2]);
-  root.len = len;
-  root.halvings = count_halvings(len, p->tree_node_resolution);
-  std::vector<uint64_t> key(n);
-  std::vector<int> perm(n);
-  for (int64_t i = 0; i < n; i++) { key[i] = morton_key(src[4 * i], src[4 * i + 1], src[4 * i + 2], root); perm[i] = i; }
-  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
-  std::vector<uint64_t> skey(n);
-  std::vector<float> sp(4 * n);
-  for (int64_t i = 0; i < n; i++) { skey[i] = key[perm[i]]; memcpy(&sp[4 * i], &src[4 * perm[i]], 16); }
-  // cells
-  std::vector<CellRange> cells(n);
-  std::vector<uint32_t> mask(n, 0);
-  for (int64_t i = 0; i + 1 < n; i++) { cells[i] = cell_of_pair(skey.data(), (int)i, 0, (int)n); if (cells[i].is_rep) mask[cells[i].l] |= 1u << cells[i].depth; }
-  std::vector<int> cinc(n);
-  int run = 0;
-  for (int64_t i = 0; i < n; i++) { run += popc32(mask[i]); cinc[i] = run; }
-  int64_t nn = n + run;
-  if (ncells_out) *ncells_out = run;
-  std::vector<double> S(4 * (n + 1), 0.0); // prefix sums of m, m*(x-c)
-  for (int64_t i = 0; i < n; i++)
-  {
-    double m = sp[4 * i + 3];
-    S[4 * (i + 1)] = S[4 * i] + m;
-    S[4 * (i + 1) + 1] = S[4 * i + 1] + m * ((double)sp[4 * i] - root.cx);
-    S[4 * (i + 1) + 2] = S[4 * i + 2] + m * ((double)sp[4 * i + 1] - root.cy);
-    S[4 * (i + 1) + 3] = S[4 * i + 3] + m * ((double)sp[4 * i + 2] - root.cz);
-  }
-  std::vector<Node> nodes(nn);
-  std::vector<char> written(nn, 0);
-  float theta2 = (float)p->tree_node_open_angle_square;
-  for (int64_t i = 0; i < n; i++)
-  {
-    int64_t pos = particle_node_pos((int)i, cinc.data());
-    if (written[pos]) return -100;
-    written[pos] = 1;
-    nodes[pos] = Node{sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], sp[4 * i + 3], 0.f, (int)(pos + 1)};
-  }
-  for (int64_t i = 0; i + 1 < n; i++)
-    if (cells[i].is_rep)
-    {
-      const CellRange &c = cells[i];
-      int64_t pos = cell_node_pos(c, cinc.data(), mask.data());
-      if (pos < 0 || pos >= nn || written[pos]) return -101;
-      written[pos] = 1;
-      double M = S[4 * (c.r + 1)] - S[4 * c.l];
-      float lenf = cell_len(root, c.depth);
-      float lenq = (lenf * lenf) / theta2;
-      nodes[pos] = Node{(float)(root.cx + (S[4 * (c.r + 1) + 1] - S[4 * c.l + 1]) / M), (float)(root.cy + (S[4 * (c.r + 1) + 2] - S[4 * c.l + 2]) / M),
-                        (float)(root.cz + (S[4 * (c.r + 1) + 3] - S[4 * c.l + 3]) / M), (float)M, lenq, (int)cell_node_end(c, cinc.data())};
-    }
-  for (int64_t i = 0; i < nn; i++) if (!written[i]) return -102;
+  std::vector<Node> nodes;
+  std::vector<float> sp;
+  if (int rc = emul_build_nodes(p, n, src, nodes, sp, ncells_out)) return rc;
+  const int64_t nn = (int64_t)nodes.size();
   // scalar fp32 walk
   const float eps = (float)p->softening_halo, h = 2.8f * eps, h2 = h * h, hinv = 1.f / h;
   const bool periodic = p->periodic_boundary_on;

@@ -1,0 +1,89 @@
+"""CPU unit test of the masked group walk's logic (hbtplus_b200/csrc/walk_masked.cuh).
+
+tests/host_emul/masked_emul.cpp compiles the SAME header with g++ behind a warp-emulation shim (32 fibers per warp,
+collectives as rendez-vous that also verify that every lane reached the same collective) and walks groups of 128 targets
+over the pre-order node array; a scalar per-target walk with the same fp32 arithmetic is the check: every target must accept
+exactly the same number of nodes (the opener masks reproduce each target's own decisions) and get the same sum.
+(Test scaffolding only - the product library has no host path; the GPU parity tests cover the compiled kernel.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hbtplus_b200 import capi, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def memul(tmp_path_factory):
+    out = tmp_path_factory.mktemp("memul") / "libmaskedemul.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                           "-I", os.path.join(ROOT, "hbtplus_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(HERE, "host_emul", "masked_emul.cpp"), "-o", str(out)])
+    return C.CDLL(str(out))
+
+
+def run(memul, p, pm, ntgt, stride=1):
+    n = len(pm)
+    ntgt = min(ntgt, n)
+    P = capi._ptr
+    sm, ss = np.zeros(ntgt), np.zeros(ntgt)
+    am, asc = np.zeros(ntgt, np.int64), np.zeros(ntgt, np.int64)
+    stats = np.zeros(4, np.int64)
+    rc = memul.emul_masked_walk(C.byref(p), C.c_int64(n), P(pm, C.c_float), C.c_int64(ntgt), C.c_int64(stride), P(sm, C.c_double), P(ss, C.c_double),
+                                P(am, C.c_int64), P(asc, C.c_int64), P(stats, C.c_int64))
+    assert rc == 0
+    return sm, ss, am, asc, stats
+
+
+def per_lane(a, ntgt):
+    """sum over the (up to 4) targets of every lane of every group"""
+    pad = (-ntgt) % 128
+    return np.concatenate([a, np.zeros(pad, a.dtype)]).reshape(-1, 4, 32).sum(axis=1)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 33, 128, 129, 1000, 20000])
+def test_masked_walk_reproduces_every_targets_decisions(memul, n, periodic):
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=periodic)
+    snap = synth.make_snapshot([n], seed=n + 11, wrap=periodic, centre=[0.1, 31, 62.4] if periodic else None)
+    pm = np.ascontiguousarray(snap.pos_mass)
+    ntgt = min(n, 1536)
+    sm, ss, am, asc, stats = run(memul, p, pm, ntgt)
+    assert stats[0] == 0  # no stack overflow
+    if periodic:  # shifted images round differently from NEAREST(dx): a decision may flip where r^2 straddles the criterion
+        assert abs(int(am.sum()) - int(asc.sum())) <= 1e-4 * asc.sum() + 2
+        assert np.mean(per_lane(am, ntgt) == per_lane(asc, ntgt)) > 0.98
+    else:
+        assert np.array_equal(per_lane(am, ntgt), per_lane(asc, ntgt))
+    # periodic: the group's common image is more accurate than NEAREST(dx) of a wrapped pair (ulp(62) = 4e-6 against
+    # pair distances of 1e-2); the same holds for walk_group.cu's dense ring
+    assert np.allclose(sm, ss, rtol=5e-5 if periodic else 2e-6, atol=0)
+
+
+def test_masked_walk_softened_and_colocated(memul):
+    """softening comparable to the inter-particle distance (many spline pairs, softened cells) and co-located particles"""
+    p = capi.make_params(box_size=62.5, softening=0.05, periodic=False)
+    snap = synth.make_snapshot([3000], seed=5, wrap=False)
+    pm = np.ascontiguousarray(snap.pos_mass)
+    pm[100:140, :3] = pm[100, :3]
+    pm[200:203, :3] = pm[200, :3] + np.float32(1e-7)
+    sm, ss, am, asc, stats = run(memul, p, pm, 3000)
+    assert stats[0] == 0
+    assert np.array_equal(per_lane(am, 3000), per_lane(asc, 3000))
+    assert np.allclose(sm, ss, rtol=2e-6, atol=0)
+
+
+def test_masked_walk_dense_core(memul):
+    """a cuspy 2e5-particle halo with the bench's tiny softening: deep trees, long sibling chains, the stack under load"""
+    p = capi.make_params(box_size=100.0, softening=4.8e-5, periodic=False)
+    snap = synth.make_snapshot([200000], seed=3, wrap=False)
+    pm = np.ascontiguousarray(snap.pos_mass)
+    sm, ss, am, asc, stats = run(memul, p, pm, 200000, stride=97)  # 17 groups across the whole halo
+    assert stats[0] == 0
+    assert asc.sum() > 0 and np.array_equal(per_lane(am, 200000), per_lane(asc, 200000))
+    assert np.allclose(sm, ss, rtol=2e-6, atol=0)
