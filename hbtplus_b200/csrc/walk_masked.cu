@@ -13,24 +13,27 @@ namespace hbt
 
 static constexpr int kMW = 4; // warps per CTA (warps are independent)
 #ifndef HBT_MASKED_MINBLOCKS
-#define HBT_MASKED_MINBLOCKS 6 // default resident CTAs per SM the register allocation allows (HBTU_WALK_MASKED_BLOCKS = 5, 6, 7 selects)
+#define HBT_MASKED_MINBLOCKS 7 // default resident CTAs per SM the register allocation allows (HBTU_WALK_MASKED_BLOCKS = 5, 6, 7 selects)
 #endif
 
+template <int STACK>
 union MaskedWarpSmem
 {
-  MaskedSmem m;
-  TileNode tile[32]; // per-lane fallback only (the group restarts from scratch, so the rings are dead by then)
+  MaskedSmemT<STACK> m;
+  TileNode tile[32]; // per-lane fallback only (the group restarts from scratch, so the lists are dead by then)
 };
+// chain-stack entries per warp for a given number of resident CTAs per SM: what fits into 228 KB of shared memory
+template <int MINB> struct MaskedStack { static constexpr int value = MINB >= 7 ? 144 : (MINB == 6 ? 200 : 280); };
 
 template <bool PERIODIC, bool COUNT, int MINB>
 __global__ void __launch_bounds__(kMW * 32, MINB) walk_masked_kernel(const WalkArgs a, const DevConfig cfg)
 {
   constexpr int T = 4;
-  __shared__ MaskedWarpSmem s_all[kMW];
+  __shared__ MaskedWarpSmem<MaskedStack<MINB>::value> s_all[kMW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kMW + w;
   if (warp >= a.nwarps) return;
-  MaskedWarpSmem &sm = s_all[w];
+  MaskedWarpSmem<MaskedStack<MINB>::value> &sm = s_all[w];
   const int seg = segment_of_warp(a.warp_off, a.nseg, warp);
   const Segment sg = a.segs[seg];
   const int j0 = (warp - a.warp_off[seg]) * (32 * T) + lane;
@@ -108,6 +111,13 @@ static void launch_masked_b(const WalkArgs &a, const DevConfig &cfg, cudaStream_
 {
   const int grid = div_up(a.nwarps, kMW);
   const bool count = a.counters != nullptr;
+  static const bool carveout = [] { // MINB CTAs of ~32 KB static shared memory only fit with the largest shared-memory carve-out
+    for (auto *k : {walk_masked_kernel<true, true, MINB>, walk_masked_kernel<true, false, MINB>, walk_masked_kernel<false, true, MINB>,
+                    walk_masked_kernel<false, false, MINB>})
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carveout;
   if (cfg.periodic)
   {
     if (count) walk_masked_kernel<true, true, MINB><<<grid, kMW * 32, 0, stream>>>(a, cfg);

@@ -12,10 +12,11 @@
 //     in walk_group.cu: FAR (all targets accept), OPEN (all open), NEAR (particle, maybe softened), MIXED;
 //   * FAR nodes of full-mask chains go to the dense ring (the bare 8-slot pair kernel, two targets per FADD2/FFMA2);
 //   * OPEN cells push their children as a new chain with the SAME mask;
-//   * every other node becomes a MASKED ENTRY (node, len^2/theta^2, mask): the warp evaluates it for the targets of the
-//     mask only - slice pairs whose mask words are empty are skipped -, each target deciding for itself; the targets
-//     that open the node form the mask of the chain of its children.  A node everyone in the mask accepts is the same
-//     entry with len^2/theta^2 = 0.  Entries whose box bound cannot exclude a softened pair or a second periodic image
+//   * every other node becomes a MASKED ELEMENT (node, len^2/theta^2, mask) in the ring of each slice pair (64 targets)
+//     that has targets in the mask: the warp evaluates it with one packed fp32x2 pair computation, each target of the
+//     mask deciding for itself; the targets that open the node form the mask of the chain of its children, which from
+//     there on belongs to that slice pair.  A node everyone in the mask accepts is the same element with
+//     len^2/theta^2 = 0.  Elements for which a softened accepted pair or a second periodic image cannot be excluded
 //     are evaluated with the reference's full kernel per target (spline in double, NEAREST per target).
 //
 // All loops are dense and free of walk-order dependencies, partial sums are fp32 over at most kMCap entries and then
@@ -26,31 +27,41 @@
 // masked_emul.cpp includes it after a warp-emulation shim (32 fibers) to unit-test the logic on the CPU.
 #pragma once
 
+#ifndef HBT_MASKED_ROOM_PER_LANE
+#define HBT_MASKED_ROOM_PER_LANE 3 // free stack entries demanded per walking lane (a chain pushes <= 8, typically 2)
+#endif
+#ifndef HBT_MASKED_TRACK
+#define HBT_MASKED_TRACK(ncs) // test hook of the CPU emulation (stack high-water mark)
+#endif
+
 namespace hbt
 {
 
-static constexpr int kMStack = 176; // chain entries per warp
-static constexpr int kMCap = 48;    // ring of pending masked entries
-static constexpr int kMPend = 16;   // evaluated whenever more than this many are pending (<= 32 arrive per iteration)
+static constexpr int kMPend = 8;          // masked elements / pending chains are drained when more than this many wait ...
+static constexpr int kMCap = kMPend + 32; // ... and at most 32 arrive per iteration
 
-struct __align__(16) MEntry
-{
-  float4 nxm;    // -x, -y, -z, -m: operands of the packed adds and of the accumulate
-  float lenq;    // len^2/theta^2; 0 = every target of the mask accepts
-  int cur1, kend; // children of the node: [cur1, kend)
-  int exact;     // 1: raw coordinates, per-target NEAREST and spline test (the box bound could not exclude them)
-  unsigned m[4]; // targets taking part (bit = lane, word = slice)
-};
+// Masked elements are kept per SLICE PAIR (slices 0,1 = targets 0..63 of the group, slices 2,3 = targets 64..127): an
+// element sits in the list of every pair that has targets in its mask, so its evaluation is one packed fp32x2 pair
+// computation without any per-word branching.  The chain of the children of a disagreeing node waits in `pending`
+// with empty masks while the evaluation of each pair fills in its two opener words; a DRAIN evaluates both lists and
+// moves the pending chains somebody opened onto the stack (the others are dropped).
 struct __align__(8) ChainEntry
 {
   int cur, pend; // siblings still to classify: cur, end(cur), ... < pend
-  unsigned m[4];
+  unsigned m[4]; // targets walking the chain (bit = lane, word = slice)
 };
-struct MaskedSmem
+template <int STACK> // chain entries per warp
+struct MaskedSmemT
 {
-  float4 alist[64]; // ring of FAR nodes of full-mask chains (periodic: shifted to the group's image)
-  MEntry mlist[kMCap];
-  ChainEntry stack[kMStack];
+  static constexpr int kStack = STACK;
+  float4 alist[64];         // ring of FAR nodes of whole-group chains (periodic: shifted to the group's image)
+  float4 r_xm[2][kMCap];    // masked elements per pair: -x, -y, -z, -m (operands of the packed adds and of the accumulate)
+  int2 r_aux[2][kMCap];     //   len^2/theta^2 bits (0 = every target of the mask accepts); index of the children's chain in
+                            //   `pending` (kMCap = none: scratch entry), bit-complemented when the element needs the exact kernel
+  uint2 r_m[2][kMCap];      //   targets taking part (bit = lane; x = first slice of the pair, y = second)
+  ChainEntry pending[kMCap + 1];
+  ChainEntry stack[STACK];
+  float box[8];             // centre and inflated half widths of the group's bounding box
 };
 
 __device__ __forceinline__ double spline_wp(float r2, double hinv_d)
@@ -86,31 +97,10 @@ __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring,
   accd[3] += (double)accf[1].y;
 }
 
-// one slice pair (K, K+1) of a masked entry whose box bound already excluded softening and a second image
-template <int K, bool COUNT>
-__device__ __forceinline__ void masked_pair(const float4 &n, float lenq, unsigned ma, unsigned mb, unsigned lanebit, const float (&px)[4],
-                                            const float (&py)[4], const float (&pz)[4], float (&accf)[4], unsigned &opa, unsigned &opb,
-                                            unsigned &n_acc)
-{
-  const float2 dx = f2_add(make_float2(px[K], px[K + 1]), make_float2(n.x, n.x));
-  const float2 dy = f2_add(make_float2(py[K], py[K + 1]), make_float2(n.y, n.y));
-  const float2 dz = f2_add(make_float2(pz[K], pz[K + 1]), make_float2(n.z, n.z));
-  const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-  const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
-  const bool ina = (ma & lanebit) != 0u, inb = (mb & lanebit) != 0u;
-  const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
-  if (ina && !opena) accf[K] = fmaf(n.w, ra, accf[K]);
-  if (inb && !openb) accf[K + 1] = fmaf(n.w, rb, accf[K + 1]);
-  opa = __ballot_sync(kFull, ina && opena);
-  opb = __ballot_sync(kFull, inb && openb);
-  if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
-}
-
-// one slice of an entry that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161)
+// one slice of an element that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161)
 template <bool PERIODIC, bool COUNT>
-__device__ __forceinline__ void masked_exact(const float4 &n, float lenq, unsigned m, unsigned lanebit, float pxk, float pyk, float pzk, float &accf,
-                                             double &accd, unsigned &op, float box_size, float box_half, float h2, double hinv_d,
-                                             unsigned &n_acc)
+__device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool in, float pxk, float pyk, float pzk, float &accf, double &accd,
+                                             unsigned &op, float box_size, float box_half, float h2, float softening, unsigned &n_acc)
 {
   float dx = pxk + n.x, dy = pyk + n.y, dz = pzk + n.z;
   if (PERIODIC)
@@ -120,14 +110,16 @@ __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, unsign
     dz = nearest_f(dz, box_size, box_half);
   }
   const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); // FMUL, FFMA, FFMA like the packed path
-  const bool in = (m & lanebit) != 0u;
   const bool open = lenq > r2;
   const bool acc = in && !open;
   const bool soft = acc && r2 < h2;
   if (__any_sync(kFull, soft))
   {
     if (soft)
+    {
+      const double hinv_d = 1.0 / (2.8 * (double)softening);
       accd += (double)(-n.w) * hinv_d * spline_wp(r2, hinv_d);
+    }
     else if (acc)
       accf = fmaf(n.w, rsqrt_raw(r2), accf);
   }
@@ -137,75 +129,65 @@ __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, unsign
   if (COUNT) n_acc += (unsigned)acc;
 }
 
-// evaluate the pending masked entries [mb, mb+cnt) of the ring; openers push the chain of the node's children.
-// Returns false when the chain stack is full.
-template <bool PERIODIC, bool COUNT>
-__device__ __forceinline__ bool masked_eval(MaskedSmem &sm, int mb, int cnt, int lane, unsigned lanebit, const float (&px)[4], const float (&py)[4],
-                                            const float (&pz)[4], double (&accd)[4], float box_size, float box_half, float h2, double hinv_d,
-                                            int &ncs, unsigned &n_acc)
+// evaluate the `cnt` elements of the list of slice pair (K, K+1); the targets that open an element are written into the
+// pending chain of the node's children
+template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
+__device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, unsigned lanebit, const float (&px)[4], const float (&py)[4],
+                                            const float (&pz)[4], double (&accd)[4], float box_size, float box_half, float h2, float softening,
+                                            unsigned &n_acc)
 {
-  float accf[4] = {0.f, 0.f, 0.f, 0.f};
-  bool ok = true;
+  constexpr int R = K / 2;
+  float acca = 0.f, accb = 0.f;
+  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
   for (int i = 0; i < cnt; i++)
   {
-    int idx = mb + i;
-    if (idx >= kMCap) idx -= kMCap;
-    const MEntry &e = sm.mlist[idx];
-    const float4 n = e.nxm;
-    const float lenq = e.lenq;
-    const int exact = e.exact;
-    const unsigned m0 = e.m[0], m1 = e.m[1], m2 = e.m[2], m3 = e.m[3];
-    unsigned o0 = 0u, o1 = 0u, o2 = 0u, o3 = 0u;
-    if (!exact)
-    {
-      if ((m0 | m1) != 0u) masked_pair<0, COUNT>(n, lenq, m0, m1, lanebit, px, py, pz, accf, o0, o1, n_acc);
-      if ((m2 | m3) != 0u) masked_pair<2, COUNT>(n, lenq, m2, m3, lanebit, px, py, pz, accf, o2, o3, n_acc);
+    const float4 n = sm.r_xm[R][i];
+    const int2 aux = sm.r_aux[R][i];
+    const uint2 m = sm.r_m[R][i];
+    const float lenq = __int_as_float(aux.x);
+    const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
+    unsigned oa, ob;
+    int slot = aux.y;
+    if (slot >= 0)
+    { // no accepted pair can be softened, one periodic image: the bare pair kernel + the criterion
+      const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+      const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+      const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+      const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
+      if (ina && !opena) acca = fmaf(n.w, ra, acca);
+      if (inb && !openb) accb = fmaf(n.w, rb, accb);
+      oa = __ballot_sync(kFull, ina && opena);
+      ob = __ballot_sync(kFull, inb && openb);
+      if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
     }
     else
     {
-      if (m0 != 0u) masked_exact<PERIODIC, COUNT>(n, lenq, m0, lanebit, px[0], py[0], pz[0], accf[0], accd[0], o0, box_size, box_half, h2, hinv_d, n_acc);
-      if (m1 != 0u) masked_exact<PERIODIC, COUNT>(n, lenq, m1, lanebit, px[1], py[1], pz[1], accf[1], accd[1], o1, box_size, box_half, h2, hinv_d, n_acc);
-      if (m2 != 0u) masked_exact<PERIODIC, COUNT>(n, lenq, m2, lanebit, px[2], py[2], pz[2], accf[2], accd[2], o2, box_size, box_half, h2, hinv_d, n_acc);
-      if (m3 != 0u) masked_exact<PERIODIC, COUNT>(n, lenq, m3, lanebit, px[3], py[3], pz[3], accf[3], accd[3], o3, box_size, box_half, h2, hinv_d, n_acc);
+      slot = ~slot;
+      masked_exact<PERIODIC, COUNT>(n, lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
+      masked_exact<PERIODIC, COUNT>(n, lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
     }
-    if ((o0 | o1 | o2 | o3) != 0u)
-    { // the targets that opened this node walk its children
-      if (ncs >= kMStack)
-      {
-        ok = false;
-        break;
-      }
-      if (lane == 0)
-      {
-        ChainEntry &c = sm.stack[ncs];
-        c.cur = e.cur1;
-        c.pend = e.kend;
-        c.m[0] = o0; c.m[1] = o1; c.m[2] = o2; c.m[3] = o3;
-      }
-      ncs++;
-    }
+    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[slot].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
   }
-#pragma unroll
-  for (int k = 0; k < 4; k++) accd[k] += (double)accf[k];
-  __syncwarp();
-  return ok;
+  accd[K] += (double)acca;
+  accd[K + 1] += (double)accb;
 }
 
 // The walk of one group: targets px/py/pz (4 per lane: slice k = targets 32k .. 32k+31 of the group; periodic: already
 // un-wrapped towards one common image; invalid slots repeat a valid position) over the pre-order nodes
 // [node_begin, node_end).  accd[k] receives sum(-m/r) (softened pairs: the spline term) of target (lane, k).
 // nacc: warp-uniform part of the accepted-interaction count; n_acc: per-lane part; n_vis: node-parallel iterations.
-template <bool PERIODIC, bool COUNT>
+template <bool PERIODIC, bool COUNT, class MaskedSmem>
 __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, const float4 *__restrict__ node_xm, const float2 *__restrict__ node_aux,
                                                   int node_begin, int node_end, const float (&px)[4], const float (&py)[4], const float (&pz)[4],
                                                   const bool (&valid)[4], int n0, float box_size, float box_half, float softening, double (&accd)[4],
                                                   unsigned long long &nacc, unsigned &n_acc, unsigned &n_vis)
 {
+  constexpr int kMStack = MaskedSmem::kStack;
   const unsigned lt = (1u << lane) - 1u, lanebit = 1u << lane;
   const float h = 2.8f * softening, h2 = h * h;
-  const double hinv_d = 1.0 / (2.8 * (double)softening);
   // bounding box of the group (ordered-uint REDUX), centre + inflated half widths
-  float cx, cy, cz, hx, hy, hz;
   {
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -215,25 +197,26 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       lo[0] = min(lo[0], ux); lo[1] = min(lo[1], uy); lo[2] = min(lo[2], uz);
       hi[0] = max(hi[0], ux); hi[1] = max(hi[1], uy); hi[2] = max(hi[2], uz);
     }
-    float l[3], hh[3];
 #pragma unroll
     for (int j = 0; j < 3; j++)
     {
-      l[j] = ordered_to_float(__reduce_min_sync(kFull, lo[j]));
-      hh[j] = ordered_to_float(__reduce_max_sync(kFull, hi[j]));
+      const float l = ordered_to_float(__reduce_min_sync(kFull, lo[j]));
+      const float hh = ordered_to_float(__reduce_max_sync(kFull, hi[j]));
+      const float c = 0.5f * (l + hh);
+      if (lane == 0)
+      {
+        sm.box[j] = c;
+        sm.box[4 + j] = fmaxf(hh - c, c - l) * 1.00001f + 1e-30f;
+      }
     }
-    cx = 0.5f * (l[0] + hh[0]); cy = 0.5f * (l[1] + hh[1]); cz = 0.5f * (l[2] + hh[2]);
-    hx = fmaxf(hh[0] - cx, cx - l[0]) * 1.00001f + 1e-30f;
-    hy = fmaxf(hh[1] - cy, cy - l[1]) * 1.00001f + 1e-30f;
-    hz = fmaxf(hh[2] - cz, cz - l[2]) * 1.00001f + 1e-30f;
   }
-  // mask of the whole group (n0 bits)
+  // masks of the whole group (n0 bits)
   const unsigned vm0 = __ballot_sync(kFull, valid[0]), vm1 = __ballot_sync(kFull, valid[1]);
   const unsigned vm2 = __ballot_sync(kFull, valid[2]), vm3 = __ballot_sync(kFull, valid[3]);
 
-  int ncs = 0;         // chains on the stack
-  int na = 0, ab = 0;  // dense ring: pending, base
-  int nm = 0, mb = 0;  // masked ring: pending, base
+  int ncs = 0;        // chains on the stack
+  int na = 0, ab = 0; // dense ring: pending, base
+  int nm0 = 0, nm1 = 0, np = 0; // masked elements of slices 0,1 / 2,3; pending chains
   if (node_end > node_begin)
   {
     if (lane == 0)
@@ -247,51 +230,49 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
   }
   __syncwarp();
 
-  // One loop: every iteration classifies the node each active lane stands on and moves the lane to the node's sibling.
-  // When no lane has a node left, up to 32 chains are taken off the stack; pending masked entries are evaluated at one
-  // place, before they could overflow their ring or when nothing else is left.
+  // One loop.  Every iteration a lane without a node takes a chain off the stack, every lane classifies the node it
+  // stands on and moves to the node's sibling.
   int cur = 0, pend = 0;
   unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u; // mask of the lane's chain
   bool full = false;                           // ... it is the whole group
   while (true)
   {
-    const bool anyact = __any_sync(kFull, cur < pend);
-    if (nm > kMPend || (!anyact && ncs == 0 && nm > 0))
-    {
-      if (!masked_eval<PERIODIC, COUNT>(sm, mb, nm, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, hinv_d, ncs, n_acc)) return false;
-      mb += nm;
-      if (mb >= kMCap) mb -= kMCap;
-      nm = 0;
-    }
-    if (!anyact)
-    {
-      if (ncs == 0) break;
-      // a chain pushes at most one entry per child; most children are accepted, so a quarter of the worst case is reserved
-      const int take = min(min(32, ncs), max(1, (kMStack - ncs - nm) >> 2));
-      ncs -= take;
-      if (lane < take)
+    const unsigned mI = __ballot_sync(kFull, !(cur < pend));
+    if (mI != 0u && ncs > 0)
+    { // idle lanes take chains; the fuller the stack, the fewer (every walking lane can push one entry per iteration)
+      const int room = kMStack - ncs;
+      const int lim = max(mI == kFull ? 1 : 0, room / HBT_MASKED_ROOM_PER_LANE - (32 - __popc(mI))); // walking lanes <= room / 3
+      const int t = min(min(__popc(mI), ncs), lim);
+      const int r = __popc(mI & lt);
+      if (!(cur < pend) && r < t)
       {
-        const ChainEntry &c = sm.stack[ncs + lane];
+        const ChainEntry &c = sm.stack[ncs - 1 - r];
         cur = c.cur;
         pend = c.pend;
         c0 = c.m[0]; c1 = c.m[1]; c2 = c.m[2]; c3 = c.m[3];
+        full = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) == n0;
       }
-      full = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) == n0;
+      ncs -= t;
       __syncwarp();
     }
+    HBT_MASKED_TRACK(ncs);
     const bool act = cur < pend;
+    const bool anyact = __any_sync(kFull, act);
+    if (!anyact && ncs == 0 && np == 0 && nm0 == 0 && nm1 == 0) break;
     int cls = 0; // 1 FAR, 2 NEAR, 3 OPEN, 4 MIXED
     float4 xm = make_float4(0.f, 0.f, 0.f, 0.f), xs = xm;
     float lenq = 0.f;
     int kend = 0;
-    bool bare = false; // box bound excludes softened pairs and a second periodic image
+    bool bare = false; // no accepted pair can be softened and the group sees one periodic image of the node
     if (act)
     {
       xm = __ldg(&node_xm[cur]);
       const float2 ax = __ldg(&node_aux[cur]);
       lenq = ax.x;
       kend = __float_as_int(ax.y);
-      float dx = xm.x - cx, dy = xm.y - cy, dz = xm.z - cz;
+      const float4 bc = *reinterpret_cast<const float4 *>(&sm.box[0]), bh = *reinterpret_cast<const float4 *>(&sm.box[4]);
+      const float hx = bh.x, hy = bh.y, hz = bh.z;
+      float dx = xm.x - bc.x, dy = xm.y - bc.y, dz = xm.z - bc.z;
       xs = xm;
       bool wrap_ok = true;
       if (PERIODIC)
@@ -307,16 +288,21 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       const float fx = adx + hx, fy = ady + hy, fz = adz + hz;
       const float r2min = (nx * nx + ny * ny + nz * nz) * 0.99998f;
       const float r2max = (fx * fx + fy * fy + fz * fz) * 1.00002f;
-      bare = wrap_ok && r2min >= h2;
-      if (lenq == 0.f) cls = bare ? 1 : 2; // a particle is accepted by everyone
+      const bool far_ok = wrap_ok && r2min >= h2;
+      // a cell is only accepted at r^2 >= len^2/theta^2: with len^2/theta^2 >= h^2 no accepted pair is softened
+      bare = wrap_ok && (r2min >= h2 || lenq >= h2);
+      if (lenq == 0.f) cls = far_ok ? 1 : 2; // a particle is accepted by everyone
       else if (!wrap_ok) cls = 4;
       else if (lenq > r2max) cls = 3;
-      else if (!(lenq > r2min) && bare) cls = 1;
+      else if (!(lenq > r2min) && far_ok) cls = 1;
       else cls = 4;
     }
     if (COUNT) n_vis++;
     const bool toA = (cls == 1) && full, toO = (cls == 3), toM = act && !toA && !toO;
-    const unsigned mA = __ballot_sync(kFull, toA), mO = __ballot_sync(kFull, toO), mM = __ballot_sync(kFull, toM);
+    const bool toP = toM && cls == 4; // the targets decide: the chain of the children waits for their answer
+    const bool toM0 = toM && (c0 | c1) != 0u, toM1 = toM && (c2 | c3) != 0u;
+    const unsigned mA = __ballot_sync(kFull, toA), mO = __ballot_sync(kFull, toO), mP = __ballot_sync(kFull, toP);
+    const unsigned mM0 = __ballot_sync(kFull, toM0), mM1 = __ballot_sync(kFull, toM1);
     const int cO = __popc(mO);
     if (ncs + cO > kMStack) return false; // stack exhausted (pathologically deep tree): the caller redoes the group per lane
     if (toA) sm.alist[(ab + na + __popc(mA & lt)) & 63] = xs;
@@ -327,22 +313,42 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       c.pend = kend;
       c.m[0] = c0; c.m[1] = c1; c.m[2] = c2; c.m[3] = c3;
     }
+    int slot = kMCap; // scratch entry: elements everybody accepts have no children chain
+    if (toP)
+    {
+      slot = np + __popc(mP & lt);
+      ChainEntry &c = sm.pending[slot];
+      c.cur = cur + 1;
+      c.pend = kend;
+      c.m[0] = 0u; c.m[1] = 0u; c.m[2] = 0u; c.m[3] = 0u; // filled in by the evaluation of the element
+    }
     if (toM)
     {
-      int idx = mb + nm + __popc(mM & lt);
-      if (idx >= kMCap) idx -= kMCap;
-      MEntry &e = sm.mlist[idx];
       const float4 p = bare ? xs : xm;
-      e.nxm = make_float4(-p.x, -p.y, -p.z, -p.w);
-      e.lenq = (cls == 1) ? 0.f : lenq; // FAR for the whole group: accepted by every target of the mask
-      e.cur1 = cur + 1;
-      e.kend = kend;
-      e.exact = bare ? 0 : 1;
-      e.m[0] = c0; e.m[1] = c1; e.m[2] = c2; e.m[3] = c3;
+      const float4 np4 = make_float4(-p.x, -p.y, -p.z, -p.w);
+      // FAR for the whole group: accepted by every target of the mask
+      const int2 aux = make_int2(__float_as_int((cls == 1) ? 0.f : lenq), bare ? slot : ~slot);
+      if (toM0)
+      {
+        const int idx = nm0 + __popc(mM0 & lt);
+        sm.r_xm[0][idx] = np4;
+        sm.r_aux[0][idx] = aux;
+        sm.r_m[0][idx] = make_uint2(c0, c1);
+      }
+      if (toM1)
+      {
+        const int idx = nm1 + __popc(mM1 & lt);
+        sm.r_xm[1][idx] = np4;
+        sm.r_aux[1][idx] = aux;
+        sm.r_m[1][idx] = make_uint2(c2, c3);
+      }
     }
     na += __popc(mA);
     ncs += cO;
-    nm += __popc(mM);
+    np += __popc(mP);
+    nm0 += __popc(mM0);
+    nm1 += __popc(mM1);
+    if (act) cur = kend;
     __syncwarp();
     if (na >= 32)
     {
@@ -351,7 +357,29 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       ab = (ab + 32) & 63;
       na -= 32;
     }
-    if (act) cur = kend;
+    if (nm0 > kMPend || nm1 > kMPend || np > kMPend || (!anyact && ncs == 0) || (mI == kFull && ncs < 32))
+    { // DRAIN: evaluate both lists, then move the pending chains somebody opened onto the stack
+      if (nm0 > 0) masked_eval<0, PERIODIC, COUNT, MaskedSmem>(sm, nm0, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      if (nm1 > 0) masked_eval<2, PERIODIC, COUNT, MaskedSmem>(sm, nm1, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      nm0 = 0;
+      nm1 = 0;
+      __syncwarp();
+      for (int b = 0; b < np; b += 32)
+      {
+        const int i = b + lane;
+        ChainEntry c;
+        c.cur = 0; c.pend = 0; c.m[0] = 0u; c.m[1] = 0u; c.m[2] = 0u; c.m[3] = 0u;
+        if (i < np) c = sm.pending[i];
+        const bool live = (c.m[0] | c.m[1] | c.m[2] | c.m[3]) != 0u;
+        const unsigned mL = __ballot_sync(kFull, live);
+        const int cL = __popc(mL);
+        if (ncs + cL > kMStack) return false;
+        if (live) sm.stack[ncs + __popc(mL & lt)] = c;
+        ncs += cL;
+      }
+      np = 0;
+      __syncwarp();
+    }
   }
   if (na > 0)
   {

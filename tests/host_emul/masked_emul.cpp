@@ -6,7 +6,15 @@
 #include "warp_emul.h"
 using hbt::float_to_ordered;
 using hbt::ordered_to_float;
+static int g_max_ncs = 0;
+static int64_t g_hist[8];
+#define HBT_MASKED_TRACK(ncs) do { if ((ncs) > g_max_ncs) g_max_ncs = (ncs); } while (0)
 #include "walk_masked.cuh"
+
+#ifndef EMUL_STACK
+#define EMUL_STACK 144
+#endif
+typedef hbt::MaskedSmemT<EMUL_STACK> SmemT;
 
 extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *src, int64_t ntgt_in, int64_t group_stride, double *sum_masked, double *sum_scalar,
                                 int64_t *acc_masked, int64_t *acc_scalar, int64_t *stats /*[4]: overflows, iterations, collectives, groups*/)
@@ -29,7 +37,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
   const float box = (float)p->box_size, half = (float)p->box_half;
   const int64_t ntgt = std::min<int64_t>(ntgt_in, n);
   int64_t overflows = 0, iters = 0, groups = 0;
-  struct Guarded { uint64_t c0[8]; hbt::MaskedSmem sm; uint64_t c1[8]; };
+  struct Guarded { uint64_t c0[8]; SmemT sm; uint64_t c1[8]; };
   static Guarded g;
   if (group_stride < 1) group_stride = 1;
   for (int64_t g0 = 0; g0 < ntgt; g0 += 128 * group_stride)
@@ -80,6 +88,8 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
     for (int q = 0; q < 8; q++)
       if (g.c0[q] != 0x5a5a5a5a5a5a5a5aull || g.c1[q] != 0x5a5a5a5a5a5a5a5aull) return -200;
     if (!ok_all) overflows++;
+    if (getenv("EMUL_VERBOSE")) fprintf(stderr, "group %ld: max stack %d iters %u ok %d\n", (long)g0, g_max_ncs, vis_lane0, (int)ok_all);
+    g_max_ncs = 0;
     iters += vis_lane0;
   }
   // scalar per-target walk, same fp32 arithmetic (FMUL, FFMA, FFMA; criterion on the fp32 r^2)
