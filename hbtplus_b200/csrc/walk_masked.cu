@@ -13,7 +13,7 @@ namespace hbt
 
 static constexpr int kMW = 4; // warps per CTA (warps are independent)
 #ifndef HBT_MASKED_MINBLOCKS
-#define HBT_MASKED_MINBLOCKS 7 // default resident CTAs per SM the register allocation allows (HBTU_WALK_MASKED_BLOCKS = 5, 6, 7 selects)
+#define HBT_MASKED_MINBLOCKS 5 // default resident CTAs per SM the register allocation allows (HBTU_WALK_MASKED_BLOCKS = 4, 5, 6 selects)
 #endif
 
 template <int STACK>
@@ -23,7 +23,7 @@ union MaskedWarpSmem
   TileNode tile[32]; // per-lane fallback only (the group restarts from scratch, so the lists are dead by then)
 };
 // chain-stack entries per warp for a given number of resident CTAs per SM: what fits into 228 KB of shared memory
-template <int MINB> struct MaskedStack { static constexpr int value = MINB >= 7 ? 144 : (MINB == 6 ? 200 : 280); };
+template <int MINB> struct MaskedStack { static constexpr int value = MINB >= 6 ? 104 : (MINB == 5 ? 184 : 216); };
 
 template <bool PERIODIC, bool COUNT, int MINB>
 __global__ void __launch_bounds__(kMW * 32, MINB) walk_masked_kernel(const WalkArgs a, const DevConfig cfg)
@@ -134,9 +134,9 @@ void launch_walk_masked(const WalkArgs &a, const DevConfig &cfg, cudaStream_t st
 {
   if (a.nwarps <= 0) return;
   static const int blocks = [] { const char *e = getenv("HBTU_WALK_MASKED_BLOCKS"); return e ? atoi(e) : HBT_MASKED_MINBLOCKS; }();
-  if (blocks == 5) launch_masked_b<5>(a, cfg, stream);
-  else if (blocks == 7) launch_masked_b<7>(a, cfg, stream);
-  else launch_masked_b<6>(a, cfg, stream);
+  if (blocks == 4) launch_masked_b<4>(a, cfg, stream);
+  else if (blocks == 6) launch_masked_b<6>(a, cfg, stream);
+  else launch_masked_b<5>(a, cfg, stream);
   HBT_CHECK_LAUNCH();
   ls.launches++;
 }

@@ -37,31 +37,44 @@
 namespace hbt
 {
 
-static constexpr int kMPend = 8;          // masked elements / pending chains are drained when more than this many wait ...
+static constexpr int kMPend = 8;          // deciding elements / pending chains are drained when more than this many wait ...
 static constexpr int kMCap = kMPend + 32; // ... and at most 32 arrive per iteration
+static constexpr int kAPend = 16;         // accept-all elements are evaluated when more than this many wait
+static constexpr int kACap = kAPend + 32;
 
 // Masked elements are kept per SLICE PAIR (slices 0,1 = targets 0..63 of the group, slices 2,3 = targets 64..127): an
 // element sits in the list of every pair that has targets in its mask, so its evaluation is one packed fp32x2 pair
-// computation without any per-word branching.  The chain of the children of a disagreeing node waits in `pending`
-// with empty masks while the evaluation of each pair fills in its two opener words; a DRAIN evaluates both lists and
-// moves the pending chains somebody opened onto the stack (the others are dropped).
+// computation without any per-word branching.  Two kinds of lists per pair:
+//   accept-all (a_*): a node that is FAR for the whole group met by a chain with a partial mask - the bare pair kernel
+//                     under the mask, nothing else (72 % of the masked elements of the bench);
+//   deciding (d):     each target of the mask applies the criterion (or needs the exact kernel).  The chain of the
+//                     children waits in `pending` with empty masks while the evaluation of each pair fills in its two
+//                     opener words; a DRAIN evaluates both deciding lists and moves the pending chains somebody opened
+//                     onto the stack (the others are dropped).
 struct __align__(8) ChainEntry
 {
   int cur, pend; // siblings still to classify: cur, end(cur), ... < pend
   unsigned m[4]; // targets walking the chain (bit = lane, word = slice)
 };
+struct __align__(16) DecidingElem
+{
+  float4 nxm;      // -x, -y, -z, -m: operands of the packed adds and of the accumulate
+  float lenq;      // len^2/theta^2 (0 for a particle: every target of the mask accepts)
+  int slot;        // index of the children's chain in `pending` (kMCap = none: scratch entry); bit-complemented when the
+                   // element needs the exact kernel (softened pair or second periodic image not excluded)
+  unsigned ma, mb; // targets taking part (bit = lane; first / second slice of the pair)
+};
 template <int STACK> // chain entries per warp
 struct MaskedSmemT
 {
   static constexpr int kStack = STACK;
-  float4 alist[64];         // ring of FAR nodes of whole-group chains (periodic: shifted to the group's image)
-  float4 r_xm[2][kMCap];    // masked elements per pair: -x, -y, -z, -m (operands of the packed adds and of the accumulate)
-  int2 r_aux[2][kMCap];     //   len^2/theta^2 bits (0 = every target of the mask accepts); index of the children's chain in
-                            //   `pending` (kMCap = none: scratch entry), bit-complemented when the element needs the exact kernel
-  uint2 r_m[2][kMCap];      //   targets taking part (bit = lane; x = first slice of the pair, y = second)
+  float4 alist[64];          // ring of FAR nodes of whole-group chains (periodic: shifted to the group's image)
+  float box[8];              // centre [0..2] and inflated half widths [4..6] of the group's bounding box (read as two float4)
+  DecidingElem d[2][kMCap];  // deciding elements per pair
+  float4 a_xm[2][kACap];     // accept-all elements per pair: -x, -y, -z, -m
+  uint2 a_m[2][kACap];       //   their masks
   ChainEntry pending[kMCap + 1];
   ChainEntry stack[STACK];
-  float box[8];             // centre and inflated half widths of the group's bounding box
 };
 
 __device__ __forceinline__ double spline_wp(float r2, double hinv_d)
@@ -129,7 +142,34 @@ __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool i
   if (COUNT) n_acc += (unsigned)acc;
 }
 
-// evaluate the `cnt` elements of the list of slice pair (K, K+1); the targets that open an element are written into the
+// evaluate the `cnt` accept-all elements of slice pair (K, K+1): the bare pair kernel under the mask
+template <int K, bool COUNT, class MaskedSmem>
+__device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt, unsigned lanebit, const float (&px)[4], const float (&py)[4],
+                                                   const float (&pz)[4], double (&accd)[4], unsigned &n_acc)
+{
+  constexpr int R = K / 2;
+  float acca = 0.f, accb = 0.f;
+  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+#pragma unroll 2
+  for (int i = 0; i < cnt; i++)
+  {
+    const float4 n = sm.a_xm[R][i];
+    const uint2 m = sm.a_m[R][i];
+    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+    const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
+    if (ina) acca = fmaf(n.w, ra, acca);
+    if (inb) accb = fmaf(n.w, rb, accb);
+    if (COUNT) n_acc += (unsigned)ina + (unsigned)inb;
+  }
+  accd[K] += (double)acca;
+  accd[K + 1] += (double)accb;
+}
+
+// evaluate the `cnt` deciding elements of slice pair (K, K+1); the targets that open an element are written into the
 // pending chain of the node's children
 template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
 __device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, unsigned lanebit, const float (&px)[4], const float (&py)[4],
@@ -141,13 +181,12 @@ __device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, u
   const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
   for (int i = 0; i < cnt; i++)
   {
-    const float4 n = sm.r_xm[R][i];
-    const int2 aux = sm.r_aux[R][i];
-    const uint2 m = sm.r_m[R][i];
-    const float lenq = __int_as_float(aux.x);
-    const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
+    const DecidingElem &e = sm.d[R][i];
+    const float4 n = e.nxm;
+    const float lenq = e.lenq;
+    int slot = e.slot;
+    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
     unsigned oa, ob;
-    int slot = aux.y;
     if (slot >= 0)
     { // no accepted pair can be softened, one periodic image: the bare pair kernel + the criterion
       const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
@@ -216,7 +255,8 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
 
   int ncs = 0;        // chains on the stack
   int na = 0, ab = 0; // dense ring: pending, base
-  int nm0 = 0, nm1 = 0, np = 0; // masked elements of slices 0,1 / 2,3; pending chains
+  int nd0 = 0, nd1 = 0, np = 0; // deciding elements of slices 0,1 / 2,3; pending chains
+  int na0 = 0, na1 = 0;         // accept-all elements of slices 0,1 / 2,3
   if (node_end > node_begin)
   {
     if (lane == 0)
@@ -258,7 +298,7 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     HBT_MASKED_TRACK(ncs);
     const bool act = cur < pend;
     const bool anyact = __any_sync(kFull, act);
-    if (!anyact && ncs == 0 && np == 0 && nm0 == 0 && nm1 == 0) break;
+    if (!anyact && ncs == 0 && np == 0 && nd0 == 0 && nd1 == 0 && na0 == 0 && na1 == 0) break;
     int cls = 0; // 1 FAR, 2 NEAR, 3 OPEN, 4 MIXED
     float4 xm = make_float4(0.f, 0.f, 0.f, 0.f), xs = xm;
     float lenq = 0.f;
@@ -300,9 +340,12 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     if (COUNT) n_vis++;
     const bool toA = (cls == 1) && full, toO = (cls == 3), toM = act && !toA && !toO;
     const bool toP = toM && cls == 4; // the targets decide: the chain of the children waits for their answer
-    const bool toM0 = toM && (c0 | c1) != 0u, toM1 = toM && (c2 | c3) != 0u;
+    const bool toAcc = toM && cls == 1; // FAR for the whole group, partial mask: accepted by every target of the mask
+    const bool toD = toM && cls != 1;
+    const bool h0 = (c0 | c1) != 0u, h1 = (c2 | c3) != 0u;
     const unsigned mA = __ballot_sync(kFull, toA), mO = __ballot_sync(kFull, toO), mP = __ballot_sync(kFull, toP);
-    const unsigned mM0 = __ballot_sync(kFull, toM0), mM1 = __ballot_sync(kFull, toM1);
+    const unsigned mD0 = __ballot_sync(kFull, toD && h0), mD1 = __ballot_sync(kFull, toD && h1);
+    const unsigned mA0 = __ballot_sync(kFull, toAcc && h0), mA1 = __ballot_sync(kFull, toAcc && h1);
     const int cO = __popc(mO);
     if (ncs + cO > kMStack) return false; // stack exhausted (pathologically deep tree): the caller redoes the group per lane
     if (toA) sm.alist[(ab + na + __popc(mA & lt)) & 63] = xs;
@@ -313,7 +356,7 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       c.pend = kend;
       c.m[0] = c0; c.m[1] = c1; c.m[2] = c2; c.m[3] = c3;
     }
-    int slot = kMCap; // scratch entry: elements everybody accepts have no children chain
+    int slot = kMCap; // scratch entry: particles have no children chain
     if (toP)
     {
       slot = np + __popc(mP & lt);
@@ -322,32 +365,47 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       c.pend = kend;
       c.m[0] = 0u; c.m[1] = 0u; c.m[2] = 0u; c.m[3] = 0u; // filled in by the evaluation of the element
     }
-    if (toM)
+    if (toAcc)
+    {
+      const float4 np4 = make_float4(-xs.x, -xs.y, -xs.z, -xs.w);
+      if (h0)
+      {
+        const int idx = na0 + __popc(mA0 & lt);
+        sm.a_xm[0][idx] = np4;
+        sm.a_m[0][idx] = make_uint2(c0, c1);
+      }
+      if (h1)
+      {
+        const int idx = na1 + __popc(mA1 & lt);
+        sm.a_xm[1][idx] = np4;
+        sm.a_m[1][idx] = make_uint2(c2, c3);
+      }
+    }
+    if (toD)
     {
       const float4 p = bare ? xs : xm;
-      const float4 np4 = make_float4(-p.x, -p.y, -p.z, -p.w);
-      // FAR for the whole group: accepted by every target of the mask
-      const int2 aux = make_int2(__float_as_int((cls == 1) ? 0.f : lenq), bare ? slot : ~slot);
-      if (toM0)
+      DecidingElem e;
+      e.nxm = make_float4(-p.x, -p.y, -p.z, -p.w);
+      e.lenq = lenq;
+      e.slot = bare ? slot : ~slot;
+      if (h0)
       {
-        const int idx = nm0 + __popc(mM0 & lt);
-        sm.r_xm[0][idx] = np4;
-        sm.r_aux[0][idx] = aux;
-        sm.r_m[0][idx] = make_uint2(c0, c1);
+        e.ma = c0; e.mb = c1;
+        sm.d[0][nd0 + __popc(mD0 & lt)] = e;
       }
-      if (toM1)
+      if (h1)
       {
-        const int idx = nm1 + __popc(mM1 & lt);
-        sm.r_xm[1][idx] = np4;
-        sm.r_aux[1][idx] = aux;
-        sm.r_m[1][idx] = make_uint2(c2, c3);
+        e.ma = c2; e.mb = c3;
+        sm.d[1][nd1 + __popc(mD1 & lt)] = e;
       }
     }
     na += __popc(mA);
     ncs += cO;
     np += __popc(mP);
-    nm0 += __popc(mM0);
-    nm1 += __popc(mM1);
+    nd0 += __popc(mD0);
+    nd1 += __popc(mD1);
+    na0 += __popc(mA0);
+    na1 += __popc(mA1);
     if (act) cur = kend;
     __syncwarp();
     if (na >= 32)
@@ -357,12 +415,23 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       ab = (ab + 32) & 63;
       na -= 32;
     }
-    if (nm0 > kMPend || nm1 > kMPend || np > kMPend || (!anyact && ncs == 0) || (mI == kFull && ncs < 32))
-    { // DRAIN: evaluate both lists, then move the pending chains somebody opened onto the stack
-      if (nm0 > 0) masked_eval<0, PERIODIC, COUNT, MaskedSmem>(sm, nm0, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
-      if (nm1 > 0) masked_eval<2, PERIODIC, COUNT, MaskedSmem>(sm, nm1, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
-      nm0 = 0;
-      nm1 = 0;
+    const bool idle_all = !anyact && ncs == 0; // nothing walking, nothing on the stack: flush everything
+    if (na0 > kAPend || (idle_all && na0 > 0))
+    {
+      masked_eval_accept<0, COUNT, MaskedSmem>(sm, na0, lanebit, px, py, pz, accd, n_acc);
+      na0 = 0;
+    }
+    if (na1 > kAPend || (idle_all && na1 > 0))
+    {
+      masked_eval_accept<2, COUNT, MaskedSmem>(sm, na1, lanebit, px, py, pz, accd, n_acc);
+      na1 = 0;
+    }
+    if (nd0 > kMPend || nd1 > kMPend || np > kMPend || idle_all || (mI == kFull && ncs < 32))
+    { // DRAIN: evaluate both deciding lists, then move the pending chains somebody opened onto the stack
+      if (nd0 > 0) masked_eval<0, PERIODIC, COUNT, MaskedSmem>(sm, nd0, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      if (nd1 > 0) masked_eval<2, PERIODIC, COUNT, MaskedSmem>(sm, nd1, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      nd0 = 0;
+      nd1 = 0;
       __syncwarp();
       for (int b = 0; b < np; b += 32)
       {
@@ -378,8 +447,8 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
         ncs += cL;
       }
       np = 0;
-      __syncwarp();
     }
+    __syncwarp();
   }
   if (na > 0)
   {

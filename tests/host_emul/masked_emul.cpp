@@ -12,7 +12,7 @@ static int64_t g_hist[8];
 #include "walk_masked.cuh"
 
 #ifndef EMUL_STACK
-#define EMUL_STACK 144
+#define EMUL_STACK 184
 #endif
 typedef hbt::MaskedSmemT<EMUL_STACK> SmemT;
 
