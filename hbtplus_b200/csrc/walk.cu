@@ -265,7 +265,7 @@ struct WalkPolicy
     big2 = env("HBTU_WALK_BIG2", 1 << 19);
     group_min = env("HBTU_WALK_GROUP_MIN", 1 << 13); // segments with at least this many targets use the group walk (0 = never)
     group_t = env("HBTU_WALK_GROUP_T", 4) == 8 ? 8 : 4;
-    masked = env("HBTU_WALK_MASKED", 0); // 1: 128-target groups use the masked group walk (walk_masked.cu) instead of walk_group.cu
+    masked = env("HBTU_WALK_MASKED", 1); // 128-target groups: masked group walk (walk_masked.cu); 0 = walk_group.cu (measured: profiles/r01_walk_notes.md)
   }
 };
 const WalkPolicy &policy()
