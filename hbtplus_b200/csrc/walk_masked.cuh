@@ -89,10 +89,12 @@ __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring,
                                                 const float (&pz)[4], double (&accd)[4])
 {
   float2 accf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float4 nxt = ring[base & 63];
 #pragma unroll 2
   for (int i = 0; i < cnt; i++)
   {
-    const float4 nd = ring[(base + i) & 63];
+    const float4 nd = nxt;
+    nxt = ring[(base + i + 1) & 63]; // software pipelining: the next node is in flight while this one is evaluated
     const float2 nx = make_float2(-nd.x, -nd.x), ny = make_float2(-nd.y, -nd.y), nz = make_float2(-nd.z, -nd.z), nw = make_float2(-nd.w, -nd.w);
 #pragma unroll
     for (int k = 0; k < 4; k += 2)
@@ -150,11 +152,16 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
   constexpr int R = K / 2;
   float acca = 0.f, accb = 0.f;
   const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+  float4 nn = sm.a_xm[R][0];
+  uint2 mn = sm.a_m[R][0];
 #pragma unroll 2
   for (int i = 0; i < cnt; i++)
   {
-    const float4 n = sm.a_xm[R][i];
-    const uint2 m = sm.a_m[R][i];
+    const float4 n = nn;
+    const uint2 m = mn;
+    const int j = min(i + 1, kACap - 1); // software pipelining: the next element is in flight while this one is evaluated
+    nn = sm.a_xm[R][j];
+    mn = sm.a_m[R][j];
     const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
     const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
     const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
@@ -179,35 +186,50 @@ __device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, u
   constexpr int R = K / 2;
   float acca = 0.f, accb = 0.f;
   const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+  // pass 1, branch-free: the bare pair kernel + the criterion.  Elements that need the exact kernel take no part (their
+  // targets are masked out and their answer goes to the scratch chain); they are redone in pass 2.
+  int any_exact = 0;
+  float4 nn = sm.d[R][0].nxm;
+  float4 an = *reinterpret_cast<const float4 *>(&sm.d[R][0].lenq);
+#pragma unroll 2
   for (int i = 0; i < cnt; i++)
   {
-    const DecidingElem &e = sm.d[R][i];
-    const float4 n = e.nxm;
-    const float lenq = e.lenq;
-    int slot = e.slot;
-    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
-    unsigned oa, ob;
-    if (slot >= 0)
-    { // no accepted pair can be softened, one periodic image: the bare pair kernel + the criterion
-      const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
-      const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
-      const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
-      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-      const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
-      const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
-      if (ina && !opena) acca = fmaf(n.w, ra, acca);
-      if (inb && !openb) accb = fmaf(n.w, rb, accb);
-      oa = __ballot_sync(kFull, ina && opena);
-      ob = __ballot_sync(kFull, inb && openb);
-      if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
-    }
-    else
+    const float4 n = nn;
+    const float lenq = an.x;
+    const int slot = __float_as_int(an.y);
+    const unsigned ma = (unsigned)__float_as_int(an.z), mb = (unsigned)__float_as_int(an.w);
+    const int j = min(i + 1, kMCap - 1); // software pipelining: the next element is in flight while this one is evaluated
+    nn = sm.d[R][j].nxm;
+    an = *reinterpret_cast<const float4 *>(&sm.d[R][j].lenq);
+    const bool fast = slot >= 0;
+    any_exact |= slot;
+    const bool ina = fast && (ma & lanebit) != 0u, inb = fast && (mb & lanebit) != 0u;
+    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+    const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
+    if (ina && !opena) acca = fmaf(n.w, ra, acca);
+    if (inb && !openb) accb = fmaf(n.w, rb, accb);
+    const unsigned oa = __ballot_sync(kFull, ina && opena);
+    const unsigned ob = __ballot_sync(kFull, inb && openb);
+    if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
+    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[fast ? slot : kMCap].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
+  }
+  if (any_exact < 0)
+  { // pass 2: the reference's full kernel per target where a softened pair or a second periodic image was not excluded
+    for (int i = 0; i < cnt; i++)
     {
-      slot = ~slot;
-      masked_exact<PERIODIC, COUNT>(n, lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
-      masked_exact<PERIODIC, COUNT>(n, lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
+      const DecidingElem &e = sm.d[R][i];
+      if (e.slot >= 0) continue;
+      const float4 n = e.nxm;
+      const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
+      unsigned oa, ob;
+      masked_exact<PERIODIC, COUNT>(n, e.lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
+      masked_exact<PERIODIC, COUNT>(n, e.lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
+      if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[~e.slot].m[K]) = make_uint2(oa, ob);
     }
-    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[slot].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
   }
   accd[K] += (double)acca;
   accd[K + 1] += (double)accb;

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== smoke masked"; HBTU_WALK_MASKED=1 HBTU_WALK_GROUP_MIN=1 timeout 240 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== parity masked (all segments)"; HBTU_WALK_MASKED=1 HBTU_WALK_GROUP_MIN=1 timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -6
-for b in 5 4 6; do
+for b in 5 4; do
   echo "== bench masked blocks=$b"; HBTU_WALK_MASKED=1 HBTU_WALK_MASKED_BLOCKS=$b timeout 200 python bench.py --profile --steps 2 --warmup 1 2>&1 | tail -1 | python -c "
 import sys, json
 l = sys.stdin.read().strip()
