@@ -448,7 +448,7 @@ def main():
                     "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "api": "hbtu_unbind_batch from pinned host buffers"},
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "fp32_issue", "achieved": inter_rate * FLOP_PER_INTERACTION / 1e12, "peak": peak_inter * FLOP_PER_INTERACTION / 1e12,
-                         "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "kernel": "walk_group_kernel (segments >= 8192 targets) + walk_kernel",
+                         "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "kernel": "walk_masked_kernel (segments >= 8192 targets) + walk_kernel",
                          "interactions_per_s": inter_rate, "peak_interactions_per_s": peak_inter,
                          "peak_source": f"{nsm} SM x 128 fp32 lanes x sm_max_mhz ({peak_src}) / 8 issue slots per interaction (SURVEY.md 8(d)); 12 flop per interaction",
                          "note": "tensor cores deliberately unused (not a dense contraction); kernel share of the step = walk/total in config.phase_ms"},

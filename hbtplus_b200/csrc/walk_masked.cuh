@@ -30,6 +30,12 @@
 #ifndef HBT_MASKED_ROOM_PER_LANE
 #define HBT_MASKED_ROOM_PER_LANE 3 // free stack entries demanded per walking lane (a chain pushes <= 8, typically 2)
 #endif
+#ifndef HBT_M_PREFETCH
+#define HBT_M_PREFETCH 0 // explicit software pipelining of the dense / accept-all list loops (measured: profiles/r01_walk_notes.md)
+#endif
+#ifndef HBT_M_TWOPASS
+#define HBT_M_TWOPASS 0 // deciding lists: branch-free pass + separate exact pass instead of one pass with a branch
+#endif
 #ifndef HBT_MASKED_TRACK
 #define HBT_MASKED_TRACK(ncs) // test hook of the CPU emulation (stack high-water mark)
 #endif
@@ -84,6 +90,7 @@ __device__ __forceinline__ double spline_wp(float r2, double hinv_d)
   return -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
 }
 
+#if HBT_M_PREFETCH
 // dense evaluation of `cnt` FAR nodes for all 128 targets: 7 packed + 2 MUFU.RSQ per two interactions
 __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring, int base, int cnt, const float (&px)[4], const float (&py)[4],
                                                 const float (&pz)[4], double (&accd)[4])
@@ -112,6 +119,34 @@ __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring,
   accd[3] += (double)accf[1].y;
 }
 
+#else
+// dense evaluation of `cnt` FAR nodes for all 128 targets: 7 packed + 2 MUFU.RSQ per two interactions
+__device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring, int base, int cnt, const float (&px)[4], const float (&py)[4],
+                                                const float (&pz)[4], double (&accd)[4])
+{
+  float2 accf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 2
+  for (int i = 0; i < cnt; i++)
+  {
+    const float4 nd = ring[(base + i) & 63];
+    const float2 nx = make_float2(-nd.x, -nd.x), ny = make_float2(-nd.y, -nd.y), nz = make_float2(-nd.z, -nd.z), nw = make_float2(-nd.w, -nd.w);
+#pragma unroll
+    for (int k = 0; k < 4; k += 2)
+    {
+      const float2 dx = f2_add(make_float2(px[k], px[k + 1]), nx);
+      const float2 dy = f2_add(make_float2(py[k], py[k + 1]), ny);
+      const float2 dz = f2_add(make_float2(pz[k], pz[k + 1]), nz);
+      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      accf[k / 2] = f2_fma(nw, make_float2(rsqrt_raw(r2.x), rsqrt_raw(r2.y)), accf[k / 2]);
+    }
+  }
+  accd[0] += (double)accf[0].x;
+  accd[1] += (double)accf[0].y;
+  accd[2] += (double)accf[1].x;
+  accd[3] += (double)accf[1].y;
+}
+
+#endif
 // one slice of an element that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161)
 template <bool PERIODIC, bool COUNT>
 __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool in, float pxk, float pyk, float pzk, float &accf, double &accd,
@@ -144,6 +179,7 @@ __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool i
   if (COUNT) n_acc += (unsigned)acc;
 }
 
+#if HBT_M_PREFETCH
 // evaluate the `cnt` accept-all elements of slice pair (K, K+1): the bare pair kernel under the mask
 template <int K, bool COUNT, class MaskedSmem>
 __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt, unsigned lanebit, const float (&px)[4], const float (&py)[4],
@@ -176,6 +212,36 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
   accd[K + 1] += (double)accb;
 }
 
+#else
+// evaluate the `cnt` accept-all elements of slice pair (K, K+1): the bare pair kernel under the mask
+template <int K, bool COUNT, class MaskedSmem>
+__device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt, unsigned lanebit, const float (&px)[4], const float (&py)[4],
+                                                   const float (&pz)[4], double (&accd)[4], unsigned &n_acc)
+{
+  constexpr int R = K / 2;
+  float acca = 0.f, accb = 0.f;
+  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+#pragma unroll 2
+  for (int i = 0; i < cnt; i++)
+  {
+    const float4 n = sm.a_xm[R][i];
+    const uint2 m = sm.a_m[R][i];
+    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+    const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
+    if (ina) acca = fmaf(n.w, ra, acca);
+    if (inb) accb = fmaf(n.w, rb, accb);
+    if (COUNT) n_acc += (unsigned)ina + (unsigned)inb;
+  }
+  accd[K] += (double)acca;
+  accd[K + 1] += (double)accb;
+}
+
+#endif
+#if HBT_M_TWOPASS
 // evaluate the `cnt` deciding elements of slice pair (K, K+1); the targets that open an element are written into the
 // pending chain of the node's children
 template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
@@ -235,6 +301,52 @@ __device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, u
   accd[K + 1] += (double)accb;
 }
 
+#else
+// evaluate the `cnt` deciding elements of slice pair (K, K+1); the targets that open an element are written into the
+// pending chain of the node's children
+template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
+__device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, unsigned lanebit, const float (&px)[4], const float (&py)[4],
+                                            const float (&pz)[4], double (&accd)[4], float box_size, float box_half, float h2, float softening,
+                                            unsigned &n_acc)
+{
+  constexpr int R = K / 2;
+  float acca = 0.f, accb = 0.f;
+  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+  for (int i = 0; i < cnt; i++)
+  {
+    const DecidingElem &e = sm.d[R][i];
+    const float4 n = e.nxm;
+    const float lenq = e.lenq;
+    int slot = e.slot;
+    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
+    unsigned oa, ob;
+    if (slot >= 0)
+    { // no accepted pair can be softened, one periodic image: the bare pair kernel + the criterion
+      const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+      const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+      const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+      const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+      const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
+      if (ina && !opena) acca = fmaf(n.w, ra, acca);
+      if (inb && !openb) accb = fmaf(n.w, rb, accb);
+      oa = __ballot_sync(kFull, ina && opena);
+      ob = __ballot_sync(kFull, inb && openb);
+      if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
+    }
+    else
+    {
+      slot = ~slot;
+      masked_exact<PERIODIC, COUNT>(n, lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
+      masked_exact<PERIODIC, COUNT>(n, lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
+    }
+    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[slot].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
+  }
+  accd[K] += (double)acca;
+  accd[K + 1] += (double)accb;
+}
+
+#endif
 // The walk of one group: targets px/py/pz (4 per lane: slice k = targets 32k .. 32k+31 of the group; periodic: already
 // un-wrapped towards one common image; invalid slots repeat a valid position) over the pre-order nodes
 // [node_begin, node_end).  accd[k] receives sum(-m/r) (softened pairs: the spline term) of target (lane, k).
