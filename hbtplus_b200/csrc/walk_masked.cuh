@@ -30,12 +30,17 @@
 #ifndef HBT_MASKED_ROOM_PER_LANE
 #define HBT_MASKED_ROOM_PER_LANE 3 // free stack entries demanded per walking lane (a chain pushes <= 8, typically 2)
 #endif
-#ifndef HBT_M_PREFETCH
-#define HBT_M_PREFETCH 0 // explicit software pipelining of the dense / accept-all list loops (measured: profiles/r01_walk_notes.md)
+#ifndef HBT_M_SPLITX
+#define HBT_M_SPLITX 1 // deciding lists: exact elements queued from the far end of the list and evaluated in their own loop (0: one loop with a branch; measured 1093 -> 1045 ms)
 #endif
-#ifndef HBT_M_TWOPASS
-#define HBT_M_TWOPASS 0 // deciding lists: branch-free pass + separate exact pass instead of one pass with a branch
+#ifndef HBT_M_UNROLL
+#define HBT_M_UNROLL 4 // unroll factor of the dense / accept-all list loops (2 -> 4: 1045 -> 992 ms with SPLITX)
 #endif
+#ifndef HBT_M_UNROLL_D
+#define HBT_M_UNROLL_D 2 // unroll factor of the branch-free deciding loop
+#endif
+#define HBT_M_PRAGMA_(x) _Pragma(#x)
+#define HBT_M_PRAGMA_UNROLL(n) HBT_M_PRAGMA_(unroll n)
 #ifndef HBT_MASKED_TRACK
 #define HBT_MASKED_TRACK(ncs) // test hook of the CPU emulation (stack high-water mark)
 #endif
@@ -90,42 +95,12 @@ __device__ __forceinline__ double spline_wp(float r2, double hinv_d)
   return -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
 }
 
-#if HBT_M_PREFETCH
 // dense evaluation of `cnt` FAR nodes for all 128 targets: 7 packed + 2 MUFU.RSQ per two interactions
 __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring, int base, int cnt, const float (&px)[4], const float (&py)[4],
                                                 const float (&pz)[4], double (&accd)[4])
 {
   float2 accf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-  float4 nxt = ring[base & 63];
-#pragma unroll 2
-  for (int i = 0; i < cnt; i++)
-  {
-    const float4 nd = nxt;
-    nxt = ring[(base + i + 1) & 63]; // software pipelining: the next node is in flight while this one is evaluated
-    const float2 nx = make_float2(-nd.x, -nd.x), ny = make_float2(-nd.y, -nd.y), nz = make_float2(-nd.z, -nd.z), nw = make_float2(-nd.w, -nd.w);
-#pragma unroll
-    for (int k = 0; k < 4; k += 2)
-    {
-      const float2 dx = f2_add(make_float2(px[k], px[k + 1]), nx);
-      const float2 dy = f2_add(make_float2(py[k], py[k + 1]), ny);
-      const float2 dz = f2_add(make_float2(pz[k], pz[k + 1]), nz);
-      const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-      accf[k / 2] = f2_fma(nw, make_float2(rsqrt_raw(r2.x), rsqrt_raw(r2.y)), accf[k / 2]);
-    }
-  }
-  accd[0] += (double)accf[0].x;
-  accd[1] += (double)accf[0].y;
-  accd[2] += (double)accf[1].x;
-  accd[3] += (double)accf[1].y;
-}
-
-#else
-// dense evaluation of `cnt` FAR nodes for all 128 targets: 7 packed + 2 MUFU.RSQ per two interactions
-__device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring, int base, int cnt, const float (&px)[4], const float (&py)[4],
-                                                const float (&pz)[4], double (&accd)[4])
-{
-  float2 accf[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll 2
+  HBT_M_PRAGMA_UNROLL(HBT_M_UNROLL)
   for (int i = 0; i < cnt; i++)
   {
     const float4 nd = ring[(base + i) & 63];
@@ -146,7 +121,6 @@ __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring,
   accd[3] += (double)accf[1].y;
 }
 
-#endif
 // one slice of an element that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161)
 template <bool PERIODIC, bool COUNT>
 __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool in, float pxk, float pyk, float pzk, float &accf, double &accd,
@@ -179,7 +153,6 @@ __device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool i
   if (COUNT) n_acc += (unsigned)acc;
 }
 
-#if HBT_M_PREFETCH
 // evaluate the `cnt` accept-all elements of slice pair (K, K+1): the bare pair kernel under the mask
 template <int K, bool COUNT, class MaskedSmem>
 __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt, unsigned lanebit, const float (&px)[4], const float (&py)[4],
@@ -188,40 +161,7 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
   constexpr int R = K / 2;
   float acca = 0.f, accb = 0.f;
   const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
-  float4 nn = sm.a_xm[R][0];
-  uint2 mn = sm.a_m[R][0];
-#pragma unroll 2
-  for (int i = 0; i < cnt; i++)
-  {
-    const float4 n = nn;
-    const uint2 m = mn;
-    const int j = min(i + 1, kACap - 1); // software pipelining: the next element is in flight while this one is evaluated
-    nn = sm.a_xm[R][j];
-    mn = sm.a_m[R][j];
-    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
-    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
-    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
-    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
-    const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
-    if (ina) acca = fmaf(n.w, ra, acca);
-    if (inb) accb = fmaf(n.w, rb, accb);
-    if (COUNT) n_acc += (unsigned)ina + (unsigned)inb;
-  }
-  accd[K] += (double)acca;
-  accd[K + 1] += (double)accb;
-}
-
-#else
-// evaluate the `cnt` accept-all elements of slice pair (K, K+1): the bare pair kernel under the mask
-template <int K, bool COUNT, class MaskedSmem>
-__device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt, unsigned lanebit, const float (&px)[4], const float (&py)[4],
-                                                   const float (&pz)[4], double (&accd)[4], unsigned &n_acc)
-{
-  constexpr int R = K / 2;
-  float acca = 0.f, accb = 0.f;
-  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
-#pragma unroll 2
+  HBT_M_PRAGMA_UNROLL(HBT_M_UNROLL)
   for (int i = 0; i < cnt; i++)
   {
     const float4 n = sm.a_xm[R][i];
@@ -240,68 +180,6 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
   accd[K + 1] += (double)accb;
 }
 
-#endif
-#if HBT_M_TWOPASS
-// evaluate the `cnt` deciding elements of slice pair (K, K+1); the targets that open an element are written into the
-// pending chain of the node's children
-template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
-__device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, unsigned lanebit, const float (&px)[4], const float (&py)[4],
-                                            const float (&pz)[4], double (&accd)[4], float box_size, float box_half, float h2, float softening,
-                                            unsigned &n_acc)
-{
-  constexpr int R = K / 2;
-  float acca = 0.f, accb = 0.f;
-  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
-  // pass 1, branch-free: the bare pair kernel + the criterion.  Elements that need the exact kernel take no part (their
-  // targets are masked out and their answer goes to the scratch chain); they are redone in pass 2.
-  int any_exact = 0;
-  float4 nn = sm.d[R][0].nxm;
-  float4 an = *reinterpret_cast<const float4 *>(&sm.d[R][0].lenq);
-#pragma unroll 2
-  for (int i = 0; i < cnt; i++)
-  {
-    const float4 n = nn;
-    const float lenq = an.x;
-    const int slot = __float_as_int(an.y);
-    const unsigned ma = (unsigned)__float_as_int(an.z), mb = (unsigned)__float_as_int(an.w);
-    const int j = min(i + 1, kMCap - 1); // software pipelining: the next element is in flight while this one is evaluated
-    nn = sm.d[R][j].nxm;
-    an = *reinterpret_cast<const float4 *>(&sm.d[R][j].lenq);
-    const bool fast = slot >= 0;
-    any_exact |= slot;
-    const bool ina = fast && (ma & lanebit) != 0u, inb = fast && (mb & lanebit) != 0u;
-    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
-    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
-    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
-    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
-    const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
-    if (ina && !opena) acca = fmaf(n.w, ra, acca);
-    if (inb && !openb) accb = fmaf(n.w, rb, accb);
-    const unsigned oa = __ballot_sync(kFull, ina && opena);
-    const unsigned ob = __ballot_sync(kFull, inb && openb);
-    if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
-    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[fast ? slot : kMCap].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
-  }
-  if (any_exact < 0)
-  { // pass 2: the reference's full kernel per target where a softened pair or a second periodic image was not excluded
-    for (int i = 0; i < cnt; i++)
-    {
-      const DecidingElem &e = sm.d[R][i];
-      if (e.slot >= 0) continue;
-      const float4 n = e.nxm;
-      const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
-      unsigned oa, ob;
-      masked_exact<PERIODIC, COUNT>(n, e.lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
-      masked_exact<PERIODIC, COUNT>(n, e.lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
-      if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[~e.slot].m[K]) = make_uint2(oa, ob);
-    }
-  }
-  accd[K] += (double)acca;
-  accd[K + 1] += (double)accb;
-}
-
-#else
 // evaluate the `cnt` deciding elements of slice pair (K, K+1); the targets that open an element are written into the
 // pending chain of the node's children
 template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
@@ -346,7 +224,52 @@ __device__ __forceinline__ void masked_eval(MaskedSmem &sm, int cnt, int lane, u
   accd[K + 1] += (double)accb;
 }
 
+#if HBT_M_SPLITX
+// split layout of a deciding list: elements [0, cnt) take the bare pair kernel + the criterion in a branch-free loop, the
+// elements that need the exact kernel were queued from the far end, [kMCap - cntx, kMCap)
+template <int K, bool PERIODIC, bool COUNT, class MaskedSmem>
+__device__ __forceinline__ void masked_eval_split(MaskedSmem &sm, int cnt, int cntx, int lane, unsigned lanebit, const float (&px)[4],
+                                                  const float (&py)[4], const float (&pz)[4], double (&accd)[4], float box_size, float box_half,
+                                                  float h2, float softening, unsigned &n_acc)
+{
+  constexpr int R = K / 2;
+  float acca = 0.f, accb = 0.f;
+  const float2 pxx = make_float2(px[K], px[K + 1]), pyy = make_float2(py[K], py[K + 1]), pzz = make_float2(pz[K], pz[K + 1]);
+  HBT_M_PRAGMA_UNROLL(HBT_M_UNROLL_D)
+  for (int i = 0; i < cnt; i++)
+  {
+    const DecidingElem &e = sm.d[R][i];
+    const float4 n = e.nxm;
+    const float lenq = e.lenq;
+    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
+    const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
+    const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
+    const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
+    const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
+    const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
+    if (ina && !opena) acca = fmaf(n.w, ra, acca);
+    if (inb && !openb) accb = fmaf(n.w, rb, accb);
+    const unsigned oa = __ballot_sync(kFull, ina && opena);
+    const unsigned ob = __ballot_sync(kFull, inb && openb);
+    if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
+    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[e.slot].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
+  }
+  for (int i = kMCap - cntx; i < kMCap; i++)
+  {
+    const DecidingElem &e = sm.d[R][i];
+    const float4 n = e.nxm;
+    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
+    unsigned oa, ob;
+    masked_exact<PERIODIC, COUNT>(n, e.lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
+    masked_exact<PERIODIC, COUNT>(n, e.lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
+    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[e.slot].m[K]) = make_uint2(oa, ob);
+  }
+  accd[K] += (double)acca;
+  accd[K + 1] += (double)accb;
+}
 #endif
+
 // The walk of one group: targets px/py/pz (4 per lane: slice k = targets 32k .. 32k+31 of the group; periodic: already
 // un-wrapped towards one common image; invalid slots repeat a valid position) over the pre-order nodes
 // [node_begin, node_end).  accd[k] receives sum(-m/r) (softened pairs: the spline term) of target (lane, k).
@@ -391,6 +314,11 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
   int na = 0, ab = 0; // dense ring: pending, base
   int nd0 = 0, nd1 = 0, np = 0; // deciding elements of slices 0,1 / 2,3; pending chains
   int na0 = 0, na1 = 0;         // accept-all elements of slices 0,1 / 2,3
+#if HBT_M_SPLITX
+  int nx0 = 0, nx1 = 0;         // deciding elements that need the exact kernel (queued from the far end of the lists)
+#else
+  constexpr int nx0 = 0, nx1 = 0;
+#endif
   if (node_end > node_begin)
   {
     if (lane == 0)
@@ -432,7 +360,7 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     HBT_MASKED_TRACK(ncs);
     const bool act = cur < pend;
     const bool anyact = __any_sync(kFull, act);
-    if (!anyact && ncs == 0 && np == 0 && nd0 == 0 && nd1 == 0 && na0 == 0 && na1 == 0) break;
+    if (!anyact && ncs == 0 && np == 0 && nd0 + nx0 == 0 && nd1 + nx1 == 0 && na0 == 0 && na1 == 0) break;
     int cls = 0; // 1 FAR, 2 NEAR, 3 OPEN, 4 MIXED
     float4 xm = make_float4(0.f, 0.f, 0.f, 0.f), xs = xm;
     float lenq = 0.f;
@@ -478,7 +406,12 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     const bool toD = toM && cls != 1;
     const bool h0 = (c0 | c1) != 0u, h1 = (c2 | c3) != 0u;
     const unsigned mA = __ballot_sync(kFull, toA), mO = __ballot_sync(kFull, toO), mP = __ballot_sync(kFull, toP);
+#if HBT_M_SPLITX
+    const unsigned mD0 = __ballot_sync(kFull, toD && h0 && bare), mD1 = __ballot_sync(kFull, toD && h1 && bare);
+    const unsigned mX0 = __ballot_sync(kFull, toD && h0 && !bare), mX1 = __ballot_sync(kFull, toD && h1 && !bare);
+#else
     const unsigned mD0 = __ballot_sync(kFull, toD && h0), mD1 = __ballot_sync(kFull, toD && h1);
+#endif
     const unsigned mA0 = __ballot_sync(kFull, toAcc && h0), mA1 = __ballot_sync(kFull, toAcc && h1);
     const int cO = __popc(mO);
     if (ncs + cO > kMStack) return false; // stack exhausted (pathologically deep tree): the caller redoes the group per lane
@@ -521,6 +454,22 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       DecidingElem e;
       e.nxm = make_float4(-p.x, -p.y, -p.z, -p.w);
       e.lenq = lenq;
+#if HBT_M_SPLITX
+      e.slot = slot;
+      if (h0)
+      {
+        e.ma = c0; e.mb = c1;
+        sm.d[0][bare ? nd0 + __popc(mD0 & lt) : kMCap - 1 - nx0 - __popc(mX0 & lt)] = e;
+      }
+      if (h1)
+      {
+        e.ma = c2; e.mb = c3;
+        sm.d[1][bare ? nd1 + __popc(mD1 & lt) : kMCap - 1 - nx1 - __popc(mX1 & lt)] = e;
+      }
+    }
+    nx0 += __popc(mX0);
+    nx1 += __popc(mX1);
+#else
       e.slot = bare ? slot : ~slot;
       if (h0)
       {
@@ -533,6 +482,7 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
         sm.d[1][nd1 + __popc(mD1 & lt)] = e;
       }
     }
+#endif
     na += __popc(mA);
     ncs += cO;
     np += __popc(mP);
@@ -560,10 +510,17 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       masked_eval_accept<2, COUNT, MaskedSmem>(sm, na1, lanebit, px, py, pz, accd, n_acc);
       na1 = 0;
     }
-    if (nd0 > kMPend || nd1 > kMPend || np > kMPend || idle_all || (mI == kFull && ncs < 32))
+    if (nd0 + nx0 > kMPend || nd1 + nx1 > kMPend || np > kMPend || idle_all || (mI == kFull && ncs < 32))
     { // DRAIN: evaluate both deciding lists, then move the pending chains somebody opened onto the stack
+#if HBT_M_SPLITX
+      if (nd0 + nx0 > 0) masked_eval_split<0, PERIODIC, COUNT, MaskedSmem>(sm, nd0, nx0, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      if (nd1 + nx1 > 0) masked_eval_split<2, PERIODIC, COUNT, MaskedSmem>(sm, nd1, nx1, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+      nx0 = 0;
+      nx1 = 0;
+#else
       if (nd0 > 0) masked_eval<0, PERIODIC, COUNT, MaskedSmem>(sm, nd0, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
       if (nd1 > 0) masked_eval<2, PERIODIC, COUNT, MaskedSmem>(sm, nd1, lane, lanebit, px, py, pz, accd, box_size, box_half, h2, softening, n_acc);
+#endif
       nd0 = 0;
       nd1 = 0;
       __syncwarp();

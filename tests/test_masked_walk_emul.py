@@ -18,10 +18,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module")
-def memul(tmp_path_factory):
-    out = tmp_path_factory.mktemp("memul") / "libmaskedemul.so"
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+@pytest.fixture(scope="module", params=[0, 1], ids=["onepass", "splitx"])
+def memul(request, tmp_path_factory):
+    """both layouts of the deciding lists (HBT_M_SPLITX, walk_masked.cuh)"""
+    out = tmp_path_factory.mktemp("memul") / f"libmaskedemul{request.param}.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", f"-DHBT_M_SPLITX={request.param}",
                            "-I", os.path.join(ROOT, "hbtplus_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
                            os.path.join(HERE, "host_emul", "masked_emul.cpp"), "-o", str(out)])
     return C.CDLL(str(out))
