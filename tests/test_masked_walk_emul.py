@@ -88,3 +88,17 @@ def test_masked_walk_dense_core(memul):
     assert stats[0] == 0
     assert asc.sum() > 0 and np.array_equal(per_lane(am, 200000), per_lane(asc, 200000))
     assert np.allclose(sm, ss, rtol=2e-6, atol=0)
+
+
+def test_masked_walk_clumpy_tree(memul):
+    """a host with 40 dense clumps inside it walked as ONE tree (the source of a central that received its satellites'
+    particles): strongly varying depth along the key order, groups that straddle clumps"""
+    p = capi.make_params(box_size=100.0, softening=4.8e-5, periodic=False)
+    sizes = [80000] + [1500] * 40
+    snap = synth.make_snapshot(sizes, seed=17, wrap=False, parent=[-1] + [0] * 40, box_size=100.0, particle_mass=1e-6, centre=[50.0, 50.0, 50.0])
+    pm = np.ascontiguousarray(snap.pos_mass)
+    n = len(pm)
+    sm, ss, am, asc, stats = run(memul, p, pm, n, stride=41)  # 27 groups across the key range
+    assert stats[0] == 0
+    assert asc.sum() > 0 and np.array_equal(per_lane(am, n), per_lane(asc, n))
+    assert np.allclose(sm, ss, rtol=2e-6, atol=0)
