@@ -281,6 +281,38 @@ def test_multi_target_walk_variants(tpl, tmp_path):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("masked", [1, 0])
+def test_group_walk_kernels_on_every_segment(masked):
+    """Every segment forced through the 128-target group kernels (HBTU_WALK_GROUP_MIN=1): the masked group walk
+    (walk_masked.cu, the shipped kernel for segments >= 8192 targets) and its predecessor walk_group.cu; the device-counted
+    accepted interactions must equal the oracle's, i.e. every target takes the reference's decisions."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path[:0] = [{os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}, {os.path.dirname(os.path.abspath(__file__))!r}]\n"
+        "import cases\nfrom hbtplus_b200.unbind import UnbindContext\nfrom oracle import pyoracle as po\n"
+        "orc = po.load_oracle()\n"
+        "for name in ('flat', 'nested', 'periodic_straddle', 'massvar'):\n"
+        "    p, e, snap = cases.CASES[name]()\n"
+        "    ctx = UnbindContext(p)\n"
+        "    g = ctx.unbind_batch(e, snap)\n"
+        "    w = po.run_batch(orc, 'hbto', p, e, snap)\n"
+        "    assert np.array_equal(g.io['nbound'], w.io['nbound']), (name, g.io['nbound'], w.io['nbound'])\n"
+        "    s = int(np.argmax(np.diff(snap.part_offset)))\n"
+        "    pm = np.ascontiguousarray(snap.pos_mass[snap.part_offset[s]:snap.part_offset[s + 1]])\n"
+        "    ctx.set_counting(True)\n"
+        "    a = ctx.tree_potential(e, pm, pm, self_mass=pm[:, 3].copy())\n"
+        "    st = ctx.stats()\n"
+        "    b = po.tree_potential(orc, 'hbto', p, e, pm, pm, self_mass=pm[:, 3].copy())\n"
+        "    assert (np.abs(a - b) / np.abs(b)).max() < 1e-4, name\n"
+        "    assert abs(st.pair_interactions - orc.hbto_last_interactions()) <= 1e-5 * st.pair_interactions + 2, name\n"
+        "    assert st.walk_fallbacks == 0, name\n"
+        "print('OK')\n"
+    )
+    env = dict(os.environ, HBTU_WALK_GROUP_MIN="1", HBTU_WALK_MASKED=str(masked))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("M,refine", [(1000, True), (200, False)])
 @pytest.mark.parametrize("periodic", [False, True])
 def test_sampled_mode_vs_oracle(make_ctx, oracle_lib, M, refine, periodic):
