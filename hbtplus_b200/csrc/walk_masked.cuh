@@ -41,6 +41,9 @@
 #endif
 #define HBT_M_PRAGMA_(x) _Pragma(#x)
 #define HBT_M_PRAGMA_UNROLL(n) HBT_M_PRAGMA_(unroll n)
+#ifndef HBT_MASKED_STAT
+#define HBT_MASKED_STAT(what, n) // test hook of the CPU emulation (element counts)
+#endif
 #ifndef HBT_MASKED_TRACK
 #define HBT_MASKED_TRACK(ncs) // test hook of the CPU emulation (stack high-water mark)
 #endif
@@ -483,6 +486,7 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       }
     }
 #endif
+    HBT_MASKED_STAT(0, __popc(mA)); HBT_MASKED_STAT(1, __popc(mA0) + __popc(mA1)); HBT_MASKED_STAT(2, __popc(mD0) + __popc(mD1)); HBT_MASKED_STAT(3, __popc(mP)); HBT_MASKED_STAT(4, cO);
     na += __popc(mA);
     ncs += cO;
     np += __popc(mP);

@@ -8,6 +8,7 @@ using hbt::float_to_ordered;
 using hbt::ordered_to_float;
 static int g_max_ncs = 0;
 static int64_t g_hist[8];
+#define HBT_MASKED_STAT(what, n) do { if (wemu::g_cur == 0) g_hist[what] += (n); } while (0)
 #define HBT_MASKED_TRACK(ncs) do { if ((ncs) > g_max_ncs) g_max_ncs = (ncs); } while (0)
 #include "walk_masked.cuh"
 
@@ -88,7 +89,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
     for (int q = 0; q < 8; q++)
       if (g.c0[q] != 0x5a5a5a5a5a5a5a5aull || g.c1[q] != 0x5a5a5a5a5a5a5a5aull) return -200;
     if (!ok_all) overflows++;
-    if (getenv("EMUL_VERBOSE")) fprintf(stderr, "group %ld: max stack %d iters %u ok %d\n", (long)g0, g_max_ncs, vis_lane0, (int)ok_all);
+    if (getenv("EMUL_VERBOSE2")) fprintf(stderr, "group %ld: max stack %d iters %u ok %d\n", (long)g0, g_max_ncs, vis_lane0, (int)ok_all);
     g_max_ncs = 0;
     iters += vis_lane0;
   }
@@ -116,6 +117,8 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
     sum_scalar[t] = pot;
     acc_scalar[t] = acc;
   }
+  if (getenv("EMUL_VERBOSE")) fprintf(stderr, "per group: dense-ring nodes %.0f accept-all elements %.0f deciding elements (bare) %.0f pending chains %.0f open cells %.0f\n", (double)g_hist[0] / groups, (double)g_hist[1] / groups, (double)g_hist[2] / groups, (double)g_hist[3] / groups, (double)g_hist[4] / groups);
+  for (int q = 0; q < 8; q++) g_hist[q] = 0;
   if (stats) { stats[0] = overflows; stats[1] = iters; stats[2] = (int64_t)wemu::g_ncollectives; stats[3] = groups; }
   return 0;
 }
