@@ -3,6 +3,7 @@
 // walk_masked.cuh; this file is the kernel around it: segment lookup, target load (periodic: un-wrapped towards the
 // warp's first target), the per-lane fallback when the chain stack runs out, interaction counters, energy epilogue.
 // Roofline: FP32 issue.  Tensor cores are deliberately not used.
+#include <atomic>
 #include <cstdlib>
 
 #include "walk_common.cuh"
@@ -111,13 +112,19 @@ static void launch_masked_b(const WalkArgs &a, const DevConfig &cfg, cudaStream_
 {
   const int grid = div_up(a.nwarps, kMW);
   const bool count = a.counters != nullptr;
-  static const bool carveout = [] { // MINB CTAs of ~32 KB static shared memory only fit with the largest shared-memory carve-out
+  // MINB CTAs of 32-48 KB static shared memory only fit with the largest shared-memory carve-out; the attribute is per device
+  // (one host thread and context per device when a rank shards over several GPUs)
+  static std::atomic<unsigned long long> carved{0ull};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(carved.load(std::memory_order_acquire) & bit))
+  {
     for (auto *k : {walk_masked_kernel<true, true, MINB>, walk_masked_kernel<true, false, MINB>, walk_masked_kernel<false, true, MINB>,
                     walk_masked_kernel<false, false, MINB>})
       cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return true;
-  }();
-  (void)carveout;
+    carved.fetch_or(bit, std::memory_order_release);
+  }
   if (cfg.periodic)
   {
     if (count) walk_masked_kernel<true, true, MINB><<<grid, kMW * 32, 0, stream>>>(a, cfg);
