@@ -37,6 +37,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
   const bool periodic = p->periodic_boundary_on;
   const float box = (float)p->box_size, half = (float)p->box_half;
   const int64_t ntgt = std::min<int64_t>(ntgt_in, n);
+  if (const char *e = getenv("EMUL_LANE_ORDER_SEED")) wemu::g_shuffle = strtoull(e, nullptr, 10); // random lane order between rendez-vous
   int64_t overflows = 0, iters = 0, groups = 0;
   struct Guarded { uint64_t c0[8]; SmemT sm; uint64_t c1[8]; };
   static Guarded g;

@@ -41,6 +41,7 @@ static int g_op[kLanes];
 static int g_arrived = 0;
 static uint64_t g_gen = 0;
 static uint64_t g_ncollectives = 0;
+static uint64_t g_shuffle = 0; // 0: lanes run in lane order; otherwise seed/state of the random lane order
 static std::function<void(int)> g_body;
 
 static inline void yield() { swapcontext(&g_ctx[g_cur], &g_main); }
@@ -83,12 +84,26 @@ static inline void run_warp(const std::function<void(int)> &body)
     g_ctx[l].uc_link = &g_main;
     makecontext(&g_ctx[l], trampoline, 0);
   }
+  // Between two rendez-vous the lanes run one after the other.  With g_shuffle != 0 the order is a fresh pseudo-random
+  // permutation on every pass, so that code whose result depends on the order in which lanes execute between two
+  // synchronisation points (a missing __syncwarp around a shared-memory hand-over) gives different answers.
   bool any = true;
+  int order[kLanes];
+  for (int l = 0; l < kLanes; l++) order[l] = l;
   while (any)
   {
     any = false;
-    for (int l = 0; l < kLanes; l++)
+    if (g_shuffle)
+      for (int l = kLanes - 1; l > 0; l--)
+      {
+        g_shuffle = g_shuffle * 6364136223846793005ull + 1442695040888963407ull;
+        std::swap(order[l], order[(g_shuffle >> 33) % (unsigned)(l + 1)]);
+      }
+    for (int q = 0; q < kLanes; q++)
+    {
+      const int l = order[q];
       if (!g_done[l]) { any = true; g_cur = l; swapcontext(&g_main, &g_ctx[l]); }
+    }
   }
   if (g_arrived != 0) { fprintf(stderr, "warp_emul: %d lanes left waiting at a collective\n", g_arrived); abort(); }
 }

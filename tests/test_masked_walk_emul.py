@@ -102,3 +102,19 @@ def test_masked_walk_clumpy_tree(memul):
     assert stats[0] == 0
     assert asc.sum() > 0 and np.array_equal(per_lane(am, n), per_lane(asc, n))
     assert np.allclose(sm, ss, rtol=2e-6, atol=0)
+
+
+def test_masked_walk_does_not_depend_on_lane_order(memul, monkeypatch):
+    """The emulation runs the lanes of a warp one after the other between two rendez-vous (collectives, __syncwarp).  With a
+    random lane order on every pass, a shared-memory hand-over that is not bracketed by a synchronisation would change the
+    result: sums and counts must be bit-identical to the run in lane order."""
+    p = capi.make_params(box_size=100.0, softening=4.8e-5, periodic=False)
+    snap = synth.make_snapshot([60000], seed=8, wrap=False)
+    pm = np.ascontiguousarray(snap.pos_mass)
+    monkeypatch.delenv("EMUL_LANE_ORDER_SEED", raising=False)
+    sm0, ss0, am0, asc0, st0 = run(memul, p, pm, 60000, stride=59)
+    for seed in ("12345", "987654321"):
+        monkeypatch.setenv("EMUL_LANE_ORDER_SEED", seed)
+        sm1, ss1, am1, asc1, st1 = run(memul, p, pm, 60000, stride=59)
+        assert st1[0] == 0 and np.array_equal(am0, am1) and np.array_equal(sm0, sm1)
+    monkeypatch.delenv("EMUL_LANE_ORDER_SEED", raising=False)
