@@ -104,7 +104,60 @@ def run_cpu(snap, threads: int | None = None):
     t0 = time.perf_counter()
     r = po.run_batch(lib, prefix, p, e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE, want_energy=False)
     dt = time.perf_counter() - t0
-    return dt, kind, ncpu, int(r.io["nbound"].sum())
+    return dt, kind, ncpu, int(r.io["nbound"].sum()), r
+
+
+def parity_block(ctx, e, csnap, cres, kind, pot_targets: int = 100_000):
+    """The GPU path on exactly the snapshot the CPU leg just unbound (same generator, BoxSize 100, eps 4.8e-5, m_p 1e-6, exact
+    potential), compared record by record with the reference's result: what the timed kernels compute is what the reference
+    computes.  Gates of BASELINE.json's north_star are reported, not assumed: Nbound / survival / death flags, bound mass,
+    bound-membership Jaccard, and the per-particle potential of the sample's largest subhalo against the reference's own
+    GravityTree_t::EvaluatePotential (src/gravity_tree.cpp:79-164) on `pot_targets` of its particles."""
+    from oracle import pyoracle as po
+
+    flags = capi.HBTU_FLAG_TRUNCATE_SOURCE
+    got = ctx.unbind_batch(e, csnap, flags=flags, want_energy=False)
+    nb_g, nb_w = got.io["nbound"].astype(np.int64), cres.io["nbound"].astype(np.int64)
+    live = nb_w > 1
+    mb_g, mb_w = got.io["mbound"].astype(np.float64), cres.io["mbound"].astype(np.float64)
+    dm = np.abs(mb_g[live] - mb_w[live]) / np.abs(mb_w[live])
+    jac = np.ones(csnap.nsub)
+    for s in np.nonzero(live | (nb_g > 1))[0]:
+        a, b = got.bound(s), cres.bound(s)
+        inter = len(np.intersect1d(a, b, assume_unique=True))
+        union = len(a) + len(b) - inter
+        jac[s] = inter / union if union else 1.0
+    miss = jac < 0.999
+    out = {
+        "against": kind, "sample": f"the cpu_baseline sample: {csnap.nsub} subhaloes, {csnap.npart} particles", "subhaloes": int(csnap.nsub),
+        "frac_identical_nbound": float(np.mean(nb_g == nb_w)), "max_abs_dnbound": int(np.abs(nb_g - nb_w).max()),
+        "survival_identical": bool(np.array_equal(nb_g > 1, nb_w > 1)),
+        "death_flags_identical": bool(np.array_equal(got.io["snapshot_index_of_death"], cres.io["snapshot_index_of_death"])),
+        "sink_flags_identical": bool(np.array_equal(got.io["sink_track_id"], cres.io["sink_track_id"])),
+        "nsource_identical_frac": float(np.mean(got.io["nsource"] == cres.io["nsource"])),
+        "max_rel_dmbound": float(dm.max()) if dm.size else 0.0, "frac_mbound_within_1e-3": float(np.mean(dm <= 1e-3)) if dm.size else 1.0,
+        "min_jaccard": float(jac.min()), "jaccard_miss_rate": float(np.mean(miss)), "jaccard_misses": int(miss.sum()),
+        "largest_subhalo_with_jaccard_miss": int(nb_w[miss].max()) if miss.any() else 0,
+        "gates": {"potential_rel_err": 1e-3, "mbound_rel": 1e-3, "jaccard": 0.999},
+    }
+    # per-particle potential, largest subhalo of the sample, default kernel routing
+    s = int(np.argmax(np.diff(csnap.part_offset)))
+    b, en = int(csnap.part_offset[s]), int(csnap.part_offset[s + 1])
+    src = csnap.pos_mass[b:en]
+    ctx.set_counting(True)
+    pot = ctx.tree_potential(e, src, src, self_mass=src[:, 3].copy())
+    st = ctx.stats()
+    ctx.set_counting(False)
+    pick = np.random.default_rng(7).choice(en - b, size=min(pot_targets, en - b), replace=False)
+    lib, prefix = (po.load_ref(), "hbtref") if kind == "reference" else (po.load_oracle(), "hbto")
+    want = po.tree_potential(lib, prefix, params_for(), e, src, src[pick], self_mass=src[pick, 3].copy())
+    rel = np.abs(pot[pick] - want) / np.abs(want)
+    out["potential"] = {"sources": en - b, "targets_compared": int(len(pick)), "max_rel_err": float(rel.max()), "mean_rel_err": float(rel.mean()),
+                        "frac_above_1e-3": float(np.mean(rel > 1e-3)), "interactions_per_target": st.pair_interactions / (en - b),
+                        "walk_fallbacks": int(st.walk_fallbacks)}
+    out["ok"] = bool(out["survival_identical"] and out["death_flags_identical"] and out["potential"]["max_rel_err"] <= 1e-3
+                     and out["frac_mbound_within_1e-3"] >= 0.998 and out["jaccard_miss_rate"] <= 0.002)
+    return out
 
 
 def phase_rooflines(st0, build_ms, other_ms, peaks):
@@ -317,7 +370,7 @@ def main():
         snap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
         times, kind, ncpu, nb = [], None, None, 0
         for i in range(args.warmup + args.steps):
-            dt, kind, ncpu, nb = run_cpu(snap)
+            dt, kind, ncpu, nb, _ = run_cpu(snap)
             if i >= args.warmup:
                 times.append(dt)
         dt = float(np.mean(times))
@@ -455,8 +508,9 @@ def main():
         }
         if world == 1 and not args.profile:
             csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
-            dt, kind, ncpu, _ = run_cpu(csnap)
+            dt, kind, ncpu, _, cres = run_cpu(csnap)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
+            out["parity"] = parity_block(ctx, e, csnap, cres, kind)
             out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
                                           "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks),
                                           "particle_query": bench_idtable_row(ctx, snap.npart, csnap.npart, peaks)}

@@ -21,6 +21,7 @@ HBTU_ERR_NODEVICE = -4
 HBTU_ERR_UNSUPPORTED = -5
 HBTU_ERR_CAPACITY = -6
 HBTU_FLAG_TRUNCATE_SOURCE = 1
+HBTU_SUB_PLAIN_UNBIND = 1  # hbtu_sub_io.flags: entered through plain Subhalo_t::Unbind (no orphan rule)
 HBTU_FLAG_NO_STRIPPING = 2  # the reference's -DNO_STRIPPING build
 HBTU_FLAG_THERMAL_ENERGY = 4  # -DUNBIND_WITH_THERMAL_ENERGY: vel[:, 3] is Particle_t::InternalEnergy
 
@@ -79,7 +80,7 @@ class SubIO(C.Structure):
         ("nsource_full", C.c_int64),
         ("nsource", C.c_int64),
         ("iterations", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -122,7 +123,7 @@ SUBIO_DTYPE = np.dtype(
         ("nsource_full", "<i8"),
         ("nsource", "<i8"),
         ("iterations", "<i4"),
-        ("reserved", "<i4"),
+        ("flags", "<i4"),
     ],
     align=True,
 )

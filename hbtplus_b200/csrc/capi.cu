@@ -124,6 +124,9 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
   if (N > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "more than 2^31 particles in one batch: split the batch"};
   if (N > 0 && (!pos_mass || !vel)) throw CudaError{HBTU_ERR_INVALID, "null particle arrays"};
   build_forest(c, nsub, part_offset, nest_offset, nest_list);
+  for (int64_t s = 0; s < nsub; s++)
+    if ((io[s].flags & HBTU_SUB_PLAIN_UNBIND) && (c.subs[s].parent >= 0 || !c.subs[s].children.empty()))
+      throw CudaError{HBTU_ERR_INVALID, "HBTU_SUB_PLAIN_UNBIND is only valid for a subhalo without parent and without nested subhaloes"};
   c.nsub = nsub;
   c.N = N;
   c.flags = flags;

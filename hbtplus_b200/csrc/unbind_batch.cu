@@ -720,23 +720,18 @@ static T *upload(Arena &arena, const std::vector<T> &v, cudaStream_t stream)
   return d;
 }
 
+// The job tables of the per-level set-up kernels are tiny; they live in the round arena, which is dead between rounds
+// (run_round / run_refine reset it when they start).  No cudaMalloc / cudaFree / stream synchronisation per level: the
+// copies are stream-ordered and cudaMemcpyAsync from pageable host memory returns once the source has been staged.
 static void run_seg_copy(Context &c, const std::vector<CopyJob> &jobs, const std::vector<int64_t> &job_off, const int *src, int *dst)
 {
   if (jobs.empty() || job_off.back() == 0) return;
-  // small persistent side buffers: jobs are tiny compared with the arena arrays
-  CopyJob *d_jobs = nullptr;
-  int64_t *d_off = nullptr;
-  HBT_CUDA(cudaMalloc(&d_jobs, sizeof(CopyJob) * jobs.size()));
-  HBT_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * job_off.size()));
-  HBT_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CopyJob) * jobs.size(), cudaMemcpyHostToDevice, c.stream));
-  HBT_CUDA(cudaMemcpyAsync(d_off, job_off.data(), sizeof(int64_t) * job_off.size(), cudaMemcpyHostToDevice, c.stream));
+  CopyJob *d_jobs = upload(c.arena, jobs, c.stream);
+  int64_t *d_off = upload(c.arena, job_off, c.stream);
   int64_t total = job_off.back();
   seg_copy_kernel<<<grid_for(total), kBlock, 0, c.stream>>>(d_jobs, d_off, (int)jobs.size(), total, src, dst);
   HBT_CHECK_LAUNCH();
   c.ls.launches++;
-  HBT_CUDA(cudaStreamSynchronize(c.stream));
-  cudaFree(d_jobs);
-  cudaFree(d_off);
 }
 
 // one potential evaluation for every active subhalo of the level
@@ -1129,7 +1124,10 @@ void execute_batch(Context &c)
     z.death = io.snapshot_index_of_death;
     z.sink = io.snapshot_index_of_sink;
     z.sinktrack = io.sink_track_id;
-    z.is_orphan = io.nbound <= 1;
+    // the orphan rule belongs to RecursiveUnbind (src/subhalo_unbind.cpp:434-446); a subhalo the caller enters through plain
+    // Unbind (HBTU_SUB_PLAIN_UNBIND) is unbound like any other whatever its entry Nbound
+    const bool orphan = io.nbound <= 1 && !(io.flags & HBTU_SUB_PLAIN_UNBIND);
+    z.is_orphan = orphan;
     for (int j = 0; j < 3; j++)
     {
       z.ref_pos[j] = (float)io.avg_pos[j];
@@ -1148,7 +1146,7 @@ void execute_batch(Context &c)
     h.correction = 0;
     h.done = h.disrupted = false;
     h.iterations = 0;
-    h.is_orphan = io.nbound <= 1;
+    h.is_orphan = orphan;
   }
   HBT_CUDA(cudaMemcpyAsync(c.d_subs, init.data(), sizeof(SubState) * nsub, cudaMemcpyHostToDevice, st));
   if (c.N > 0)
@@ -1163,6 +1161,7 @@ void execute_batch(Context &c)
   {
     const std::vector<int> &lv = c.levels[level];
     const int64_t M = c.cfg.max_sample;
+    c.arena.reset(); // the previous level's rounds are over: the arena holds this level's small job tables until its first round
     // 1. feed children's unbound tails into this level's sources (src/subhalo_unbind.cpp:437-443)
     {
       std::vector<CopyJob> jobs;
@@ -1217,15 +1216,23 @@ void execute_batch(Context &c)
       }
       li[i] = LevelInit{s, h.n_src, h.done ? 0 : 1, shuffled ? 1 : 0};
     }
+    { // orphans keep their list in the order it had BEFORE the sampling shuffle: RecursiveUnbind swaps the untouched
+      // extended list back in after Unbind worked on the backup (src/subhalo_unbind.cpp:436,444-446)
+      std::vector<CopyJob> snap;
+      std::vector<int64_t> snap_off{0};
+      for (int s : lv)
+        if (c.subs[s].is_orphan && c.subs[s].n_src > 0)
+        {
+          snap.push_back(CopyJob{c.subs[s].slot_base, c.subs[s].slot_base});
+          snap_off.push_back(snap_off.back() + c.subs[s].n_src);
+        }
+      run_seg_copy(c, snap, snap_off, c.d_ids, c.d_ids_orig);
+    }
     { // n_src, the entry value of Particles[0] and the active flag on the device
-      LevelInit *d_li = nullptr;
-      HBT_CUDA(cudaMalloc(&d_li, sizeof(LevelInit) * li.size()));
-      HBT_CUDA(cudaMemcpyAsync(d_li, li.data(), sizeof(LevelInit) * li.size(), cudaMemcpyHostToDevice, st));
+      LevelInit *d_li = upload(c.arena, li, st);
       level_init_kernel<<<grid_for((int64_t)li.size()), kBlock, 0, st>>>(d_li, (int)li.size(), c.d_subs, c.d_ids);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
-      HBT_CUDA(cudaStreamSynchronize(st));
-      cudaFree(d_li);
     }
     if (!shuf.empty())
     {
@@ -1253,13 +1260,13 @@ void execute_batch(Context &c)
       shuffle_write_kernel<<<grid_for(total), kBlock, 0, st>>>(d_jobs, d_off, (int)shuf.size(), total, tmp, c.d_ids);
       HBT_CHECK_LAUNCH();
       c.ls.launches += 4 + (bits + 7) / 8;
-      HBT_CUDA(cudaStreamSynchronize(st));
+      ar.reset();
     }
-    { // snapshot of the (shuffled) input order: what Particles holds when Unbind does not reorder it
+    { // snapshot of the (shuffled) input order: what Particles holds when a disrupted Unbind does not reorder it (:361-379)
       std::vector<CopyJob> snap;
       std::vector<int64_t> snap_off{0};
       for (int s : lv)
-        if (c.subs[s].n_src > 0)
+        if (!c.subs[s].is_orphan && c.subs[s].n_src > 0)
         {
           snap.push_back(CopyJob{c.subs[s].slot_base, c.subs[s].slot_base});
           snap_off.push_back(snap_off.back() + c.subs[s].n_src);
@@ -1268,14 +1275,10 @@ void execute_batch(Context &c)
     }
     if (!trivial.empty())
     {
-      int *d_list = nullptr;
-      HBT_CUDA(cudaMalloc(&d_list, sizeof(int) * trivial.size()));
-      HBT_CUDA(cudaMemcpyAsync(d_list, trivial.data(), sizeof(int) * trivial.size(), cudaMemcpyHostToDevice, st));
+      int *d_list = upload(c.arena, trivial, st);
       trivial_kernel<<<grid_for((int64_t)trivial.size()), kBlock, 0, st>>>(d_list, (int)trivial.size(), c.d_subs, c.d_ids, c.d_pos, c.cfg, c.d_E);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
-      HBT_CUDA(cudaStreamSynchronize(st));
-      cudaFree(d_list);
     }
     // 3. iterate; then re-rank the most-bound sample of converged sampled subhaloes (RefineBindingEnergyOrder)
     c.refine_list.clear();
@@ -1287,6 +1290,7 @@ void execute_batch(Context &c)
       std::vector<CopyJob> jobs;
       std::vector<int64_t> job_off{0};
       std::vector<int> job_sub;
+      c.arena.reset(); // the level's rounds are over
       for (int s : lv)
       {
         SubHost &h = c.subs[s];
@@ -1301,7 +1305,6 @@ void execute_batch(Context &c)
       if (M > 0 && !jobs.empty())
       {
         Arena &ar = c.arena;
-        ar.reset();
         CopyJob *d_jobs = upload(ar, jobs, st);
         int64_t *d_off = upload(ar, job_off, st);
         int *d_sub = upload(ar, job_sub, st);
@@ -1309,7 +1312,6 @@ void execute_batch(Context &c)
                                                                            c.d_ids_orig, c.d_ids);
         HBT_CHECK_LAUNCH();
         c.ls.launches++;
-        HBT_CUDA(cudaStreamSynchronize(st));
       }
     }
   }
@@ -1377,7 +1379,7 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
     o.nsource_full = full;
     o.nsource = ns;
     o.iterations = z.iterations;
-    o.reserved = 0;
+    o.flags = c.io_in[s].flags;
   }
   const int64_t total = out_off[nsub];
   if (total > order_capacity) throw CudaError{HBTU_ERR_CAPACITY, "order_out too small"};

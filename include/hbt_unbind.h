@@ -101,8 +101,15 @@ typedef struct hbtu_sub_io
   int64_t nsource_full;    /* [out] Particles.size() after unbinding, before TruncateSource */
   int64_t nsource;         /* [out] entries written to order_out for this subhalo        */
   int32_t iterations;      /* [out] potential evaluations performed (diagnostic)         */
-  int32_t reserved;
+  int32_t flags;           /* [in]  HBTU_SUB_* (0 = a subhalo reached through RecursiveUnbind)    */
 } hbtu_sub_io;
+
+/* hbtu_sub_io.flags */
+#define HBTU_SUB_PLAIN_UNBIND 1 /* the caller enters this subhalo through plain Subhalo_t::Unbind, not RecursiveUnbind
+                                   (field and new-born subhaloes, src/subhalo_unbind.cpp:498-510; the merge path,
+                                   src/subhalo_merge.cpp:210; INCLUSIVE_MASS builds, :470-476): the orphan rule of
+                                   RecursiveUnbind (:434-446, entry Nbound <= 1: the list is not reordered) does not
+                                   apply.  Only valid for a subhalo without parent and without nested subhaloes. */
 
 /* flags for hbtu_unbind_batch */
 #define HBTU_FLAG_TRUNCATE_SOURCE 1 /* apply Subhalo_t::TruncateSource to every subhalo at the end

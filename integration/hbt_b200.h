@@ -23,3 +23,10 @@ void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap);
 //     std::vector<char> merged; HBT_B200_DetectTraps(*this, merged);  for(i...) Helpers[i].IsMerged = merged[i];
 // (20-particle core moments, host chain walk and sink test on the device through hbtu_detect_traps).
 void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged);
+
+// src/subhalo_merge.cpp:207-214 of the reference (the two loops `if(Helpers[subid].IsMerged) Subhalos[subid].Unbind(*this);` and
+// `... TruncateSource();`) become
+//     HBT_B200_UnbindMerged(*this, merged);      // merged[subid] = Helpers[subid].IsMerged
+// ONE batch for all merged hosts.  Without this patch the unmodified loop still works: the replaced Subhalo_t::Unbind is
+// thread-safe and combines the concurrent OpenMP callers into batches (UnbindCombiner in subhalo_unbind_b200.cpp).
+void HBT_B200_UnbindMerged(SubhaloSnapshot_t &snap, const std::vector<char> &is_merged);

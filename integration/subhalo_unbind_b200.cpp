@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -65,58 +67,103 @@ void fill_params(hbtu_params &p)
 // Devices this process drives.  Default: one (HBT_UNBIND_DEVICE, the usual one-MPI-rank-per-GPU launch).  With
 // HBT_UNBIND_DEVICES=0,1,2,3 one rank shards its hierarchies over several GPUs of the box (whole
 // hierarchies, cost-weighted longest-processing-time-first, no data-path collective; see run_sharded below).
-std::vector<hbtu_ctx *> g_ctxs;
+//
+// Threading.  An hbtu_ctx is not re-entrant, while the reference calls Subhalo_t::Unbind from an OpenMP
+// worksharing loop (src/subhalo_merge.cpp:207-210, `if(ParallelizeHaloes)`).  So: the device table is guarded by
+// g_table_mutex, every library call on a context runs under that Device's own mutex (devices of a sharded batch still run
+// concurrently), Device objects are never freed while the process lives (a context is re-created in place, under its mutex,
+// when HBTConfig changed), and concurrent Unbind callers are COMBINED into one batch per flight (UnbindCombiner below)
+// instead of queueing one-subhalo batches behind a lock.
+struct Device
+{
+  hbtu_ctx *ctx = nullptr;
+  std::mutex mu;
+};
+std::mutex g_table_mutex;
+std::vector<Device *> g_devs;    // current device list
+std::vector<Device *> g_retired; // devices of an earlier HBT_UNBIND_DEVICES list (contexts destroyed, objects kept)
 std::string g_devices;
 
-std::vector<hbtu_ctx *> &contexts()
+std::vector<Device *> devices()
 { // one context per device; re-created if the configuration or the device list changed
+  std::lock_guard<std::mutex> table_lock(g_table_mutex);
   hbtu_params p;
   fill_params(p);
   const char *list = getenv("HBT_UNBIND_DEVICES");
   const std::string devs = list ? list : std::to_string(p.device);
-  if (!g_ctxs.empty() && devs == g_devices && std::memcmp(&p, &g_params, sizeof(p)) == 0) return g_ctxs;
-  for (auto *c : g_ctxs) hbtu_destroy(c);
-  g_ctxs.clear();
+  if (!g_devs.empty() && devs == g_devices && std::memcmp(&p, &g_params, sizeof(p)) == 0) return g_devs;
+  std::vector<int> ids;
   size_t pos = 0;
   while (pos <= devs.size())
   {
     size_t comma = devs.find(',', pos);
     if (comma == std::string::npos) comma = devs.size();
-    if (comma > pos)
-    {
-      hbtu_params q = p;
-      q.device = atoi(devs.substr(pos, comma - pos).c_str());
-      hbtu_ctx *c = nullptr;
-      int rc = hbtu_create(&q, &c);
-      if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_create failed: ") + hbtu_last_error(nullptr));
-      g_ctxs.push_back(c);
-    }
+    if (comma > pos) ids.push_back(atoi(devs.substr(pos, comma - pos).c_str()));
     pos = comma + 1;
   }
-  if (g_ctxs.empty()) throw std::runtime_error("HBT_UNBIND_DEVICES names no device");
+  if (ids.empty()) throw std::runtime_error("HBT_UNBIND_DEVICES names no device");
+  while (g_devs.size() > ids.size())
+  { // the list shrank: retire the surplus devices (their contexts go, the objects stay for late holders of the pointer)
+    Device *d = g_devs.back();
+    g_devs.pop_back();
+    std::lock_guard<std::mutex> lk(d->mu);
+    if (d->ctx) hbtu_destroy(d->ctx);
+    d->ctx = nullptr;
+    g_retired.push_back(d);
+  }
+  while (g_devs.size() < ids.size()) g_devs.push_back(new Device());
+  for (size_t i = 0; i < ids.size(); i++)
+  {
+    Device *d = g_devs[i];
+    std::lock_guard<std::mutex> lk(d->mu); // waits for a call in flight on the old context
+    if (d->ctx) hbtu_destroy(d->ctx);
+    d->ctx = nullptr;
+    hbtu_params q = p;
+    q.device = ids[i];
+    int rc = hbtu_create(&q, &d->ctx);
+    if (rc != HBTU_OK)
+    {
+      g_devices.clear(); // retry from scratch on the next call
+      throw std::runtime_error(std::string("hbtu_create failed: ") + hbtu_last_error(nullptr));
+    }
+  }
   g_params = p;
   g_devices = devs;
   static bool registered = false;
   if (!registered)
   {
-    atexit([] { for (auto *c : g_ctxs) hbtu_destroy(c); g_ctxs.clear(); });
+    atexit([] {
+      for (auto *d : g_devs)
+        if (d->ctx) { hbtu_destroy(d->ctx); d->ctx = nullptr; }
+    });
     registered = true;
   }
-  return g_ctxs;
+  return g_devs;
 }
-hbtu_ctx *context() { return contexts()[0]; }
+Device *device0() { return devices()[0]; }
+
+// run f(ctx) under the device's mutex; a non-zero return code becomes the reference's error style (config_parser.cpp:70)
+template <class F>
+void call_library(Device *d, const char *what, F &&f)
+{
+  std::lock_guard<std::mutex> lk(d->mu);
+  if (!d->ctx) throw std::runtime_error(std::string(what) + ": the device was retired (HBT_UNBIND_DEVICES changed during a call)");
+  const int rc = f(d->ctx);
+  if (rc != HBTU_OK) throw std::runtime_error(std::string(what) + " failed: " + hbtu_last_error(d->ctx));
+}
 
 struct Batch
 { // pack -> call -> unpack of a set of subhaloes given by index into `Subhalos`
   std::vector<Subhalo_t *> subs;
+  std::vector<int32_t> sub_flags; // HBTU_SUB_* per subhalo (missing entries = 0): which reference entry point this subhalo goes through
   std::vector<int64_t> part_offset, nest_offset;
   std::vector<int32_t> nest_list;
 
-  void run(const Snapshot_t &epoch, int32_t flags, hbtu_ctx *ctx = nullptr)
+  void run(const Snapshot_t &epoch, int32_t flags, Device *dev = nullptr)
   {
     const int64_t nsub = subs.size();
     if (nsub == 0) return;
-    if (!ctx) ctx = context();
+    if (!dev) dev = device0();
     // the caller's compile-time physics variant travels as batch flags
 #ifdef NO_STRIPPING
     flags |= HBTU_FLAG_NO_STRIPPING;
@@ -165,6 +212,7 @@ struct Batch
       o.mbound = sub.Mbound;
       o.specific_self_potential_energy = sub.SpecificSelfPotentialEnergy;
       o.specific_self_kinetic_energy = sub.SpecificSelfKineticEnergy;
+      o.flags = (size_t)s < sub_flags.size() ? sub_flags[s] : 0;
     }
     hbtu_epoch e;
     e.scale_factor = epoch.Cosmology.ScaleFactor;
@@ -183,9 +231,10 @@ struct Batch
 #else
     float *pe = nullptr;
 #endif
-    int rc = hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), no, nl, io.data(), flags, cap,
+    call_library(dev, "hbtu_unbind_batch", [&](hbtu_ctx *ctx) {
+      return hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), no, nl, io.data(), flags, cap,
                                order_offset.data(), order.data(), pe);
-    if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_unbind_batch failed: ") + hbtu_last_error(ctx));
+    });
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t s = 0; s < nsub; s++)
     {
@@ -219,6 +268,15 @@ struct Batch
   }
 };
 
+// a subhalo the reference unbinds with plain Subhalo_t::Unbind (no RecursiveUnbind, hence no orphan rule)
+void add_plain(Batch &b, std::vector<std::vector<int32_t>> &lists, Subhalo_t &sub)
+{
+  b.sub_flags.resize(b.subs.size(), 0);
+  b.subs.push_back(&sub);
+  b.sub_flags.push_back(HBTU_SUB_PLAIN_UNBIND);
+  lists.emplace_back();
+}
+
 // append `sub` and, depth first, everything nested in it; returns its batch index
 int64_t add_hierarchy(Batch &b, std::vector<std::vector<int32_t>> &lists, SubhaloList_t &Subhalos, Subhalo_t &sub)
 {
@@ -240,7 +298,7 @@ void close_nests(Batch &b, const std::vector<std::vector<int32_t>> &lists);
 // host thread and context.  Results do not depend on the split: hierarchies never interact.
 void run_sharded(Batch &b, const std::vector<std::vector<int32_t>> &lists, const Snapshot_t &epoch, int32_t flags)
 {
-  std::vector<hbtu_ctx *> &ctxs = contexts();
+  const std::vector<Device *> ctxs = devices();
   const int64_t nsub = b.subs.size();
   const int G = (int)ctxs.size();
   if (G == 1 || nsub < 2)
@@ -282,6 +340,7 @@ void run_sharded(Batch &b, const std::vector<std::vector<int32_t>> &lists, const
       {
         remap[s] = (int32_t)parts[g].subs.size();
         parts[g].subs.push_back(b.subs[s]);
+        parts[g].sub_flags.push_back((size_t)s < b.sub_flags.size() ? b.sub_flags[s] : 0);
       }
     part_lists[g].resize(parts[g].subs.size());
     for (size_t u : mine[g])
@@ -313,11 +372,91 @@ void close_nests(Batch &b, const std::vector<std::vector<int32_t>> &lists)
 }
 } // namespace
 
+namespace
+{
+// Subhalo_t::Unbind is called one subhalo at a time, concurrently from the OpenMP threads of the merge loop
+// (src/subhalo_merge.cpp:207-210).  Flat combining: a caller queues its request; whoever finds no batch in flight becomes the
+// leader, takes everything queued for the same epoch (its own request included), runs ONE hbtu_unbind_batch for it and wakes
+// the owners.  Every call still returns only when its own subhalo is done, so the unmodified caller sees the reference's
+// synchronous semantics; with T threads the merged hosts go through in batches of up to T subhaloes instead of one by one.
+// (Results do not depend on how subhaloes are grouped into batches, bit for bit: DESIGN.md section 7.)
+struct UnbindCombiner
+{
+  struct Request
+  {
+    Subhalo_t *sub;
+    const Snapshot_t *epoch;
+    bool done;
+    std::string error;
+  };
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<Request *> queue;
+  bool running = false;
+
+  void submit(Subhalo_t *sub, const Snapshot_t &epoch)
+  {
+    Request r{sub, &epoch, false, std::string()};
+    std::unique_lock<std::mutex> lk(m);
+    queue.push_back(&r);
+    while (!r.done)
+    {
+      if (running)
+      {
+        cv.wait(lk);
+        continue;
+      }
+      running = true;
+      std::vector<Request *> take, rest;
+      const Snapshot_t *ep = queue.front()->epoch;
+      for (Request *q : queue) (q->epoch == ep ? take : rest).push_back(q);
+      queue.swap(rest);
+      lk.unlock();
+      std::string error;
+      try
+      {
+        Batch b;
+        std::vector<std::vector<int32_t>> lists;
+        for (Request *q : take) add_plain(b, lists, *q->sub);
+        b.run(*ep, 0);
+      }
+      catch (const std::exception &ex) { error = ex.what(); if (error.empty()) error = "unbinding failed"; }
+      lk.lock();
+      for (Request *q : take)
+      {
+        q->error = error;
+        q->done = true;
+      }
+      running = false;
+      cv.notify_all();
+    }
+    lk.unlock();
+    if (!r.error.empty()) throw std::runtime_error(r.error);
+  }
+} g_unbind_combiner;
+} // namespace
+
 void Subhalo_t::Unbind(const Snapshot_t &epoch)
-{ // second caller: subhalo_merge.cpp:207-210 (merged hosts), one subhalo per call
+{ // second caller: subhalo_merge.cpp:207-210 (merged hosts), one subhalo per call, from concurrent OpenMP threads
+  g_unbind_combiner.submit(this, epoch);
+}
+
+// The batched form of the merge path.  src/subhalo_merge.cpp:207-214 of the reference reads
+//     #pragma omp parallel for schedule(dynamic,1) if(ParallelizeHaloes)
+//     for(subid...) if(Helpers[subid].IsMerged) Subhalos[subid].Unbind(*this);
+//     #pragma omp parallel for
+//     for(subid...) if(Helpers[subid].IsMerged) Subhalos[subid].TruncateSource();
+// and becomes   HBT_B200_UnbindMerged(*this, merged);   with merged[subid] = Helpers[subid].IsMerged:
+// ONE batch (sharded over HBT_UNBIND_DEVICES like RefineParticles) with the truncation done by the library.
+void HBT_B200_UnbindMerged(SubhaloSnapshot_t &snap, const std::vector<char> &is_merged)
+{
   Batch b;
-  b.subs.push_back(this);
-  b.run(epoch, 0);
+  std::vector<std::vector<int32_t>> lists;
+  for (size_t i = 0; i < snap.Subhalos.size() && i < is_merged.size(); i++)
+    if (is_merged[i]) add_plain(b, lists, snap.Subhalos[i]);
+  if (b.subs.empty()) return;
+  close_nests(b, lists);
+  run_sharded(b, lists, snap, HBTU_FLAG_TRUNCATE_SOURCE);
 }
 
 void Subhalo_t::RecursiveUnbind(SubhaloList_t &Subhalos, const Snapshot_t &snap)
@@ -343,7 +482,7 @@ void SubhaloSnapshot_t::RefineParticles()
   std::vector<std::vector<int32_t>> lists;
   std::vector<char> done(Subhalos.size(), 0);
 #ifdef INCLUSIVE_MASS
-  for (auto &sub : Subhalos) { b.subs.push_back(&sub); lists.emplace_back(); }
+  for (auto &sub : Subhalos) add_plain(b, lists, sub); // flat loop of plain Unbind calls (subhalo_unbind.cpp:470-476)
 #else
   HBTInt NumHalos = MemberTable.SubGroups.size();
   for (HBTInt haloid = 0; haloid < NumHalos; haloid++)
@@ -366,15 +505,13 @@ void SubhaloSnapshot_t::RefineParticles()
   { // field subhaloes: plain Unbind, no recursion (subhalo_unbind.cpp:498-503)
     HBTInt subid = MemberTable.SubGroups[-1][i];
     if (done[subid]) continue;
-    b.subs.push_back(&Subhalos[subid]);
-    lists.emplace_back();
+    add_plain(b, lists, Subhalos[subid]);
     done[subid] = 1;
   }
   for (HBTInt i = MemberTable.AllMembers.size(); i < (HBTInt)Subhalos.size(); i++)
   { // new-born subhaloes (subhalo_unbind.cpp:505-510)
     if (done[i]) continue;
-    b.subs.push_back(&Subhalos[i]);
-    lists.emplace_back();
+    add_plain(b, lists, Subhalos[i]);
     done[i] = 1;
   }
 #endif
@@ -428,14 +565,13 @@ void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epo
     o.bound_r200crit_comoving = sub.BoundR200CritComoving;
     o.bound_m200crit = sub.BoundM200Crit;
   }
-  hbtu_ctx *ctx = context();
   hbtu_epoch e;
   e.scale_factor = epoch.Cosmology.ScaleFactor;
   e.hz = epoch.Cosmology.Hz;
   e.snapshot_index = epoch.GetSnapshotIndex();
   e.reserved = 0;
-  int rc = hbtu_profile_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), io.data());
-  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_profile_batch failed: ") + hbtu_last_error(ctx));
+  call_library(device0(), "hbtu_profile_batch",
+               [&](hbtu_ctx *ctx) { return hbtu_profile_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), io.data()); });
   for (int64_t s = 0; s < nsub; s++)
   {
     Subhalo_t &sub = Subhalos[s];
@@ -490,10 +626,10 @@ void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap)
 #pragma omp parallel for schedule(dynamic, 16)
   for (int64_t s = 0; s < nsub; s++)
     for (size_t i = 0; i < b.subs[s]->Particles.size(); i++) ids[part_offset[s] + i] = b.subs[s]->Particles[i].Id;
-  hbtu_ctx *ctx = context();
-  int rc = hbtu_mask_batch(ctx, nsub, part_offset.data(), ids.data(), b.nest_offset.data(), b.nest_list.data(), nbound.data(),
+  call_library(device0(), "hbtu_mask_batch", [&](hbtu_ctx *ctx) {
+    return hbtu_mask_batch(ctx, nsub, part_offset.data(), ids.data(), b.nest_offset.data(), b.nest_list.data(), nbound.data(),
                            new_count.data(), keep.data());
-  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_mask_batch failed: ") + hbtu_last_error(ctx));
+  });
 #pragma omp parallel for schedule(dynamic, 16)
   for (int64_t s = 0; s < nsub; s++)
   { // keep is ascending: compact in place, like the reference's move loop (:809-820)
@@ -565,14 +701,14 @@ void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged)
     o.snapshot_index_of_sink = sub.SnapshotIndexOfSink;
     o.is_merged = 0;
   }
-  hbtu_ctx *ctx = context();
   hbtu_epoch e;
   e.scale_factor = snap.Cosmology.ScaleFactor;
   e.hz = snap.Cosmology.Hz;
   e.snapshot_index = snap.GetSnapshotIndex();
   e.reserved = 0;
-  int rc = hbtu_detect_traps(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), nest_offset.data(), nest_list.data(), io.data());
-  if (rc != HBTU_OK) throw std::runtime_error(std::string("hbtu_detect_traps failed: ") + hbtu_last_error(ctx));
+  call_library(device0(), "hbtu_detect_traps", [&](hbtu_ctx *ctx) {
+    return hbtu_detect_traps(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), nest_offset.data(), nest_list.data(), io.data());
+  });
   for (int64_t s = 0; s < nsub; s++)
   {
     Subhalos[s].SinkTrackId = (HBTInt)io[s].sink_track_id;

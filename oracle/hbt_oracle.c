@@ -905,7 +905,14 @@ int hbto_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int64_
         is_child[ch] = 1;
       }
   for (int64_t s = 0; s < nsub; s++)
-    if (!is_child[s]) recursive_unbind(&c, subs, &subs[s]);
+    if ((io[s].flags & HBTU_SUB_PLAIN_UNBIND) && (is_child[s] || subs[s].nnest > 0)) return HBTU_ERR_INVALID;
+  for (int64_t s = 0; s < nsub; s++)
+    if (!is_child[s])
+    { /* field / new-born subhaloes and the merge path call plain Unbind: no orphan rule (src/subhalo_unbind.cpp:498-510,
+         src/subhalo_merge.cpp:210) */
+      if (io[s].flags & HBTU_SUB_PLAIN_UNBIND) unbind(&c, &subs[s]);
+      else recursive_unbind(&c, subs, &subs[s]);
+    }
   int rc = HBTU_OK;
   int64_t pos = 0;
   for (int64_t s = 0; s < nsub; s++)

@@ -213,3 +213,28 @@ def detect_traps(lib, prefix, params, epoch, part_offset, pos_mass, vel, nest_of
     if rc != 0:
         raise RuntimeError(f"{prefix}_detect_traps failed: {rc}")
     return out
+
+
+def merge_subhalos(lib, params, epoch, snap, mode=0, nthreads=0):
+    """``SubhaloSnapshot_t::MergeSubhalos()`` with MergeTrappedSubhalos on, through ref_build/ref_capi.cpp::hbtref_merge_subhalos.
+    mode 0 = the unmodified member function (its Unbind calls come from `nthreads` OpenMP threads); mode 1 = the patched sequence
+    with HBT_B200_UnbindMerged (drop-in libraries only).  Returns (Result, is_merged)."""
+    f = lib.hbtref_merge_subhalos
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(capi.Params), C.POINTER(capi.Epoch), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                  C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(capi.SubIO), C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64),
+                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    cap = 2 * snap.npart + 16  # MergeTo can append a whole satellite list to its sink
+    io = snap.io.copy()
+    order_offset = np.zeros(snap.nsub + 1, np.int64)
+    order = np.full(cap, -1, np.int32)
+    merged = np.zeros(snap.nsub, np.int32)
+    pm = np.ascontiguousarray(snap.pos_mass, np.float32)
+    vv = np.ascontiguousarray(snap.vel, np.float32)
+    P = capi._ptr
+    rc = f(C.byref(params), C.byref(epoch), snap.nsub, P(snap.part_offset, C.c_int64), P(pm, C.c_float), P(vv, C.c_float),
+           P(snap.nest_offset, C.c_int64), P(snap.nest_list, C.c_int32), io.ctypes.data_as(C.POINTER(capi.SubIO)), mode, nthreads, cap,
+           P(order_offset, C.c_int64), P(order, C.c_int32), P(merged, C.c_int32))
+    if rc != 0:
+        raise RuntimeError(f"hbtref_merge_subhalos failed: {rc}")
+    return Result(io, order_offset, order, None), merged

@@ -44,6 +44,7 @@
 void HBT_B200_MaskSubhalos(SubhaloSnapshot_t &snap) __attribute__((weak));
 void HBT_B200_DetectTraps(SubhaloSnapshot_t &snap, std::vector<char> &is_merged) __attribute__((weak));
 void HBT_B200_CalculateProperties(SubhaloList_t &Subhalos, const Snapshot_t &epoch) __attribute__((weak));
+void HBT_B200_UnbindMerged(SubhaloSnapshot_t &snap, const std::vector<char> &is_merged) __attribute__((weak));
 
 /* the real body lives in src/io/subhalo_io.cpp, which needs libhdf5 (absent) */
 void SubhaloSnapshot_t::BuildHDFDataType()
@@ -143,6 +144,11 @@ void fill_subhalo(Subhalo_t &sub, int64_t s, const int64_t *part_offset, const f
   sub.SnapshotIndexOfDeath = io.snapshot_index_of_death;
   sub.SnapshotIndexOfSink = io.snapshot_index_of_sink;
   sub.TrackId = (HBTInt)s;
+  /* [out] fields a subhalo keeps when nothing unbinds it (Subhalo_t's constructor leaves them uninitialised) */
+  sub.Mbound = io.mbound;
+  sub.SpecificSelfPotentialEnergy = io.specific_self_potential_energy;
+  sub.SpecificSelfKineticEnergy = io.specific_self_kinetic_energy;
+  for (int j = 0; j < 3; j++) sub.SpecificAngularMomentum[j] = io.specific_angular_momentum[j];
 }
 
 void read_subhalo(const Subhalo_t &sub, hbtu_sub_io &io)
@@ -257,9 +263,15 @@ int hbtref_unbind_batch(const hbtu_params *params, const hbtu_epoch *epoch, int6
       }
   /* largest roots first so that dynamic scheduling balances, as the reference's
    * mass-sorted member lists effectively do */
+  for (int64_t s = 0; s < nsub; s++)
+    if ((io[s].flags & HBTU_SUB_PLAIN_UNBIND) && (is_child[s] || !subs[s].NestedSubhalos.empty())) return HBTU_ERR_INVALID;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int64_t s = 0; s < nsub; s++)
-    if (!is_child[s]) subs[s].RecursiveUnbind(subs, snap);
+    if (!is_child[s])
+    { /* HBTU_SUB_PLAIN_UNBIND: the reference's plain Unbind call sites (src/subhalo_unbind.cpp:498-510, subhalo_merge.cpp:210) */
+      if (io[s].flags & HBTU_SUB_PLAIN_UNBIND) subs[s].Unbind(snap);
+      else subs[s].RecursiveUnbind(subs, snap);
+    }
 
   std::vector<int64_t> full(nsub);
   for (int64_t s = 0; s < nsub; s++) full[s] = subs[s].Particles.size();
@@ -650,6 +662,102 @@ int hbtref_detect_traps(const hbtu_params *params, const hbtu_epoch *epoch, int6
     io[s].is_merged = merged[s];
   }
   return HBTU_OK;
+}
+
+/* SubhaloSnapshot_t::MergeSubhalos() of the reference with HBTConfig.MergeTrappedSubhalos ON (src/subhalo_merge.cpp:187-220):
+ * trap detection, MergeRecursive / MergeTo, then Subhalo_t::Unbind of every host flagged IsMerged FROM THE OpenMP LOOP at
+ * :207-210 and TruncateSource (:211-214).  Every subhalo is a member of one host halo per nest tree (root = central).
+ *   mode 0  the unmodified member function.  In libhbtref_* its Unbind is the reference's; in libhbtdropin_* it is the shim's
+ *           (integration/subhalo_unbind_b200.cpp), called concurrently by `nthreads` OpenMP threads: the thread-safety test.
+ *   mode 1  (drop-in build only) the patched sequence INTEGRATION.md documents: HBT_B200_DetectTraps, the reference's own
+ *           MergeRecursive, then ONE batch through HBT_B200_UnbindMerged.
+ * Particle Ids are the input indices, so order_out reports the final lists the same way hbtu_unbind_batch does. */
+int hbtref_merge_subhalos(const hbtu_params *params, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
+                          const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_sub_io *io, int32_t mode,
+                          int32_t nthreads, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, int32_t *is_merged_out)
+{
+  if ((params->real_bytes != 4 && params->real_bytes != (int)sizeof(HBTReal))) return HBTU_ERR_UNSUPPORTED;
+  if (mode == 1 && !(HBT_B200_DetectTraps && HBT_B200_UnbindMerged)) return HBTU_ERR_UNSUPPORTED;
+  apply_params(params);
+  HBTConfig.MergeTrappedSubhalos = true;
+  omp_set_max_active_levels(1);
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  SubhaloSnapshot_t snap;
+  set_epoch(snap, epoch);
+  snap.ParallelizeHaloes = true;
+  snap.Subhalos.resize(nsub);
+  std::vector<int32_t> root(nsub, -1);
+  std::vector<char> is_child(nsub, 0);
+  if (nest_offset)
+    for (int64_t k = 0; k < nest_offset[nsub]; k++) is_child[nest_list[k]] = 1;
+  int32_t nhalos = 0;
+  std::vector<int64_t> stack;
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    if (is_child[s]) continue;
+    stack.assign(1, s);
+    while (!stack.empty())
+    {
+      int64_t q = stack.back();
+      stack.pop_back();
+      root[q] = nhalos;
+      if (nest_offset)
+        for (int64_t k = nest_offset[q]; k < nest_offset[q + 1]; k++) stack.push_back(nest_list[k]);
+    }
+    nhalos++;
+  }
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    Subhalo_t &sub = snap.Subhalos[s];
+    fill_subhalo(sub, s, part_offset, pos_mass, vel, io[s]);
+    sub.Mbound = is_child[s] ? 1.f : 1e30f; /* the root sorts first in its group: it is the central */
+    sub.HostHaloId = root[s];
+    sub.Rank = 0;
+    if (nest_offset)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++) sub.NestedSubhalos.push_back(nest_list[k]);
+  }
+#pragma omp parallel
+  snap.MemberTable.Build(nhalos, snap.Subhalos, true);
+  snap.MemberTable.SubGroupsOfHeads.assign(nhalos, std::vector<HBTInt>());
+  for (HBTInt h = 0; h < nhalos; h++) snap.MemberTable.SubGroupsOfHeads[h].push_back(snap.MemberTable.SubGroups[h][0]);
+  std::vector<int64_t> sink_before(nsub), nbound_before(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    sink_before[s] = io[s].sink_track_id;
+    nbound_before[s] = io[s].nbound;
+  }
+  std::vector<char> merged(nsub, 0);
+  try
+  {
+    if (mode == 0)
+    {
+      snap.MergeSubhalos();
+      /* SubHelper_t::IsMerged is local to MergeSubhalos: set exactly for the sinks of real subhaloes trapped now (:152-153) */
+      for (int64_t s = 0; s < nsub; s++)
+        if (sink_before[s] == -1 && snap.Subhalos[s].SinkTrackId != SpecialConst::NullTrackId && nbound_before[s] > 1)
+          merged[snap.Subhalos[s].SinkTrackId] = 1;
+    }
+    else
+    {
+      HBT_B200_DetectTraps(snap, merged);
+      for (HBTInt grpid = 0; grpid < nhalos; grpid++)
+        if (snap.MemberTable.SubGroups[grpid].size()) snap.MergeRecursive(snap.MemberTable.SubGroups[grpid][0]);
+      HBT_B200_UnbindMerged(snap, merged);
+    }
+  }
+  catch (const std::exception &ex)
+  {
+    fprintf(stderr, "MergeSubhalos threw: %s\n", ex.what());
+    return HBTU_ERR_CUDA;
+  }
+  std::vector<int64_t> full(nsub);
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    full[s] = snap.Subhalos[s].Particles.size();
+    read_subhalo(snap.Subhalos[s], io[s]);
+    if (is_merged_out) is_merged_out[s] = merged[s];
+  }
+  return write_orders(snap.Subhalos, full, io, order_capacity, order_offset, order_out, nullptr);
 }
 
 } // extern "C"

@@ -214,3 +214,63 @@ def case_traps(seed=51, periodic=True):
     nest_offset = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int64)
     nest_list = np.array([c for cs in children for c in cs], np.int32)
     return snap, nest_offset, nest_list, io
+
+
+def case_merge(seed=61, periodic=True, nhosts=12):
+    """`nhosts` host haloes, each a central with satellites (and satellites of satellites); about half of the satellites sit on
+    their host's 20-particle core in phase space and get trapped, so MergeSubhalos (MergeTrappedSubhalos on) merges them into
+    their sinks and re-unbinds those hosts (src/subhalo_merge.cpp:201-214).  Returns a synth.Snapshot whose io carries the
+    trap inputs (mostbound position / velocity, Nbound, sink ids)."""
+    rng = np.random.default_rng(seed)
+    sizes, parent = [], []
+    for h in range(nhosts):
+        c = len(sizes)
+        sizes.append(int(rng.integers(1500, 5000)))
+        parent.append(-1)
+        for k in range(int(rng.integers(2, 5))):
+            s = len(sizes)
+            sizes.append(int(rng.integers(60, 600)))
+            parent.append(c)
+            if rng.random() < 0.5:
+                sizes.append(int(rng.integers(25, 50)))
+                parent.append(s)
+    snap = synth.make_snapshot(sizes, seed=seed, wrap=periodic, parent=parent, f_contam=0.1)
+    box = 62.5
+    nsub = snap.nsub
+    io = snap.io
+    for s in range(nsub):
+        p_ = parent[s]
+        if p_ < 0:
+            continue
+        hb = snap.part_offset[p_]
+        hp = snap.pos_mass[hb:hb + 20, :3].astype(np.float64)
+        hv = snap.vel[hb:hb + 20, :3].astype(np.float64)
+        d0 = hp - hp[0]
+        if periodic:
+            d0 -= box * np.round(d0 / box)
+        cpos, cvel = hp[0] + d0.mean(0), hv.mean(0)
+        sr, sv = np.sqrt(d0.var(0).sum()), np.sqrt(hv.var(0).sum())
+        if rng.random() < 0.5:  # inside the host's core: delta ~ 0.9 < 2
+            x = cpos + 0.4 * sr * np.array([1.0, 0, 0])
+            io["mostbound_pos"][s] = np.mod(x, box) if periodic else x
+            io["mostbound_vel"][s] = cvel + 0.5 * sv * np.array([0, 1.0, 0])
+        else:
+            io["mostbound_vel"][s] = cvel + 3.0 * sv * np.array([0, 0, 1.0])
+    return snap
+
+
+def report(name, **stats):
+    """Observed parity statistics of a GPU test, appended to gpurun_out/parity_stats.jsonl (travels back from the GPU box;
+    summarised under profiles/) and printed (pytest -s)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.dumps({"test": name, **stats})
+    print("PARITY", line)
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_stats.jsonl"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass

@@ -138,3 +138,42 @@ def test_detect_traps_drop_in(variant):
     for f in ("sink_track_id", "snapshot_index_of_sink", "is_merged"):
         assert np.array_equal(got[f], want[f]), f
     assert (want["sink_track_id"] >= 0).sum() >= 4
+
+
+def _check_merge(got, gm, want, wm, snap):
+    assert np.array_equal(gm, wm)
+    for f in ("snapshot_index_of_death", "snapshot_index_of_sink", "sink_track_id", "nsource", "nsource_full"):
+        assert np.array_equal(got.io[f], want.io[f]), f
+    assert np.all(np.abs(got.io["nbound"] - want.io["nbound"]) <= np.maximum(1, 2e-4 * want.io["nbound"]))
+    assert np.array_equal(got.io["nbound"] > 1, want.io["nbound"] > 1)
+    hosts = np.nonzero(wm)[0]
+    assert np.allclose(got.io["mbound"][hosts], want.io["mbound"][hosts], rtol=1e-3)
+    for f in ("avg_pos", "avg_vel", "mostbound_pos", "mostbound_vel"):
+        assert np.allclose(got.io[f][hosts], want.io[f][hosts], rtol=2e-6, atol=1e-6), f
+    for s in range(snap.nsub):
+        assert cases.jaccard(got.bound(s), want.bound(s)) >= 0.999, s
+        assert cases.jaccard(got.particles(s), want.particles(s)) >= 0.999, s
+
+
+@pytest.mark.parametrize("variant", ["v32", "v64"])
+def test_merge_subhalos_drop_in(variant):
+    """SURVEY.md 8(b) threading + 8(f) next-3: the reference's UNMODIFIED SubhaloSnapshot_t::MergeSubhalos with
+    MergeTrappedSubhalos on calls Subhalo_t::Unbind from its OpenMP loop (src/subhalo_merge.cpp:207-210).  In libhbtdropin that
+    is the shim's Unbind, entered here by 8 concurrent threads (combined into batches under the device mutex); the catalogue must
+    equal the reference's.  Then the patched sequence with ONE batch (HBT_B200_UnbindMerged) must give the same again."""
+    if not po.have_dropin(variant):
+        pytest.skip("oracle/_ref libraries not built (reference sources absent at build time)")
+    ref, drop = po.load_ref_variant(variant), po.load_dropin(variant)
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=True)
+    e = capi.make_epoch(0.8, snapshot_index=23)
+    snap = cases.case_merge()
+    want, wm = po.merge_subhalos(ref, p, e, snap, mode=0, nthreads=4)
+    assert wm.sum() >= 8 and (want.io["nbound"] != snap.io["nbound"]).sum() >= 8
+    for rep in range(3):  # the race, if any, is timing dependent
+        got, gm = po.merge_subhalos(drop, p, e, snap, mode=0, nthreads=8)
+        _check_merge(got, gm, want, wm, snap)
+    one, om = po.merge_subhalos(drop, p, e, snap, mode=1, nthreads=8)
+    _check_merge(one, om, want, wm, snap)
+    # one batch or many: bit-identical records (DESIGN.md section 7)
+    for f in got.io.dtype.names:
+        assert np.array_equal(one.io[f], got.io[f]), f

@@ -38,13 +38,18 @@ def make_ctx():
         c.close()
 
 
-def check_batch(snap, got, want, exact_frames=True, exact_counts=False):
+JACCARD_MISS_CEILING = 2e-3  # hard ceiling of the fraction of subhaloes allowed below Jaccard 0.999 (each by <= 2 particles)
+
+
+def check_batch(snap, got, want, exact_frames=True, exact_counts=False, name=None):
     """The north-star gates.  Survival (Nbound > 1, death/sink flags: what subhalo counts and track IDs depend on) must be
     bit-exact; bound mass within 0.1 %; membership Jaccard >= 0.999.  A particle whose |E| is within fp32 round-off of 0
     may flip (observed: ~1 per 1e6 particle evaluations), so Nbound itself is compared to 2e-4 unless exact_counts is
     asked for (the golden fixtures, where no flip occurs).  A subhalo of < 2000 particles cannot lose one particle and
-    keep Jaccard >= 0.999, so for those a flip of <= 2 particles is tolerated in at most 0.2 % of the subhaloes; the mass
-    gate is applied to subhaloes with unchanged Nbound and to all subhaloes above 2000 particles.
+    keep Jaccard >= 0.999; such MISSES are counted and reported (cases.report -> gpurun_out/parity_stats.jsonl), never
+    hidden: the miss rate has the hard ceiling JACCARD_MISS_CEILING, every miss must be a flip of <= 2 particles in a
+    subhalo of < 2000 particles, and with exact_counts no miss is allowed at all.  The mass gate is applied to subhaloes
+    with unchanged Nbound and to all subhaloes above 2000 particles.
     Average positions are compared as they are, NOT modulo the box: in periodic runs the image the reference reports
     depends on which particle its hole-based partition leaves in Elist[0] (src/subhalo_unbind.cpp:21-58,152-154), and the
     library tracks exactly that (unbind_batch.cu, rho_*)."""
@@ -66,15 +71,23 @@ def check_batch(snap, got, want, exact_frames=True, exact_counts=False):
     gate = ~skip & (same | big)
     mb_g, mb_w = got.io["mbound"][gate], want.io["mbound"][gate]
     assert np.all(np.abs(mb_g - mb_w) <= 1e-3 * np.abs(mb_w))  # gate: 0.1 %
-    flipped = 0
+    misses, min_j = [], 1.0
     for s in range(snap.nsub):
         jb = cases.jaccard(got.bound(s), want.bound(s))
+        min_j = min(min_j, jb)
         if jb < 0.999:
             assert not exact_counts and nb_w[s] < 2000, s
             assert len(set(got.bound(s).tolist()) ^ set(want.bound(s).tolist())) <= 2, s
-            flipped += 1
+            misses.append(s)
         assert cases.jaccard(got.particles(s), want.particles(s)) >= (0.999 if jb >= 0.999 else 0.97), s
-    assert flipped <= max(1, 2e-3 * snap.nsub), flipped
+    live = int((nb_w > 1).sum())
+    stats = {"subhaloes": int(snap.nsub), "live": live, "frac_identical_nbound": float(np.mean(same)), "jaccard_misses": len(misses),
+             "jaccard_miss_rate": len(misses) / max(snap.nsub, 1), "min_jaccard": float(min_j),
+             "largest_miss_nbound": int(max((nb_w[s] for s in misses), default=0)),
+             "max_rel_dmbound": float(np.max(np.abs(mb_g - mb_w) / np.abs(mb_w))) if mb_w.size else 0.0}
+    if name:
+        cases.report(name, **stats)
+    assert len(misses) <= max(1, JACCARD_MISS_CEILING * snap.nsub), stats
     sel = ~skip & same if not exact_counts else ~skip
     for f in ("avg_pos", "avg_vel", "mostbound_pos", "mostbound_vel"):
         a, b = got.io[f][sel].astype(np.float64), want.io[f][sel].astype(np.float64)
@@ -83,6 +96,7 @@ def check_batch(snap, got, want, exact_frames=True, exact_counts=False):
     for f in ("specific_self_potential_energy", "specific_self_kinetic_energy", "specific_angular_momentum"):
         a, b = got.io[f][~skip & same], want.io[f][~skip & same]
         assert np.allclose(a, b, rtol=2e-4, atol=1e-3 * np.abs(b).max() if b.size else 0), f
+    return stats
 
 
 @pytest.mark.parametrize("name", list(cases.VARIANT_CASES))

@@ -306,3 +306,42 @@ def test_oracle_traps_match_reference(oracle_lib, ref_lib, periodic):
     assert trapped.sum() >= 3 and (a["sink_track_id"][(io["sink_track_id"] < 0)] < 0).sum() >= 3  # both outcomes occur
     assert a["sink_track_id"][8] == 0 and a["snapshot_index_of_sink"][8] == 4  # already trapped: untouched
     assert np.all(a["snapshot_index_of_sink"][trapped] == 23) and a["is_merged"].sum() >= 1
+
+
+def plain_unbind_case(seed=77):
+    """Roots the reference unbinds with plain Subhalo_t::Unbind (field / new-born subhaloes, the merge path): entry Nbound <= 1
+    with a full particle list is NOT an orphan there (the orphan rule lives in RecursiveUnbind, src/subhalo_unbind.cpp:434-446)."""
+    sizes = [400, 60, 25, 1, 0, 900]
+    snap = synth.make_snapshot(sizes, seed=seed, wrap=False, f_contam=0.25)
+    snap.io["nbound"] = [1, 0, 1, 1, 0, 900]
+    snap.io["flags"] = capi.HBTU_SUB_PLAIN_UNBIND
+    return snap
+
+
+def test_plain_unbind_flag_oracle_matches_reference(oracle_lib, ref_lib):
+    oracle_lib.hbto_set_num_threads(1)
+    p = capi.make_params(box_size=62.5, softening=5e-3, periodic=False)
+    e = capi.make_epoch(0.9, snapshot_index=7)
+    snap = plain_unbind_case()
+    a = po.run_batch(ref_lib, "hbtref", p, e, snap)
+    b = po.run_batch(oracle_lib, "hbto", p, e, snap)
+    for f in cases.IO_EXACT:
+        assert np.array_equal(a.io[f], b.io[f]), f
+    live = a.io["nbound"] > 1
+    for f in cases.IO_FLOAT:
+        assert np.array_equal(a.io[f][live], b.io[f][live]), f
+    for s in range(snap.nsub):
+        assert orders_equal_modulo_ties(b.particles(s), a.particles(s), a.energy[a.order_offset[s]:], int(a.io["nbound"][s]))
+    # the flag matters: without it sub 0 is an orphan (RecursiveUnbind semantics) and keeps its input order
+    assert a.io["nbound"][0] > 100 and not np.array_equal(a.particles(0), np.arange(400))
+    snap.io["flags"] = 0
+    c = po.run_batch(ref_lib, "hbtref", p, e, snap)
+    assert np.array_equal(c.particles(0), np.arange(400))
+    # and it is only legal on a subhalo without parent and children
+    nested = synth.make_snapshot([300, 50], seed=3, parent=[-1, 0], wrap=False)
+    nested.io["flags"] = capi.HBTU_SUB_PLAIN_UNBIND
+    with pytest.raises(RuntimeError):
+        po.run_batch(oracle_lib, "hbto", p, e, nested)
+    with pytest.raises(RuntimeError):
+        po.run_batch(ref_lib, "hbtref", p, e, nested)
+    oracle_lib.hbto_set_num_threads(8)
