@@ -37,61 +37,150 @@ from hbtplus_b200 import capi, synth  # noqa: E402
 
 METRIC = "bound-particle unbinding throughput"
 UNIT = "particles/s"
-BOX, EPS = 100.0, 4.8e-5
-SEED = 20240002
 FLOP_PER_INTERACTION = 12  # 3 FADD + FMUL + 2 FFMA + FSETP + FFMA (+MUFU) = 8 issue slots = 12 flop
 
 
-def params_for(device: int = 0) -> capi.Params:
-    return capi.make_params(box_size=BOX, softening=EPS, periodic=False, max_sample_size=0, device=device)
+class Workload:
+    """One synthetic configuration of BASELINE.json / SURVEY.md 8(d): parameters, the size list + nest forest, the generator call."""
+
+    def __init__(self, name, seed, box, eps, periodic, mass, full_particles, desc):
+        self.name, self.seed, self.box, self.eps, self.periodic, self.mass, self.full_particles, self.desc = name, seed, box, eps, periodic, mass, full_particles, desc
+
+    def params(self, device: int = 0) -> capi.Params:
+        return capi.make_params(box_size=self.box, softening=self.eps, periodic=self.periodic, max_sample_size=0, device=device)
+
+    def sizes(self, particles: float):
+        raise NotImplementedError
+
+    def centres(self, sizes, parent):
+        return [self.box / 2] * 3
+
+    def describe(self, particles: float) -> str:
+        return self.desc.format(P=particles, box=self.box, eps=self.eps)
+
+    def make(self, particles: float, dev, rank: int):
+        sizes, parent = self.sizes(particles)
+        return synth.make_snapshot_torch(sizes, device=dev, seed=self.seed + rank, box_size=self.box, particle_mass=self.mass, parent=parent,
+                                         centre=self.centres(sizes, parent), wrap=self.periodic, pin=True)
+
+    def cpu_sample(self, particles: float, target: int):
+        """Bounded sample of the workload for the CPU legs: whole hierarchies in a shuffled order until ~`target` particles are
+        collected; a hierarchy larger than target/10 is replaced by the hierarchies of its nested subhaloes (so the dominant
+        sources - the AqA2 central, the two cfg-5 haloes - are excluded: each alone would take the CPU hours)."""
+        sizes, parent = self.sizes(particles)
+        nsub = len(sizes)
+        children = [[] for _ in range(nsub)]
+        for s in range(nsub):
+            if parent[s] >= 0:
+                children[parent[s]].append(s)
+        tot = sizes.astype(np.int64).copy()
+        for s in np.argsort(sizes, kind="stable"):  # children are smaller than their parents: they come first
+            if parent[s] >= 0:
+                tot[parent[s]] += tot[s]
+        tops, todo = [], [s for s in range(nsub) if parent[s] < 0]
+        while todo:
+            s = todo.pop()
+            if tot[s] > target // 10:
+                todo.extend(children[s])
+            else:
+                tops.append(s)
+        tops = np.array(sorted(tops))
+        np.random.default_rng(self.seed + 1).shuffle(tops)
+        chosen, n = [], 0
+        for t in tops:
+            stack = [int(t)]
+            while stack:
+                q = stack.pop()
+                chosen.append(q)
+                stack.extend(children[q])
+            n += int(tot[t])
+            if n >= target:
+                break
+        chosen = np.array(sorted(chosen))
+        local = {int(g): i for i, g in enumerate(chosen)}
+        par = np.array([local.get(int(parent[g]), -1) for g in chosen])
+        snap = synth.make_snapshot(sizes[chosen], seed=self.seed + 2, box_size=self.box, particle_mass=self.mass, parent=par, wrap=self.periodic,
+                                   centre=None if self.periodic else [self.box / 2] * 3, f_contam=0.2)
+        desc = (f"{len(chosen)} subhaloes in {int((par < 0).sum())} whole hierarchies (sizes {int(sizes[chosen].min())}..{int(sizes[chosen].max())}, "
+                f"{snap.npart} particles), same generator/seed family as the GPU batch; hierarchies above {target // 10} particles are "
+                f"replaced by their nested subhaloes (the dominant sources are excluded)")
+        return snap, desc
 
 
-def workload_sizes(particles: float, seed: int):
-    rng = np.random.default_rng(seed)
-    nsub = max(50, int(40000 * min(1.0, particles / 1.8e8)))
-    n_max = 5e6 * min(1.0, particles / 1.8e8)
-    sizes = synth.aqa2_sizes(rng, n_total=particles, central_frac=0.72, nsub=nsub, n_max=max(n_max, 2000))
-    parent = synth.nest_forest(rng, sizes, max_depth=4, p_nest=0.5, root=0)
-    return sizes, parent
+class AqA2(Workload):
+    def sizes(self, particles):
+        rng = np.random.default_rng(self.seed)
+        nsub = max(50, int(40000 * min(1.0, particles / 1.8e8)))
+        n_max = 5e6 * min(1.0, particles / 1.8e8)
+        sizes = synth.aqa2_sizes(rng, n_total=particles, central_frac=0.72, nsub=nsub, n_max=max(n_max, 2000))
+        parent = synth.nest_forest(rng, sizes, max_depth=4, p_nest=0.5, root=0)
+        return sizes, parent
 
 
-def cpu_sample(particles: float, seed: int, target: int):
-    """Bounded sample of the workload for the CPU legs: whole sub-hierarchies (depth-1 subhaloes of the central with
-    everything nested in them), taken in index order with a stride until ~`target` particles are collected."""
-    sizes, parent = workload_sizes(particles, seed)
-    nsub = len(sizes)
-    root = np.arange(nsub)
-    for s in np.argsort(-sizes, kind="stable"):  # parents are larger, so they come first
-        if parent[s] > 0:
-            root[s] = root[parent[s]]
-    tops = np.nonzero(parent == 0)[0]
-    rng = np.random.default_rng(seed + 1)
-    rng.shuffle(tops)
-    chosen, tot = [], 0
-    for t in tops:
-        members = np.nonzero(root == t)[0]
-        n = int(sizes[members].sum())
-        if n > target // 10:
-            continue  # keep the sample bounded: one giant sub-hierarchy would be most of the CPU time
-        chosen.extend(members.tolist())
-        tot += n
-        if tot >= target:
-            break
-    chosen = np.array(sorted(chosen))
-    local = {int(g): i for i, g in enumerate(chosen)}
-    par = np.array([local.get(int(parent[g]), -1) for g in chosen])
-    snap = synth.make_snapshot(sizes[chosen], seed=seed + 2, box_size=BOX, particle_mass=1e-6, parent=par, wrap=False,
-                               centre=[BOX / 2] * 3, f_contam=0.2)
-    desc = (f"{len(chosen)} subhaloes in {int((par < 0).sum())} whole sub-hierarchies of the central (sizes {int(sizes[chosen].min())}.."
-            f"{int(sizes[chosen].max())}, {snap.npart} particles), same generator/seed family as the GPU batch; the 0.72*P central is excluded")
-    return snap, desc
+class MilliMill(Workload):
+    def sizes(self, particles):
+        rng = np.random.default_rng(self.seed)
+        f = min(1.0, particles / self.full_particles)
+        nsub = max(100, int(25000 * f))
+        sizes = synth.subhalo_sizes(rng, nsub, 20, int(max(5e5 * f, 2000)))
+        for _ in range(4):
+            sizes = np.clip((sizes * (particles / sizes.sum())).astype(np.int64), 20, int(max(5e5 * f, 2000)))
+        parent = synth.nest_forest(rng, sizes, max_depth=3, p_nest=0.2, root=None)  # ~2e4 FoF groups (roots) + ~5e3 satellites
+        return sizes, parent
+
+    def centres(self, sizes, parent):
+        return None  # groups uniformly in the periodic box
 
 
-def run_cpu(snap, threads: int | None = None):
-    """One RefineParticles-equivalent pass on the host cores; returns (seconds, kind, threads)."""
+class DynamicMerger(Workload):
+    def sizes(self, particles):
+        rng = np.random.default_rng(self.seed)
+        f = min(1.0, particles / self.full_particles)
+        nsub = max(100, int(1e5 * f))
+        big = int(5e6 * f)
+        small = rng.integers(20, 201, nsub).astype(np.int64)
+        sizes = np.concatenate([[big, big], small]).astype(np.int64)
+        parent = np.concatenate([[-1, -1], rng.integers(0, 2, nsub)]).astype(np.int64)  # every tiny subhalo sits in one of the two haloes
+        return sizes, parent
+
+    def centres(self, sizes, parent):
+        c = np.tile(np.array([self.box / 2] * 3), (len(sizes), 1))
+        c[0, 0] -= 0.5  # two haloes at 1 Mpc/h separation
+        c[1, 0] += 0.5
+        return c
+
+
+WORKLOADS = {
+    "cfg2": AqA2("cfg2", 20240002, 100.0, 4.8e-5, False, 1e-6, 1.8e8,
+                 "BASELINE configs[1] / SURVEY 8(d) cfg 2: AqA2-shaped synthetic Milky-Way halo per GPU: central source 0.72*P + subhaloes dN/dn~n^-1.9 on "
+                 "[20,5e6], nest depth<=4, P={P:.3g} particles, BoxSize {box}, eps {eps}, periodic off, exact potential (MaxSample 0), theta 0.45"),
+    "cfg3": MilliMill("cfg3", 20240003, 62.5, 5e-3, True, 0.086, 8.9e6,
+                      "BASELINE configs[2] / SURVEY 8(d) cfg 3: MilliMill-shaped 270^3 box per GPU: P={P:.3g} grouped particles (45 % of 1.97e7) in ~2e4 FoF groups + ~5e3 "
+                      "satellites, dN/dn~n^-1.9 on [20,5e5], nest depth<=3, BoxSize {box}, eps {eps}, periodic on, exact potential, theta 0.45"),
+    "cfg5": DynamicMerger("cfg5", 20240005, 250.0, 2.1e-3, False, 0.086, 1.0e7 + 1.1e7,
+                          "BASELINE configs[4] / SURVEY 8(d) cfg 5: DynamicMerger-shaped: two 5e6-particle haloes at 1 Mpc/h separation + 1e5 tiny subhaloes "
+                          "n in [20,200] nested in them (small-subhalo batched path), P={P:.3g} particles, BoxSize {box}, eps {eps}, periodic off, exact potential, theta 0.45"),
+}
+SEED = WORKLOADS["cfg2"].seed
+
+
+def params_for(device: int = 0, workload: str = "cfg2") -> capi.Params:
+    return WORKLOADS[workload].params(device)
+
+
+def workload_sizes(particles: float, seed: int = SEED):  # kept for tools/ and tests that size the cfg-2 batch
+    return WORKLOADS["cfg2"].sizes(particles)
+
+
+def cpu_sample(particles: float, seed: int, target: int, workload: str = "cfg2"):
+    return WORKLOADS[workload].cpu_sample(particles, target)
+
+
+def run_cpu(snap, threads: int | None = None, workload: str = "cfg2"):
+    """One RefineParticles-equivalent pass on the host cores; returns (seconds, kind, threads, sum Nbound, result)."""
     from oracle import pyoracle as po
 
-    p = params_for()
+    p = params_for(0, workload)
     e = capi.make_epoch(1.0)
     ncpu = threads or os.cpu_count() or 1
     if po.have_ref():
@@ -107,9 +196,9 @@ def run_cpu(snap, threads: int | None = None):
     return dt, kind, ncpu, int(r.io["nbound"].sum()), r
 
 
-def parity_block(ctx, e, csnap, cres, kind, pot_targets: int = 100_000):
-    """The GPU path on exactly the snapshot the CPU leg just unbound (same generator, BoxSize 100, eps 4.8e-5, m_p 1e-6, exact
-    potential), compared record by record with the reference's result: what the timed kernels compute is what the reference
+def parity_block(ctx, e, csnap, cres, kind, workload: str = "cfg2", pot_targets: int = 100_000):
+    """The GPU path on exactly the snapshot the CPU leg just unbound (same generator and parameters - cfg 2: BoxSize 100, eps 4.8e-5,
+    m_p 1e-6 - exact potential), compared record by record with the reference's result: what the timed kernels compute is what the reference
     computes.  Gates of BASELINE.json's north_star are reported, not assumed: Nbound / survival / death flags, bound mass,
     bound-membership Jaccard, and the per-particle potential of the sample's largest subhalo against the reference's own
     GravityTree_t::EvaluatePotential (src/gravity_tree.cpp:79-164) on `pot_targets` of its particles."""
@@ -150,7 +239,7 @@ def parity_block(ctx, e, csnap, cres, kind, pot_targets: int = 100_000):
     ctx.set_counting(False)
     pick = np.random.default_rng(7).choice(en - b, size=min(pot_targets, en - b), replace=False)
     lib, prefix = (po.load_ref(), "hbtref") if kind == "reference" else (po.load_oracle(), "hbto")
-    want = po.tree_potential(lib, prefix, params_for(), e, src, src[pick], self_mass=src[pick, 3].copy())
+    want = po.tree_potential(lib, prefix, params_for(0, workload), e, src, src[pick], self_mass=src[pick, 3].copy())
     rel = np.abs(pot[pick] - want) / np.abs(want)
     out["potential"] = {"sources": en - b, "targets_compared": int(len(pick)), "max_rel_err": float(rel.max()), "mean_rel_err": float(rel.mean()),
                         "frac_above_1e-3": float(np.mean(rel > 1e-3)), "interactions_per_target": st.pair_interactions / (en - b),
@@ -161,15 +250,13 @@ def parity_block(ctx, e, csnap, cres, kind, pot_targets: int = 100_000):
 
 
 def phase_rooflines(st0, build_ms, other_ms, peaks):
-    """HBM rooflines of the two non-walk phases of a step: algorithmic bytes per particle per round
-     x particles summed over the step's rounds / CUDA-event time of the phase."""
+    """HBM rooflines of the two non-walk phases of a step with SURVEY.md 8(d)'s ALGORITHMIC bytes (not this implementation's
+    pass list): per source particle and tree build 16 B position read + 12 B key/index write, one sort pass 12 B read + 12 B
+    write, 16 B sorted read + 8 B moment traffic + 24 B node write = 100 B; per walk target and round 32 B energy inputs,
+    4 B E write, partition 8 B read + 8 B write, one E-sort pass 12 B + 12 B = 76 B.  x particles summed over the step's
+    rounds / CUDA-event time of the phase."""
     hbm = peaks.get("hbm_gbs", 6650.0)
-    # tree build, per source particle: gather 16 R + 16 W, bbox 16 R, key 16 R + 12 W, sort 12 R + 12 W (one algorithmic
-    # pass), sorted copy 28 R + 28 W, cell pairs 8 R + 13 W, moment scan 16 R + 32 W, node emit 32 R + 24+24 W
-    build_bytes = 16 + 16 + 16 + 16 + 12 + 12 + 12 + 28 + 28 + 8 + 13 + 16 + 32 + 32 + 48
-    # partition / sort / reduce, per target: E count 4 R, key 4 R + 12 W, sort 12 R + 12 W, permute 8 R + 8 W,
-    # frame reduction 4 + 32 R, kinematics 4 + 32 + 4 R (converged only: counted once)
-    other_bytes = 4 + 4 + 12 + 12 + 12 + 8 + 8 + 36 + 40
+    build_bytes, other_bytes = 100, 76
     out = {}
     for name, n, ms, b in (("tree_build", st0.tree_sources, build_ms, build_bytes), ("partition_sort_reduce", st0.walk_targets, other_ms, other_bytes)):
         ach = b * n / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
@@ -353,24 +440,29 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--particles", type=float, default=1.8e8, help="particles per GPU (BASELINE configs[1]: 1.8e8)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="cfg2 = BASELINE configs[1] (the headline); cfg3 / cfg5 = SURVEY 8(d) cfg 3 / 5")
+    ap.add_argument("--particles", type=float, default=None, help="particles per GPU (default: the configuration's full size; cfg2: 1.8e8)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="particles in the bounded CPU sample (10-30 s on 16 cores)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps)")
     ap.add_argument("--profile", action="store_true", help="for ncu: no counting pass, no e2e, no CPU leg (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"AqA2-shaped synthetic Milky-Way halo per GPU: central source 0.72*P + subhaloes dN/dn~n^-1.9 on [20,5e6], nest depth<=4, "
-                f"P={args.particles:.3g} particles, BoxSize {BOX}, eps {EPS}, periodic off, exact potential (MaxSample 0), theta 0.45")
+    wl = WORKLOADS[args.workload]
+    if args.particles is None:
+        args.particles = wl.full_particles
+    if args.e2e_steps is None:
+        args.e2e_steps = args.steps
+    workload = wl.describe(args.particles)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        snap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
+        snap, desc = wl.cpu_sample(args.particles, args.cpu_sample)
         times, kind, ncpu, nb = [], None, None, 0
         for i in range(args.warmup + args.steps):
-            dt, kind, ncpu, nb, _ = run_cpu(snap)
+            dt, kind, ncpu, nb, _ = run_cpu(snap, workload=wl.name)
             if i >= args.warmup:
                 times.append(dt)
         dt = float(np.mean(times))
@@ -396,12 +488,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    sizes, parent = workload_sizes(args.particles, SEED)  # same halo shape on every rank (weak scaling), own particle realisation
-    snap = synth.make_snapshot_torch(sizes, device=dev, seed=SEED + rank, box_size=BOX, particle_mass=1e-6, parent=parent,
-                                     centre=[BOX / 2] * 3, wrap=False, pin=True)
+    snap = wl.make(args.particles, dev, rank)  # same shape on every rank (weak scaling), own particle realisation
     torch.cuda.empty_cache()
     n_local = snap.npart
-    ctx = UnbindContext(params_for(local_rank))
+    ctx = UnbindContext(wl.params(local_rank))
     e = capi.make_epoch(1.0)
     flags = capi.HBTU_FLAG_TRUNCATE_SOURCE
 
@@ -482,38 +572,42 @@ def main():
         nsm = torch.cuda.get_device_properties(dev).multi_processor_count
         peak_inter = nsm * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 8
         inter_rate = st0.pair_interactions * args.steps / (sum(walk_ms) * 1e-3)
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "walk_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        if os.path.exists(tpath) and wl.name == "cfg2":
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("kernel")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_exec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "particles_per_gpu": n_local, "subhaloes_per_gpu": snap.nsub, "sum_nbound": nb_all,
-                       "l2_policy": "inputs (5.8 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
+            "config": {"workload": workload, "workload_id": wl.name, "particles_per_gpu": n_local, "subhaloes_per_gpu": snap.nsub, "sum_nbound": nb_all,
+                       "l2_policy": f"inputs ({n_local * 32 / 1e9:.2f} GB per GPU) are larger than the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the library stream around hbtu_execute, max over ranks", "wall_ms_per_step": float(np.mean(wall)) * 1e3,
                        "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
                        "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all,
+                       "walk_fallbacks": int(st0.walk_fallbacks),
                        "phase_rooflines": phase_rooflines(st0, float(np.mean(build_ms)), float(np.mean(other_ms)), peaks)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
-                    "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "api": "hbtu_unbind_batch from pinned host buffers"},
+                    "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "steps": len(e2e_wall), "api": "hbtu_unbind_batch from pinned host buffers"},
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "fp32_issue", "achieved": inter_rate * FLOP_PER_INTERACTION / 1e12, "peak": peak_inter * FLOP_PER_INTERACTION / 1e12,
-                         "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "kernel": "walk_masked_kernel (segments >= 8192 targets) + walk_kernel",
+                         "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "traffic_kernel": traffic_note,
+                         "kernel": "walk phase: walk_masked_kernel (segments >= 8192 targets) + walk_small_kernel / walk_kernel (smaller ones)",
                          "interactions_per_s": inter_rate, "peak_interactions_per_s": peak_inter,
                          "peak_source": f"{nsm} SM x 128 fp32 lanes x sm_max_mhz ({peak_src}) / 8 issue slots per interaction (SURVEY.md 8(d)); 12 flop per interaction",
                          "note": "tensor cores deliberately unused (not a dense contraction); kernel share of the step = walk/total in config.phase_ms"},
         }
         if world == 1 and not args.profile:
-            csnap, desc = cpu_sample(args.particles, SEED, args.cpu_sample)
-            dt, kind, ncpu, _, cres = run_cpu(csnap)
+            csnap, desc = wl.cpu_sample(args.particles, args.cpu_sample)
+            dt, kind, ncpu, _, cres = run_cpu(csnap, workload=wl.name)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
-            out["parity"] = parity_block(ctx, e, csnap, cres, kind)
-            out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
-                                          "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks),
-                                          "particle_query": bench_idtable_row(ctx, snap.npart, csnap.npart, peaks)}
+            out["parity"] = parity_block(ctx, e, csnap, cres, kind, workload=wl.name)
+            if wl.name == "cfg2":
+                out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
+                                              "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks),
+                                              "particle_query": bench_idtable_row(ctx, snap.npart, csnap.npart, peaks)}
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:

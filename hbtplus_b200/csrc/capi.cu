@@ -225,7 +225,7 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
   Arena &ar = c.arena;
   ar.reset();
   ar.reserve(tree_arena_bytes(S, 1) + (int64_t)T * 96 + (1 << 20));
-  const WalkClass wcl = walk_class(T);
+  const WalkClass wcl = walk_class(T, S);
   const int tpl = wcl.targets_per_lane;
   std::vector<int> tree_off{0, S}, warp_off{0, (T + wcl.targets_per_warp - 1) / wcl.targets_per_warp};
   Segment sg{};
@@ -524,6 +524,38 @@ int hbtu_set_counting(hbtu_ctx *ctx, int on)
   if (!ctx) return HBTU_ERR_INVALID;
   ctx->c.count_interactions = on != 0;
   return HBTU_OK;
+}
+
+/* diagnostics (no reference counterpart): kernel-routing knobs of the walk, process-wide (device_tree.cuh: WalkTuning).
+ * Results do not depend on them up to fp64 summation order; tests force every route, tools/ab_walk.py times them. */
+int hbtu_set_tuning(const char *key, int64_t value)
+{
+  if (!key) return HBTU_ERR_INVALID;
+  WalkTuning &t = walk_tuning();
+  const std::string k(key);
+  if (k == "walk_tpl") t.forced_tpl = (int)value;
+  else if (k == "walk_big4") t.big4 = (int)value;
+  else if (k == "walk_big2") t.big2 = (int)value;
+  else if (k == "walk_group_min") t.group_min = (int)value;
+  else if (k == "walk_masked_pairs") t.masked_pairs = value == 1 ? 1 : 2;
+  else if (k == "walk_masked_blocks") t.masked_blocks = (int)value;
+  else if (k == "walk_small_max") t.small_max = (int)value;
+  else return HBTU_ERR_INVALID;
+  return HBTU_OK;
+}
+int64_t hbtu_get_tuning(const char *key)
+{
+  if (!key) return -1;
+  const WalkTuning &t = walk_tuning();
+  const std::string k(key);
+  if (k == "walk_tpl") return t.forced_tpl;
+  if (k == "walk_big4") return t.big4;
+  if (k == "walk_big2") return t.big2;
+  if (k == "walk_group_min") return t.group_min;
+  if (k == "walk_masked_pairs") return t.masked_pairs;
+  if (k == "walk_masked_blocks") return t.masked_blocks;
+  if (k == "walk_small_max") return t.small_max;
+  return -1;
 }
 
 } // extern "C"

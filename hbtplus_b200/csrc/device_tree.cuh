@@ -134,7 +134,7 @@ struct WalkArgs
   const Segment *segs;   // [nseg]
   const int *warp_off;   // [nseg+1]
   int nseg, nwarps;
-  int targets_per_lane;  // walk class: 1, 2 or 4 (walk.cu, warps own 32*T consecutive targets) or kWalkGroup4/8 (walk_group.cu)
+  int targets_per_lane;  // walk class: 1, 2 or 4 (walk.cu, warps own 32*T consecutive targets) or kWalkGroup2/4 (walk_masked.cu)
   const float4 *tgt_pm;  // [T] x,y,z,self mass
   const int64_t *tgt_slot; // [T] slot in ids/E (unbind modes)
   const int *ids;        // Elist pid per slot
@@ -149,16 +149,41 @@ struct WalkArgs
 constexpr int kWalkCounters = 4;
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 // Walk classes.  A segment belongs to one class; every class has its own warp numbering (warp_off) and launch.
-constexpr int kWalkGroup4 = 104, kWalkGroup8 = 108; // group walk with 128 / 256 targets per warp
-constexpr int kWalkClasses = 4;
+constexpr int kWalkGroup2 = 102, kWalkGroup4 = 104; // masked group walk with 64 / 128 targets per warp
+constexpr int kWalkSmall = 201;                     // small-subhalo kernel (walk_small.cu): 32 targets per warp, dense sweep of the whole tree
+constexpr int kWalkClasses = 5;
 struct WalkClass
 {
   int index;            // 0..kWalkClasses-1
   int targets_per_lane; // value for WalkArgs::targets_per_lane
   int targets_per_warp;
 };
-// class used for a segment with tgt_n targets (env HBTU_WALK_TPL / HBTU_WALK_BIG* / HBTU_WALK_GROUP* override)
-WalkClass walk_class(int tgt_n);
-int walk_class_tpl(int index); // targets_per_lane value of class `index` (the group class depends on the environment)
+// class used for a segment with tgt_n targets over a tree of tree_n sources (walk_tuning() decides)
+WalkClass walk_class(int tgt_n, int tree_n);
+int walk_class_tpl(int index); // targets_per_lane value of class `index` (the group class depends on the tuning)
+
+// kernel routing knobs (process-wide; defaults = measured best, HBTU_* environment variables and hbtu_set_tuning override)
+#ifndef HBT_MASKED_DEFAULT_PAIRS
+#define HBT_MASKED_DEFAULT_PAIRS 2
+#endif
+#ifndef HBT_MASKED_DEFAULT_BLOCKS_NP2
+#define HBT_MASKED_DEFAULT_BLOCKS_NP2 5
+#endif
+#ifndef HBT_MASKED_DEFAULT_BLOCKS_NP1
+#define HBT_MASKED_DEFAULT_BLOCKS_NP1 8
+#endif
+#ifndef HBT_SMALL_DEFAULT_MAX
+#define HBT_SMALL_DEFAULT_MAX 0
+#endif
+struct WalkTuning
+{
+  int forced_tpl;    // HBTU_WALK_TPL: force the per-lane walk with 1, 2 or 4 targets per lane for every segment (0 = off)
+  int big4, big2;    // per-lane walk: segments with at least this many targets take 4 / 2 targets per lane
+  int group_min;     // HBTU_WALK_GROUP_MIN: segments with at least this many targets use the masked group walk (0 = never)
+  int masked_pairs;  // HBTU_WALK_MASKED_PAIRS: slice pairs per warp of the masked walk (1: 64-target groups, 2: 128-target groups)
+  int masked_blocks; // HBTU_WALK_MASKED_BLOCKS: resident CTAs per SM the masked kernel variant is compiled for
+  int small_max;     // HBTU_WALK_SMALL_MAX: segments with at most this many tree sources use the small-subhalo kernel (0 = never)
+};
+WalkTuning &walk_tuning();
 
 } // namespace hbt

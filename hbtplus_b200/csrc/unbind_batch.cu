@@ -743,7 +743,7 @@ static void run_round(Context &c, std::vector<int> &active)
   // walk warps per walk class (device_tree.cuh: T=1, 2, 4 per-lane walks and the group walk); a segment belongs to one class
   std::vector<int> warp_off[kWalkClasses];
   for (auto &v : warp_off) v.resize(nseg + 1);
-  int64_t S = 0, T = 0, W[kWalkClasses] = {0, 0, 0, 0};
+  int64_t S = 0, T = 0, W[kWalkClasses] = {};
   bool any_hoare = false;
   for (int a = 0; a < nseg; a++)
   {
@@ -777,7 +777,7 @@ static void run_round(Context &c, std::vector<int> &active)
     sg.tgt_n = h.nbound;
     sg.tree_off = (int)S;
     sg.tgt_off = (int)T;
-    const WalkClass wcl = walk_class(sg.tgt_n);
+    const WalkClass wcl = walk_class(sg.tgt_n, sg.tree_n);
     const int cls = wcl.index;
     sg.warp_off = (int)W[cls];
     tree_off[a] = (int)S;

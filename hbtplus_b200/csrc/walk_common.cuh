@@ -1,4 +1,4 @@
-// walk_common.cuh - helpers shared by the walk kernels (walk.cu: per-lane pre-order walk, walk_group.cu: group walk).
+// walk_common.cuh - helpers shared by the walk kernels (walk.cu: per-lane pre-order walk, walk_masked.cu: masked group walk).
 #pragma once
 #include "device_tree.cuh"
 
@@ -295,8 +295,8 @@ __device__ __forceinline__ int segment_of_warp(const int *__restrict__ warp_off,
   return lo;
 }
 
-// walk_group.cu
-void launch_walk_group(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
+// walk_small.cu
+void launch_walk_small(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 // walk_masked.cu
 void launch_walk_masked(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 

@@ -294,6 +294,12 @@ int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted
  * interactions and warp node visits into hbtu_stats (costs a few percent; off by default). */
 int hbtu_set_counting(hbtu_ctx *ctx, int on);
+/* diagnostics (no reference counterpart): process-wide kernel-routing knobs of the walk ("walk_group_min", "walk_masked_pairs",
+ * "walk_masked_blocks", "walk_tpl", "walk_big2", "walk_big4", "walk_small_max"; defaults = measured best, also settable
+ * through HBTU_WALK_* environment variables read at the first use).  Results do not depend on them beyond fp64 summation
+ * order.  hbtu_get_tuning returns -1 for an unknown key. */
+int hbtu_set_tuning(const char *key, int64_t value);
+int64_t hbtu_get_tuning(const char *key);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ using hbt::float_to_ordered;
 using hbt::ordered_to_float;
 static int g_max_ncs = 0;
 static int64_t g_hist[8];
+#define HBT_MASKED_STAT_ON 1
 #define HBT_MASKED_STAT(what, n) do { if (wemu::g_cur == 0) g_hist[what] += (n); } while (0)
 #define HBT_MASKED_TRACK(ncs) do { if ((ncs) > g_max_ncs) g_max_ncs = (ncs); } while (0)
 #include "walk_masked.cuh"
@@ -15,11 +16,16 @@ static int64_t g_hist[8];
 #ifndef EMUL_STACK
 #define EMUL_STACK 184
 #endif
-typedef hbt::MaskedSmemT<EMUL_STACK> SmemT;
+#ifndef EMUL_NP
+#define EMUL_NP 2 // slice pairs per warp: 1 = 64-target groups, 2 = 128-target groups
+#endif
+typedef hbt::MaskedSmemT<EMUL_STACK, EMUL_NP> SmemT;
+static constexpr int kT = 2 * EMUL_NP, kGroup = 32 * kT;
+extern "C" int emul_group_size(void) { return kGroup; }
 
 extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *src, int64_t ntgt_in, int64_t group_stride, double *sum_masked, double *sum_scalar,
                                 int64_t *acc_masked, int64_t *acc_scalar, int64_t *stats /*[4]: overflows, iterations, collectives, groups*/)
-{ // targets = the sources in key order (a full evaluation), groups of 128 consecutive targets; only the first ntgt_in
+{ // targets = the sources in key order (a full evaluation), groups of kGroup (64 or 128) consecutive targets; only the first ntgt_in
   // targets, and of those only every group_stride-th group, are walked (the others keep their zeros)
   std::vector<Node> nodes;
   std::vector<float> sp;
@@ -42,19 +48,19 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
   struct Guarded { uint64_t c0[8]; SmemT sm; uint64_t c1[8]; };
   static Guarded g;
   if (group_stride < 1) group_stride = 1;
-  for (int64_t g0 = 0; g0 < ntgt; g0 += 128 * group_stride)
+  for (int64_t g0 = 0; g0 < ntgt; g0 += kGroup * group_stride)
   {
-    const int n0 = (int)std::min<int64_t>(128, ntgt - g0);
+    const int n0 = (int)std::min<int64_t>(kGroup, ntgt - g0);
     for (int q = 0; q < 8; q++) g.c0[q] = g.c1[q] = 0x5a5a5a5a5a5a5a5aull;
     memset(&g.sm, 0xff, sizeof(g.sm));
     bool ok_all = true;
     unsigned vis_lane0 = 0;
     groups++;
     wemu::run_warp([&](int lane) {
-      float px[4], py[4], pz[4];
-      bool valid[4];
+      float px[kT], py[kT], pz[kT];
+      bool valid[kT];
       const float *r = &sp[4 * g0];
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < kT; k++)
       {
         const int j = lane + 32 * k;
         valid[k] = j < n0;
@@ -68,7 +74,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
           if (az > half) pz[k] = t[2] - box; else if (az < -half) pz[k] = t[2] + box;
         }
       }
-      double accd[4] = {0, 0, 0, 0};
+      double accd[kT] = {};
       unsigned long long nacc = 0;
       unsigned n_acc = 0, n_vis = 0;
       bool ok;
@@ -78,7 +84,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
         ok = hbt::masked_group_walk<false, true>(g.sm, lane, node_xm.data(), node_aux.data(), 0, (int)nn, px, py, pz, valid, n0, box, half, eps, accd, nacc, n_acc, n_vis);
       if (!ok) ok_all = false;
       if (lane == 0) vis_lane0 = n_vis;
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < kT; k++)
         if (valid[k])
         {
           sum_masked[g0 + lane + 32 * k] = accd[k];
@@ -97,7 +103,7 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
   // scalar per-target walk, same fp32 arithmetic (FMUL, FFMA, FFMA; criterion on the fp32 r^2)
   for (int64_t t = 0; t < ntgt; t++)
   {
-    if ((t / 128) % group_stride != 0) continue;
+    if ((t / kGroup) % group_stride != 0) continue;
     const float px = sp[4 * t], py = sp[4 * t + 1], pz = sp[4 * t + 2];
     double pot = 0;
     int64_t acc = 0, no = 0;

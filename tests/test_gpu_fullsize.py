@@ -25,12 +25,10 @@ def test_full_size_properties(make_ctx):
     import bench
     import cases_bench
 
-    P = 1.8e8
-    sizes, parent = bench.workload_sizes(P, bench.SEED)
-    snap = synth.make_snapshot_torch(sizes, device=torch.device("cuda", 0), seed=bench.SEED, box_size=bench.BOX, particle_mass=1e-6, parent=parent,
-                                     centre=[bench.BOX / 2] * 3, wrap=False, pin=False)
+    wl = bench.WORKLOADS["cfg2"]
+    snap = wl.make(1.8e8, torch.device("cuda", 0), 0)
     torch.cuda.empty_cache()
-    p = bench.params_for(0)
+    p = wl.params(0)
     e = capi.make_epoch(1.0)
     ctx = make_ctx(p)
     ctx.stage(e, snap, capi.HBTU_FLAG_TRUNCATE_SOURCE)
@@ -78,7 +76,7 @@ def test_full_size_properties(make_ctx):
     # checksum of checksums
     top = (par < 0) & big
     com = (io["avg_pos"][top] * io["mbound"][top, None]).sum(0) / io["mbound"][top].sum()
-    assert np.all(np.abs(com - bench.BOX / 2) < 0.05)
+    assert np.all(np.abs(com - wl.box / 2) < 0.05)
     # repeatability
     ctx.execute()
     r2 = ctx.fetch(want_energy=True)

@@ -295,11 +295,12 @@ def test_multi_target_walk_variants(tpl, tmp_path):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("masked", [1, 0])
-def test_group_walk_kernels_on_every_segment(masked):
-    """Every segment forced through the 128-target group kernels (HBTU_WALK_GROUP_MIN=1): the masked group walk
-    (walk_masked.cu, the shipped kernel for segments >= 8192 targets) and its predecessor walk_group.cu; the device-counted
-    accepted interactions must equal the oracle's, i.e. every target takes the reference's decisions."""
+@pytest.mark.parametrize("route", ["masked128", "masked64", "small"])
+def test_forced_walk_kernels_on_every_segment(route):
+    """Every segment forced through ONE kernel family: the masked group walk with 128-target groups (HBTU_WALK_GROUP_MIN=1; the
+    kernel of segments >= 8192 targets), the same with 64-target groups (HBTU_WALK_MASKED_PAIRS=1), and the small-subhalo
+    kernel (HBTU_WALK_SMALL_MAX huge: the dense sweep on every tree).  The device-counted accepted interactions must equal
+    the oracle's, i.e. every target takes the reference's decisions under every routing."""
     code = (
         "import sys, numpy as np\n"
         f"sys.path[:0] = [{os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}, {os.path.dirname(os.path.abspath(__file__))!r}]\n"
@@ -322,7 +323,10 @@ def test_group_walk_kernels_on_every_segment(masked):
         "    assert st.walk_fallbacks == 0, name\n"
         "print('OK')\n"
     )
-    env = dict(os.environ, HBTU_WALK_GROUP_MIN="1", HBTU_WALK_MASKED=str(masked))
+    extra = {"masked128": {"HBTU_WALK_GROUP_MIN": "1", "HBTU_WALK_MASKED_PAIRS": "2", "HBTU_WALK_SMALL_MAX": "0"},
+             "masked64": {"HBTU_WALK_GROUP_MIN": "1", "HBTU_WALK_MASKED_PAIRS": "1", "HBTU_WALK_SMALL_MAX": "0"},
+             "small": {"HBTU_WALK_SMALL_MAX": "1000000000"}}[route]
+    env = dict(os.environ, **extra)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 

@@ -18,11 +18,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["onepass", "splitx"])
+@pytest.fixture(scope="module", params=[2, 1], ids=["groups128", "groups64"])
 def memul(request, tmp_path_factory):
-    """both layouts of the deciding lists (HBT_M_SPLITX, walk_masked.cuh)"""
+    """both group sizes of the masked walk: two slice pairs per warp (128 targets) and one (64 targets)"""
     out = tmp_path_factory.mktemp("memul") / f"libmaskedemul{request.param}.so"
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", f"-DHBT_M_SPLITX={request.param}",
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", f"-DEMUL_NP={request.param}",
                            "-I", os.path.join(ROOT, "hbtplus_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
                            os.path.join(HERE, "host_emul", "masked_emul.cpp"), "-o", str(out)])
     return C.CDLL(str(out))
@@ -41,10 +41,11 @@ def run(memul, p, pm, ntgt, stride=1):
     return sm, ss, am, asc, stats
 
 
-def per_lane(a, ntgt):
-    """sum over the (up to 4) targets of every lane of every group"""
-    pad = (-ntgt) % 128
-    return np.concatenate([a, np.zeros(pad, a.dtype)]).reshape(-1, 4, 32).sum(axis=1)
+def per_lane(a, ntgt, memul):
+    """sum over the (2 or 4) targets of every lane of every group"""
+    g = memul.emul_group_size()
+    pad = (-ntgt) % g
+    return np.concatenate([a, np.zeros(pad, a.dtype)]).reshape(-1, g // 32, 32).sum(axis=1)
 
 
 @pytest.mark.parametrize("periodic", [False, True])
@@ -58,9 +59,9 @@ def test_masked_walk_reproduces_every_targets_decisions(memul, n, periodic):
     assert stats[0] == 0  # no stack overflow
     if periodic:  # shifted images round differently from NEAREST(dx): a decision may flip where r^2 straddles the criterion
         assert abs(int(am.sum()) - int(asc.sum())) <= 1e-4 * asc.sum() + 2
-        assert np.mean(per_lane(am, ntgt) == per_lane(asc, ntgt)) > 0.98
+        assert np.mean(per_lane(am, ntgt, memul) == per_lane(asc, ntgt, memul)) > 0.98
     else:
-        assert np.array_equal(per_lane(am, ntgt), per_lane(asc, ntgt))
+        assert np.array_equal(per_lane(am, ntgt, memul), per_lane(asc, ntgt, memul))
     # periodic: the group's common image is more accurate than NEAREST(dx) of a wrapped pair (ulp(62) = 4e-6 against
     # pair distances of 1e-2); the same holds for walk_group.cu's dense ring
     assert np.allclose(sm, ss, rtol=5e-5 if periodic else 2e-6, atol=0)
@@ -75,7 +76,7 @@ def test_masked_walk_softened_and_colocated(memul):
     pm[200:203, :3] = pm[200, :3] + np.float32(1e-7)
     sm, ss, am, asc, stats = run(memul, p, pm, 3000)
     assert stats[0] == 0
-    assert np.array_equal(per_lane(am, 3000), per_lane(asc, 3000))
+    assert np.array_equal(per_lane(am, 3000, memul), per_lane(asc, 3000, memul))
     assert np.allclose(sm, ss, rtol=2e-6, atol=0)
 
 
@@ -86,7 +87,7 @@ def test_masked_walk_dense_core(memul):
     pm = np.ascontiguousarray(snap.pos_mass)
     sm, ss, am, asc, stats = run(memul, p, pm, 200000, stride=97)  # 17 groups across the whole halo
     assert stats[0] == 0
-    assert asc.sum() > 0 and np.array_equal(per_lane(am, 200000), per_lane(asc, 200000))
+    assert asc.sum() > 0 and np.array_equal(per_lane(am, 200000, memul), per_lane(asc, 200000, memul))
     assert np.allclose(sm, ss, rtol=2e-6, atol=0)
 
 
@@ -100,7 +101,7 @@ def test_masked_walk_clumpy_tree(memul):
     n = len(pm)
     sm, ss, am, asc, stats = run(memul, p, pm, n, stride=41)  # 27 groups across the key range
     assert stats[0] == 0
-    assert asc.sum() > 0 and np.array_equal(per_lane(am, n), per_lane(asc, n))
+    assert asc.sum() > 0 and np.array_equal(per_lane(am, n, memul), per_lane(asc, n, memul))
     assert np.allclose(sm, ss, rtol=2e-6, atol=0)
 
 

@@ -345,3 +345,41 @@ def test_plain_unbind_flag_oracle_matches_reference(oracle_lib, ref_lib):
     with pytest.raises(RuntimeError):
         po.run_batch(ref_lib, "hbtref", p, e, nested)
     oracle_lib.hbto_set_num_threads(8)
+
+
+def _direct_sum(pm, eps, G, a):
+    """Exact pairwise potential with the reference's spline softening (src/gravity_tree.cpp:141-163) and its self-term rule."""
+    x = pm[:, :3].astype(np.float64)
+    m = pm[:, 3].astype(np.float64)
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt((d * d).sum(-1))
+    h = 2.8 * eps
+    u = r / h
+    with np.errstate(divide="ignore", invalid="ignore"):
+        wp_in = -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6))
+        wp_out = -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)))
+        g = np.where(r >= h, -1.0 / r, np.where(u < 0.5, wp_in, wp_out) / h)
+    pot = (g * m[None, :]).sum(1) + m / eps  # the walk includes the target itself (-2.8 m/h = -m/eps) and cancels it (:98)
+    return pot * G / a
+
+
+@pytest.mark.parametrize("n", [100, 1000])
+def test_direct_sum_vs_reference_tree(oracle_lib, ref_lib, n):
+    """Pins DESIGN.md section 3: the reference's theta = 0.45 monopole tree differs from the exact direct sum by more than the
+    1e-3 per-particle parity gate, already for subhaloes of 100 particles.  So the north star's "direct-sum tile kernel for
+    small subhaloes" cannot meet the north star's own gate against the reference; the small-subhalo kernel (walk_small.cu)
+    therefore sweeps the reference's TREE with the reference's per-target decisions instead."""
+    p = capi.make_params(box_size=250.0, softening=2.1e-3, periodic=False)  # SURVEY 8(d) cfg 5
+    e = capi.make_epoch(1.0)
+    worst, mean = 0.0, 0.0
+    for seed in range(5):
+        snap = synth.make_snapshot([n], seed=40 + seed, box_size=250.0, wrap=False, centre=[125.0] * 3)
+        pm = snap.pos_mass
+        tree = po.tree_potential(ref_lib, "hbtref", p, e, pm, pm, self_mass=pm[:, 3].copy())
+        assert np.array_equal(tree, po.tree_potential(oracle_lib, "hbto", p, e, pm, pm, self_mass=pm[:, 3].copy()))
+        exact = _direct_sum(pm, p.softening_halo, p.G, e.scale_factor)
+        rel = np.abs(tree - exact) / np.abs(exact)
+        worst, mean = max(worst, float(rel.max())), mean + float(rel.mean()) / 5
+    print(f"n={n}: reference tree vs exact direct sum: max rel. deviation {worst:.2e}, mean {mean:.2e}")
+    assert worst > 1e-3      # a direct sum would fail the 1e-3 gate against the reference
+    assert mean < 5e-3       # ... while the tree is of course a decent approximation of the sum
