@@ -380,6 +380,66 @@ def bench_idtable_row(ctx, n, n_cpu, peaks):
     return row
 
 
+def bench_dropin_row(wl, particles, dev, csnap, cpu_threads):
+    """The metric as SURVEY.md 8(d) defines it: wall time of SubhaloSnapshot_t::RefineParticles() itself on an in-memory
+    SubhaloSnapshot_t (vector<Particle_t> per subhalo) through the drop-in seam - libhbtdropin_v32.so = the reference's own
+    objects with subhalo_unbind.o replaced by integration/subhalo_unbind_b200.o.  Inside the timed call: AoS -> pinned SoA pack
+    (OpenMP), H2D, all kernels, D2H, the permutation of every vector<Particle_t>.  Beside it: the reference's own
+    RefineParticles (libhbtref_v32.so) on the CPU sample, timed the same way."""
+    from oracle import pyoracle as po
+
+    if not po.have_dropin("v32"):
+        return {"unavailable": "oracle/_ref/libhbtdropin_v32.so not built"}
+    drop = po.load_dropin("v32")
+    drop.hbtref_set_num_threads(cpu_threads)
+    snap = wl.make(particles, dev, 7)
+    nsub = snap.nsub
+    roots = np.ones(nsub, bool)
+    if snap.nest_list is not None:
+        roots[snap.nest_list] = False
+    # every root is the central of its own host halo; nested subhaloes are its old nests (src/subhalo_unbind.cpp:479-493)
+    root_of = np.arange(nsub)
+    if snap.nest_offset is not None:
+        parent = np.full(nsub, -1, np.int64)
+        for s in range(nsub):
+            parent[snap.nest_list[snap.nest_offset[s]:snap.nest_offset[s + 1]]] = s
+        order = np.argsort(-np.diff(snap.part_offset), kind="stable")
+        for s in order:  # parents are larger: they come first
+            if parent[s] >= 0:
+                root_of[s] = root_of[parent[s]]
+    halo_index = {int(r): i for i, r in enumerate(np.nonzero(roots)[0])}
+    host = np.array([halo_index[int(r)] for r in root_of], np.int32)
+    mb = np.diff(snap.part_offset).astype(np.float32)
+    e = capi.make_epoch(1.0)
+    secs = []
+    for _ in range(3):  # the first call pays the page-locking of the pinned staging buffers
+        r = po.refine_particles(drop, wl.params(0), e, snap, host, nsub, len(halo_index), mb)
+        secs.append(r.refine_seconds)
+    row = {"api": "SubhaloSnapshot_t::RefineParticles() via libhbtdropin_v32.so", "particles": int(snap.npart), "subhaloes": int(nsub),
+           "seconds_first_call": secs[0], "seconds": float(np.min(secs[1:])), "value": snap.npart / float(np.min(secs[1:])), "unit": UNIT,
+           "host_threads": cpu_threads, "sum_nbound": int(r.io["nbound"].sum())}
+    if po.have_ref():
+        ref = po.load_ref()
+        ref.hbtref_set_num_threads(cpu_threads)
+        croots = np.ones(csnap.nsub, bool)
+        if csnap.nest_list is not None:
+            croots[csnap.nest_list] = False
+        cparent = np.full(csnap.nsub, -1, np.int64)
+        if csnap.nest_offset is not None:
+            for s in range(csnap.nsub):
+                cparent[csnap.nest_list[csnap.nest_offset[s]:csnap.nest_offset[s + 1]]] = s
+        croot_of = np.arange(csnap.nsub)
+        for s in np.argsort(-np.diff(csnap.part_offset), kind="stable"):
+            if cparent[s] >= 0:
+                croot_of[s] = croot_of[cparent[s]]
+        cidx = {int(r_): i for i, r_ in enumerate(np.nonzero(croots)[0])}
+        chost = np.array([cidx[int(r_)] for r_ in croot_of], np.int32)
+        cr = po.refine_particles(ref, wl.params(0), e, csnap, chost, csnap.nsub, len(cidx), np.diff(csnap.part_offset).astype(np.float32))
+        row["reference"] = {"api": "the reference's own SubhaloSnapshot_t::RefineParticles() (libhbtref_v32.so)", "particles": int(csnap.npart),
+                            "seconds": cr.refine_seconds, "value": csnap.npart / cr.refine_seconds, "unit": UNIT, "host_threads": cpu_threads}
+    return row
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -444,6 +504,7 @@ def main():
     ap.add_argument("--particles", type=float, default=None, help="particles per GPU (default: the configuration's full size; cfg2: 1.8e8)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="particles in the bounded CPU sample (10-30 s on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps)")
+    ap.add_argument("--dropin-particles", type=float, default=4e7, help="size of the in-memory SubhaloSnapshot_t of the drop-in e2e row (RefineParticles via libhbtdropin)")
     ap.add_argument("--profile", action="store_true", help="for ncu: no counting pass, no e2e, no CPU leg (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -604,7 +665,11 @@ def main():
             dt, kind, ncpu, _, cres = run_cpu(csnap, workload=wl.name)
             out["cpu_baseline"] = {"value": csnap.npart / dt, "unit": UNIT, "cores": ncpu, "kind": kind, "sample": desc, "seconds": dt}
             out["parity"] = parity_block(ctx, e, csnap, cres, kind, workload=wl.name)
+            ctx.close()  # free the HBM of the timed batch: the drop-in row brings its own context
+            out["e2e"]["drop_in"] = bench_dropin_row(wl, min(args.particles, args.dropin_particles), dev, csnap, ncpu)
+            ctx = UnbindContext(wl.params(local_rank))
             if wl.name == "cfg2":
+                res = ctx.unbind_batch(e, snap, flags=flags, want_energy=False, order_buf=order_pinned)
                 out["config"]["next_rows"] = {"profile_properties": bench_profile_row(ctx, e, snap, res, csnap, peaks),
                                               "mask_subhalos": bench_mask_row(ctx, snap, csnap, peaks),
                                               "particle_query": bench_idtable_row(ctx, snap.npart, csnap.npart, peaks)}

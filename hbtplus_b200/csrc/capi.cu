@@ -113,8 +113,12 @@ void build_forest(Context &c, int64_t nsub, const int64_t *part_offset, const in
   if (slot > 0x7fffffff00ll) throw CudaError{HBTU_ERR_UNSUPPORTED, "batch too large"};
 }
 
+// overlap == false: hbtu_stage, returns when everything is in HBM.  overlap == true (hbtu_unbind_batch): the particle arrays
+// travel on the copy stream in two waves - first everything except the dominant root subhalo (the source that holds more
+// than a quarter of the batch: an AqA2 central), then that root, which the level-synchronous scheduler reaches last - and
+// execute_batch waits for each wave only where it is first needed, so the big upload hides behind the deeper levels' rounds.
 void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, const float *vel,
-           const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags)
+           const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags, bool overlap = false)
 {
   if (!epoch || nsub < 0 || !part_offset || (nsub > 0 && !io)) throw CudaError{HBTU_ERR_INVALID, "null argument"};
   if (nsub > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
@@ -155,23 +159,50 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
     grow(c.d_slot_base, cap2, nsub + 1);
     c.cap_subs = cap0;
   }
-  HBT_CUDA(cudaEventRecord(c.ev[0], st));
-  if (N > 0)
-  {
-    HBT_CUDA(cudaMemcpyAsync(c.d_pos, pos_mass, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
-    HBT_CUDA(cudaMemcpyAsync(c.d_vel, vel, sizeof(float4) * (size_t)N, cudaMemcpyHostToDevice, st));
-  }
   std::vector<int64_t> sb((size_t)nsub + 1, 0);
   for (int64_t s = 0; s < nsub; s++) sb[s] = c.subs[s].slot_base;
   sb[nsub] = c.total_cap;
   HBT_CUDA(cudaMemcpyAsync(c.d_part_offset, part_offset, sizeof(int64_t) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
   HBT_CUDA(cudaMemcpyAsync(c.d_slot_base, sb.data(), sizeof(int64_t) * (size_t)(nsub + 1), cudaMemcpyHostToDevice, st));
-  HBT_CUDA(cudaEventRecord(c.ev[1], st));
-  HBT_CUDA(cudaStreamSynchronize(st));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
-  c.stats.h2d_ms = ms;
+  HBT_CUDA(cudaStreamSynchronize(st)); // `sb` is a local; also orders the (re)allocations above before the copy stream's work
+  auto copy_range = [&](cudaStream_t cs, int64_t b, int64_t e) {
+    if (e <= b) return;
+    HBT_CUDA(cudaMemcpyAsync(c.d_pos + b, pos_mass + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs));
+    HBT_CUDA(cudaMemcpyAsync(c.d_vel + b, vel + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs));
+  };
   c.stats.h2d_bytes = N * 32 + (nsub + 1) * 16;
+  c.waves_pending = false;
+  c.staged_async = overlap;
+  if (!overlap)
+  {
+    HBT_CUDA(cudaEventRecord(c.ev[0], st));
+    copy_range(st, 0, N);
+    HBT_CUDA(cudaEventRecord(c.ev[1], st));
+    HBT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+    c.stats.h2d_ms = ms;
+  }
+  else
+  {
+    int64_t big = -1; // the dominant root, if any
+    for (int64_t s = 0; s < nsub; s++)
+      if (c.subs[s].parent < 0 && c.subs[s].n_own > N / 4 && (big < 0 || c.subs[s].n_own > c.subs[big].n_own)) big = s;
+    if (c.max_depth == 0 || N < (1 << 20)) big = -1; // nothing to hide the upload behind
+    cudaStream_t cs = c.copy_stream;
+    HBT_CUDA(cudaEventRecord(c.ev_copy0, cs));
+    if (big < 0)
+      copy_range(cs, 0, N);
+    else
+    {
+      copy_range(cs, 0, part_offset[big]);
+      copy_range(cs, part_offset[big + 1], N);
+    }
+    HBT_CUDA(cudaEventRecord(c.ev_wave[0], cs));
+    if (big >= 0) copy_range(cs, part_offset[big], part_offset[big + 1]);
+    HBT_CUDA(cudaEventRecord(c.ev_wave[1], cs));
+    c.waves_pending = true;
+  }
   c.staged = true;
 }
 
@@ -383,6 +414,9 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
   c.cfg.scale_factor = 1.f;
   int rc = guarded(ctx, [&](Context &cc) {
     HBT_CUDA(cudaStreamCreateWithFlags(&cc.stream, cudaStreamNonBlocking));
+    HBT_CUDA(cudaStreamCreateWithFlags(&cc.copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : cc.ev_wave) HBT_CUDA(cudaEventCreate(&ev));
+    HBT_CUDA(cudaEventCreate(&cc.ev_copy0));
     for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
     for (auto &ev : cc.ev_exec) HBT_CUDA(cudaEventCreate(&ev));
     HBT_CUDA(cudaMalloc(&cc.d_counters, kWalkCounters * sizeof(unsigned long long)));
@@ -402,6 +436,7 @@ void hbtu_destroy(hbtu_ctx *ctx)
   if (!ctx) return;
   Context &c = ctx->c;
   cudaSetDevice(c.device);
+  if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
   if (c.stream) cudaStreamSynchronize(c.stream);
   c.arena.release();
   cudaFree(c.d_pos);
@@ -419,6 +454,10 @@ void hbtu_destroy(hbtu_ctx *ctx)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c.ev_exec)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c.ev_wave)
+    if (ev) cudaEventDestroy(ev);
+  if (c.ev_copy0) cudaEventDestroy(c.ev_copy0);
+  if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;
 }
@@ -458,11 +497,33 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
                       const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_sub_io *io, int32_t flags,
                       int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
 {
-  int rc = hbtu_stage(ctx, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags);
-  if (rc != HBTU_OK) return rc;
-  rc = hbtu_execute(ctx);
-  if (rc != HBTU_OK) return rc;
+  // stage with the uploads on the copy stream (they overlap the kernels of the deeper nesting levels when the source arrays
+  // are pinned - hbtu_host_alloc - and are plain staged copies otherwise), then execute + fetch
+  int rc = guarded(ctx, [&](Context &c) { stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags, true); });
+  if (rc == HBTU_OK) rc = hbtu_execute(ctx);
+  if (rc != HBTU_OK)
+  { // never leave copies from the caller's buffers in flight behind an error return
+    if (ctx) cudaStreamSynchronize(ctx->c.copy_stream);
+    return rc;
+  }
   return hbtu_fetch(ctx, io, order_capacity, order_offset, order_out, energy_out);
+}
+
+/* Pinned host memory for the caller's staging arrays (pos_mass / vel / order_out): with it the uploads of hbtu_unbind_batch
+ * are true asynchronous DMA that overlaps the kernels; any other host memory works too, just slower. */
+void *hbtu_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void hbtu_host_free(void *p)
+{
+  if (p) cudaFreeHost(p);
 }
 
 int hbtu_tree_potential(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsrc, const float *src_pos_mass, int64_t ntgt,

@@ -23,6 +23,11 @@ struct Context
   DevConfig cfg{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                 // uploads that run behind the kernels of the deeper nesting levels
+  cudaEvent_t ev_wave[2] = {nullptr, nullptr};        // [0]: everything but the dominant root is in HBM, [1]: the dominant root too
+  cudaEvent_t ev_copy0 = nullptr;                     // start of the uploads on copy_stream (h2d_ms)
+  bool staged_async = false;                          // ... and its h2d_ms is read from the copy stream's events after the execution
+  bool waves_pending = false;                         // the staged batch was uploaded asynchronously (hbtu_unbind_batch)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_exec[2] = {nullptr, nullptr};
   std::string last_error;
@@ -52,6 +57,11 @@ struct Context
   int64_t idt_n = 0;
   unsigned long long *d_counters = nullptr;
   bool count_interactions = false;
+
+  // target split of the walk across cooperating contexts (hbtu_set_walk_split / hbtu_split_group_*)
+  int split_rank = 0, split_n = 1;
+  hbtu_allreduce_fn split_fn = nullptr;
+  void *split_user = nullptr;
 
   Arena arena;
   LaunchStats ls;

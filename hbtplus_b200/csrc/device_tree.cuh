@@ -145,7 +145,24 @@ struct WalkArgs
   float *out_f;          // kWalkRefine: per target
   float ref_pos[3], ref_vel[3]; // kWalkBindingEnergy frame
   unsigned long long *counters; // [kWalkCounters]: accepted interactions, warp node visits, groups redone per lane (nullptr = do not count)
+  // target split of the walk over cooperating contexts (the non-natural case): this context walks the CTAs
+  // whose 16-CTA chunk index is congruent to split_rank modulo split_n and writes the new energies to E_stage[t] (T-order,
+  // zero elsewhere) instead of E[slot]; a sum all-reduce over the contexts then completes E_stage everywhere
+  int split_rank, split_n;
+  float *E_stage;
 };
+// global CTA index of a walk kernel's block under the target split (identity without it), and the grid that covers `ctas` of them
+__device__ __forceinline__ int walk_cta(const WalkArgs &a)
+{
+  return a.split_n > 1 ? ((((int)blockIdx.x >> 4) * a.split_n + a.split_rank) << 4) + ((int)blockIdx.x & 15) : (int)blockIdx.x;
+}
+inline int walk_grid(const WalkArgs &a, int ctas)
+{
+  if (a.split_n <= 1) return ctas;
+  const int chunks = (ctas + 15) >> 4;                       // 16-CTA chunks in all
+  const int mine = (chunks - a.split_rank + a.split_n - 1) / a.split_n; // chunks split_rank, split_rank + split_n, ...
+  return mine << 4;
+}
 constexpr int kWalkCounters = 4;
 void launch_walk(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls);
 // Walk classes.  A segment belongs to one class; every class has its own warp numbering (warp_off) and launch.

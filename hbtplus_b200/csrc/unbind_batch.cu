@@ -659,6 +659,14 @@ __global__ void __launch_bounds__(kBlock) kinematics_kernel(const Segment *__res
   seg_reduce_chunk<6>(v, partial);
 }
 
+// target split: E_stage (target order, summed over the cooperating contexts) -> E[slot]
+__global__ void __launch_bounds__(kBlock) scatter_stage_kernel(const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ stage,
+                                                                float *__restrict__ E)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) E[tgt_slot[t]] = stage[t];
+}
+
 struct RoundResult
 {
   int status, nbound, nlast, correction;
@@ -794,7 +802,7 @@ static void run_round(Context &c, std::vector<int> &active)
 
   Arena &ar = c.arena;
   ar.reset();
-  ar.reserve(tree_arena_bytes(S, nseg) + T * 64 + (int64_t)nseg * 128);
+  ar.reserve(tree_arena_bytes(S, nseg) + T * 68 + (int64_t)nseg * 128);
   cudaStream_t st = c.stream;
   Segment *d_segs = upload(ar, segs, st);
   int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st);
@@ -855,12 +863,30 @@ static void run_round(Context &c, std::vector<int> &active)
   wa.subs = c.d_subs;
   wa.out = nullptr;
   wa.counters = c.count_interactions ? c.d_counters : nullptr;
+  const bool split = c.split_n > 1 && c.split_fn != nullptr;
+  float *e_stage = nullptr;
+  if (split)
+  { // this context walks its share of the CTAs and writes E in target order; the others' entries stay zero until the all-reduce
+    e_stage = ar.alloc<float>(T);
+    HBT_CUDA(cudaMemsetAsync(e_stage, 0, sizeof(float) * (size_t)T, st));
+    wa.split_rank = c.split_rank;
+    wa.split_n = c.split_n;
+    wa.E_stage = e_stage;
+  }
   for (int q = kWalkClasses - 1; q >= 0; q--)
   { // largest segments first: their long-running warps start while the small classes fill the tail
     wa.warp_off = d_warp_off[q];
     wa.nwarps = (int)W[q];
     wa.targets_per_lane = walk_class_tpl(q);
     launch_walk(wa, c.cfg, st, c.ls);
+  }
+  if (split)
+  {
+    HBT_CUDA(cudaStreamSynchronize(st)); // the exchange may run on another stream (NCCL through the caller's runtime)
+    if (c.split_fn(c.split_user, e_stage, T, (void *)st) != 0) throw CudaError{HBTU_ERR_CUDA, "walk split: the all-reduce callback failed"};
+    scatter_stage_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_slot, (int)T, e_stage, c.d_E);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches++;
   }
   HBT_CUDA(cudaEventRecord(c.ev[2], st));
 
@@ -1157,8 +1183,16 @@ void execute_batch(Context &c)
   }
   HBT_CUDA(cudaStreamSynchronize(st));
 
+  // asynchronous staging (hbtu_unbind_batch): the first wave of the upload is needed by the first round, the dominant root only
+  // by level 0; a re-execution of the same staged batch finds both events completed
+  if (c.waves_pending) HBT_CUDA(cudaStreamWaitEvent(st, c.ev_wave[0], 0));
   for (int level = c.max_depth; level >= 0; level--)
   {
+    if (level == 0 && c.waves_pending)
+    {
+      HBT_CUDA(cudaStreamWaitEvent(st, c.ev_wave[1], 0));
+      c.waves_pending = false;
+    }
     const std::vector<int> &lv = c.levels[level];
     const int64_t M = c.cfg.max_sample;
     c.arena.reset(); // the previous level's rounds are over: the arena holds this level's small job tables until its first round
@@ -1329,6 +1363,12 @@ void execute_batch(Context &c)
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
     c.stats.execute_ms = ms;
+  }
+  if (c.staged_async && cudaEventQuery(c.ev_wave[1]) == cudaSuccess)
+  { // duration of the asynchronous uploads (they ran behind the kernels)
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev_copy0, c.ev_wave[1]) == cudaSuccess) c.stats.h2d_ms = ms;
+    cudaGetLastError();
   }
   c.stats.kernel_launches = c.ls.launches;
   c.executed = true;

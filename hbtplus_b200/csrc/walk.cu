@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
 {
   __shared__ TileNode s_tile[kWalkWarps][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * kWalkWarps + w;
+  const int warp = walk_cta(a) * kWalkWarps + w;
   if (warp >= a.nwarps) return;
   // segment of this warp: largest s with warp_off[s] <= warp (segments of the other class have no warps)
   int lo = 0, hi = a.nseg;
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(kWalkWarps * 32) walk_kernel(const WalkArgs a,
 template <int T>
 static void launch_t(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream)
 {
-  const int grid = div_up(a.nwarps, kWalkWarps);
+  const int grid = walk_grid(a, div_up(a.nwarps, kWalkWarps));
+  if (grid <= 0) return; // target split: none of the 16-CTA chunks of this launch is this context's
   const bool count = a.counters != nullptr;
   if (cfg.periodic)
   {

@@ -270,14 +270,15 @@ __device__ __forceinline__ void walk_epilogue(const WalkArgs &a, const DevConfig
       relative_velocity(x, v, st.ref_pos, st.ref_vel, cfg, dv);
       float e = (float)((double)dot3_rn(dv, dv) * 0.5 + pot);
       if (cfg.thermal_energy) e = __fadd_rn(e, v4.w); // UNBIND_WITH_THERMAL_ENERGY: E += InternalEnergy (src/subhalo_unbind.cpp:351-353)
-      a.E[slot] = e;
+      if (a.E_stage) a.E_stage[t] = e; else a.E[slot] = e;
     }
     else
     { // E += VecDot(OldVel, RefVelDiff) + dK - pot_removed  (src/subhalo_unbind.cpp:326-327)
       float ov[3];
       relative_velocity(x, v, st.old_ref_pos, st.old_ref_vel, cfg, ov);
       float s = __fadd_rn(dot3_rn(ov, st.ref_diff), st.dK);
-      a.E[slot] = (float)((double)a.E[slot] + ((double)s - pot));
+      const float e = (float)((double)a.E[slot] + ((double)s - pot));
+      if (a.E_stage) a.E_stage[t] = e; else a.E[slot] = e;
     }
   }
 }

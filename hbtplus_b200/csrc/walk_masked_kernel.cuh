@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kMW * 32, MINB) walk_masked_kernel(const WalkA
   typedef MaskedWarpSmem<MaskedStack<MINB, NP>::value, NP> Smem;
   __shared__ Smem s_all[kMW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * kMW + w;
+  const int warp = walk_cta(a) * kMW + w;
   if (warp >= a.nwarps) return;
   Smem &sm = s_all[w];
   const int seg = segment_of_warp(a.warp_off, a.nseg, warp);
@@ -126,7 +126,8 @@ void launch_masked_variant(const WalkArgs &a, const DevConfig &cfg, cudaStream_t
   }
   else
   {
-  const int grid = div_up(a.nwarps, kMW);
+  const int grid = walk_grid(a, div_up(a.nwarps, kMW));
+  if (grid <= 0) return; // target split: none of the 16-CTA chunks of this launch is this context's
   const bool count = a.counters != nullptr;
   // MINB CTAs of up to 48 KB static shared memory only fit with the largest shared-memory carve-out; the attribute is per device
   // (one host thread and context per device when a rank shards over several GPUs)

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) walk_small_kernel(const Walk
 {
   __shared__ float2 s_soft[kSmallWarps][kSoftFlush][32]; // [warp][entry][lane]: conflict-free (bank = lane)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * kSmallWarps + w;
+  const int warp = walk_cta(a) * kSmallWarps + w;
   if (warp >= a.nwarps) return;
   const int seg = segment_of_warp(a.warp_off, a.nseg, warp);
   const Segment sg = a.segs[seg];
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32) walk_small_kernel(const Walk
 void launch_walk_small(const WalkArgs &a, const DevConfig &cfg, cudaStream_t stream, LaunchStats &ls)
 {
   if (a.nwarps <= 0) return;
-  const int grid = div_up(a.nwarps, kSmallWarps);
+  const int grid = walk_grid(a, div_up(a.nwarps, kSmallWarps));
+  if (grid <= 0) return; // target split: none of the 16-CTA chunks of this launch is this context's
   const bool count = a.counters != nullptr;
   if (cfg.periodic)
   {

@@ -119,3 +119,25 @@ def gather_records(io_local: np.ndarray, index_local: np.ndarray, nsub_total: in
         idx_r = raw[nmax * rec: nmax * rec + k * 8].view(np.int64)
         full[idx_r] = io_r
     return full
+
+
+class _DevicePtr:
+    """A raw device pointer as a CUDA array (for torch.as_tensor): the library's staging array, owned by the library."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def torch_allreduce(device):
+    """The all-reduce callback of UnbindContext.set_walk_split for one-process-per-GPU jobs (torchrun): a sum all-reduce of the
+    library's staging array over the default process group (NCCL over NVLink / NVSwitch), complete when it returns.  This is
+    the walk split's only collective: 4 bytes per walk target and round (the non-natural case)."""
+    import torch
+    import torch.distributed as dist
+
+    def allreduce(ptr: int, count: int, stream: int):
+        t = torch.as_tensor(_DevicePtr(ptr, count), device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream(device).synchronize()
+
+    return allreduce

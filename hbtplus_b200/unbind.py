@@ -63,6 +63,29 @@ class UnbindContext:
         if rc != capi.HBTU_OK:
             raise UnbindError(rc, (self._lib.hbtu_last_error(self._ctx) or b"").decode())
 
+    # -- target split of the walk over cooperating contexts (the non-natural case) ------------
+    def set_walk_split(self, rank: int, nranks: int, allreduce=None):
+        """Deal every round's walk targets over `nranks` contexts that execute the SAME batch in lock step.
+        ``allreduce(device_ptr: int, count: int, stream: int)`` must sum the `count` floats at `device_ptr` over all
+        contexts in place and be complete when it returns (e.g. torch.distributed.all_reduce on a tensor wrapped around the
+        pointer, see hbtplus_b200.sched.torch_allreduce).  nranks <= 1 or allreduce None switches the split off."""
+        self._lib.hbtu_set_walk_split.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        if nranks <= 1 or allreduce is None:
+            self._split_cb = None
+            self._check(self._lib.hbtu_set_walk_split(self._ctx, 0, 1, None, None))
+            return
+
+        def thunk(user, buf, count, stream):
+            try:
+                allreduce(int(buf), int(count), int(stream or 0))
+                return 0
+            except Exception as ex:  # reported as HBTU_ERR_CUDA by the library
+                print(f"walk-split all-reduce failed: {ex!r}")
+                return 1
+
+        self._split_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)(thunk)  # keep alive
+        self._check(self._lib.hbtu_set_walk_split(self._ctx, rank, nranks, C.cast(self._split_cb, C.c_void_p), None))
+
     def set_counting(self, on: bool):
         self._check(self._lib.hbtu_set_counting(self._ctx, int(on)))
 
@@ -181,4 +204,49 @@ class UnbindContext:
             self._ctx, C.byref(epoch), len(src), P(src, C.c_float), len(tgt), P(tgt, C.c_float), P(sm, C.c_float), P(tv, C.c_float),
             P(rp, C.c_double), P(rv, C.c_double), P(out, C.c_double))
         self._check(rc)
+        return out
+
+
+class SplitGroup:
+    """Contexts of ONE process that cooperate on the same batch through the library's built-in peer-memory all-reduce
+    (hbtu_split_group_*): one host thread per context must call execute()/unbind_batch() concurrently."""
+
+    def __init__(self, contexts):
+        self._lib = contexts[0]._lib
+        self._lib.hbtu_split_group_create.restype = C.c_void_p
+        self._lib.hbtu_split_group_create.argtypes = [C.c_int]
+        self._lib.hbtu_split_group_join.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._lib.hbtu_split_group_destroy.argtypes = [C.c_void_p]
+        self._g = C.c_void_p(self._lib.hbtu_split_group_create(len(contexts)))
+        if not self._g:
+            raise UnbindError(capi.HBTU_ERR_INVALID, "hbtu_split_group_create failed")
+        self.contexts = list(contexts)
+        for r, ctx in enumerate(self.contexts):
+            ctx._check(self._lib.hbtu_split_group_join(self._g, ctx._ctx, r))
+
+    def close(self):
+        if self._g:
+            self._lib.hbtu_split_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def run(self, fn):
+        """fn(rank, ctx) on one thread per member; returns the list of results (exceptions are re-raised)."""
+        import threading
+
+        out, err = [None] * len(self.contexts), [None] * len(self.contexts)
+
+        def work(r):
+            try:
+                out[r] = fn(r, self.contexts[r])
+            except BaseException as ex:  # noqa: BLE001
+                err[r] = ex
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(len(self.contexts))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
         return out

@@ -25,6 +25,7 @@
 #ifndef HBT_UNBIND_H
 #define HBT_UNBIND_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -156,6 +157,13 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
                       const int32_t *nest_list, hbtu_sub_io *io, int32_t flags, int64_t order_capacity,
                       int64_t *order_offset, int32_t *order_out, float *energy_out);
 
+/* Pinned (page-locked) host memory for the caller's staging arrays.  hbtu_unbind_batch uploads the particle arrays on a copy
+ * stream in two waves (everything but the dominant root subhalo first, that root - which the level-synchronous scheduler
+ * reaches last - behind the kernels of the deeper levels); from pinned memory these are asynchronous DMA transfers, from any
+ * other host memory they are plain staged copies.  NULL when the allocation fails. */
+void *hbtu_host_alloc(size_t bytes);
+void hbtu_host_free(void *p);
+
 /* The same call split so that a caller can keep a snapshot resident in HBM:
  *   hbtu_stage   : validate + host->device copies of the batch
  *   hbtu_execute : all kernels (may be called repeatedly on the staged batch; inputs are not modified)
@@ -167,6 +175,35 @@ int hbtu_stage(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64
 int hbtu_execute(hbtu_ctx *ctx);
 int hbtu_fetch(hbtu_ctx *ctx, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset,
                int32_t *order_out, float *energy_out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Target split of the walk over several GPUs ("the non-natural case": one subhalo >> all others, so
+ * that whole hierarchies cannot balance the GPUs - the AqA2 central holds 72 % of the particles).  The reference itself
+ * parallelises over PARTICLES there (the OpenMP target loops of src/subhalo_unbind.cpp:319,341, chosen at
+ * src/subhalo_tracking.cpp:420).  Here `nranks` cooperating contexts (one per GPU; in one process or in several) are given
+ * the SAME batch and execute it in lock step: everything except the walk is replicated (it is ~15 % of a step), every round's
+ * walk targets are dealt block-cyclically (16 CTAs = 2048..8192 targets at a time) to the contexts, each writes the new
+ * binding energies of its targets into a zero-initialised array in target order, and `allreduce` must sum that array
+ * element-wise over all contexts, in place (every element is non-zero on at most one context, so the sum is exact).
+ * The results of all contexts are identical, bit for bit, to the unsplit execution.
+ *
+ *   allreduce(user, device_buf, count, cuda_stream): device_buf holds `count` floats in this context's device memory; the
+ *   library's stream is idle while the function runs; when it returns the summed data must be complete in device_buf (or the
+ *   work enqueued on `cuda_stream`, a cudaStream_t).  Return 0, anything else aborts the execution with HBTU_ERR_CUDA.
+ *   It is called once per round, the same number of times, in the same order, on every context of the group.
+ * nranks <= 1 or allreduce == NULL switches the split off. */
+typedef int (*hbtu_allreduce_fn)(void *user, float *device_buf, int64_t count, void *cuda_stream);
+int hbtu_set_walk_split(hbtu_ctx *ctx, int rank, int nranks, hbtu_allreduce_fn allreduce, void *user);
+
+/* The same for contexts of ONE process (one host thread per context, e.g. the shim's HBT_UNBIND_DEVICES mode): a built-in
+ * all-reduce over peer-mapped device memory - after a host barrier every context launches ONE kernel that sums its 1/nranks
+ * slice of all members' arrays through NVLink peer loads and stores the result into every member's array (reduce-scatter +
+ * all-gather fused; no NCCL).  hbtu_split_group_join sets the walk split of `ctx`; all members must then execute the same
+ * batch concurrently.  Destroy the group after its members stopped executing (their split is switched off). */
+typedef struct hbtu_split_group hbtu_split_group;
+hbtu_split_group *hbtu_split_group_create(int nranks);
+int hbtu_split_group_join(hbtu_split_group *group, hbtu_ctx *ctx, int rank);
+void hbtu_split_group_destroy(hbtu_split_group *group);
 
 /* GravityTree_t::Build + EvaluatePotential / BindingEnergy for one particle set
  * (src/gravity_tree.cpp:79-175): tree over the nsrc source particles, potential at ntgt targets.

@@ -74,10 +74,37 @@ void fill_params(hbtu_params &p)
 // concurrently), Device objects are never freed while the process lives (a context is re-created in place, under its mutex,
 // when HBTConfig changed), and concurrent Unbind callers are COMBINED into one batch per flight (UnbindCombiner below)
 // instead of queueing one-subhalo batches behind a lock.
+// grow-only pinned host buffer (hbtu_host_alloc): from page-locked memory the library's uploads are asynchronous DMA that
+// overlaps its kernels; the page-locking itself is paid once per process, not per snapshot
+template <class T>
+struct PinnedBuffer
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  T *get(size_t n)
+  {
+    if (n > cap)
+    {
+      hbtu_host_free(p);
+      cap = n + n / 8 + 1024;
+      p = static_cast<T *>(hbtu_host_alloc(cap * sizeof(T)));
+      if (!p)
+      {
+        cap = 0;
+        throw std::runtime_error("hbtu_host_alloc failed (pinned staging buffer)");
+      }
+    }
+    return p;
+  }
+};
+
 struct Device
 {
   hbtu_ctx *ctx = nullptr;
-  std::mutex mu;
+  std::mutex mu; // guards ctx AND the staging buffers below
+  PinnedBuffer<float> pos_mass, vel;
+  PinnedBuffer<int32_t> order;
+  PinnedBuffer<float> energy;
 };
 std::mutex g_table_mutex;
 std::vector<Device *> g_devs;    // current device list
@@ -142,7 +169,15 @@ std::vector<Device *> devices()
 }
 Device *device0() { return devices()[0]; }
 
-// run f(ctx) under the device's mutex; a non-zero return code becomes the reference's error style (config_parser.cpp:70)
+// run f(ctx); a non-zero return code becomes the reference's error style (config_parser.cpp:70).  The _locked form expects the
+// caller to hold d->mu already.
+template <class F>
+void call_library_locked(Device *d, const char *what, F &&f)
+{
+  if (!d->ctx) throw std::runtime_error(std::string(what) + ": the device was retired (HBT_UNBIND_DEVICES changed during a call)");
+  const int rc = f(d->ctx);
+  if (rc != HBTU_OK) throw std::runtime_error(std::string(what) + " failed: " + hbtu_last_error(d->ctx));
+}
 template <class F>
 void call_library(Device *d, const char *what, F &&f)
 {
@@ -164,6 +199,7 @@ struct Batch
     const int64_t nsub = subs.size();
     if (nsub == 0) return;
     if (!dev) dev = device0();
+    std::lock_guard<std::mutex> device_lock(dev->mu); // the pinned staging buffers belong to the device
     // the caller's compile-time physics variant travels as batch flags
 #ifdef NO_STRIPPING
     flags |= HBTU_FLAG_NO_STRIPPING;
@@ -175,7 +211,7 @@ struct Batch
     for (int64_t s = 0; s < nsub; s++) part_offset[s + 1] = part_offset[s] + (int64_t)subs[s]->Particles.size();
     const int64_t N = part_offset[nsub];
     std::vector<Particle_t> all(N); // the reference's Unbind also makes one full copy (subhalo_unbind.cpp:409-415)
-    std::vector<float> pos_mass(4 * (size_t)N), vel(4 * (size_t)N);
+    float *pos_mass = dev->pos_mass.get(4 * (size_t)N), *vel = dev->vel.get(4 * (size_t)N);
     std::vector<hbtu_sub_io> io(nsub);
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t s = 0; s < nsub; s++)
@@ -224,16 +260,15 @@ struct Batch
     int64_t cap = hbtu_order_capacity(nsub, part_offset.data(), no, nl);
     if (cap < 0) throw std::runtime_error("hbtu_order_capacity: malformed nesting");
     std::vector<int64_t> order_offset(nsub + 1);
-    std::vector<int32_t> order(cap > 0 ? cap : 1);
+    int32_t *order = dev->order.get(cap > 0 ? cap : 1);
 #ifdef SAVE_BINDING_ENERGY
-    std::vector<float> energy(cap > 0 ? cap : 1);
-    float *pe = energy.data();
+    float *energy = dev->energy.get(cap > 0 ? cap : 1);
+    float *pe = energy;
 #else
     float *pe = nullptr;
 #endif
-    call_library(dev, "hbtu_unbind_batch", [&](hbtu_ctx *ctx) {
-      return hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass.data(), vel.data(), no, nl, io.data(), flags, cap,
-                               order_offset.data(), order.data(), pe);
+    call_library_locked(dev, "hbtu_unbind_batch", [&](hbtu_ctx *ctx) {
+      return hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass, vel, no, nl, io.data(), flags, cap, order_offset.data(), order, pe);
     });
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t s = 0; s < nsub; s++)

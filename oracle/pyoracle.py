@@ -154,7 +154,10 @@ def refine_particles(lib, params, epoch, snap, host_halo_id, n_old, nhalos, mbou
            io.ctypes.data_as(C.POINTER(capi.SubIO)), cap, P(order_offset, C.c_int64), P(order, C.c_int32), P(energy, C.c_float))
     if rc != 0:
         raise RuntimeError(f"hbtref_refine_particles failed: {rc}")
-    return Result(io, order_offset, order, energy)
+    r = Result(io, order_offset, order, energy)
+    lib.hbtref_last_refine_seconds.restype = C.c_double
+    r.refine_seconds = lib.hbtref_last_refine_seconds()  # SubhaloSnapshot_t::RefineParticles() alone
+    return r
 
 
 def profile_batch(lib, prefix, params, epoch, part_offset, pos_mass, io):

@@ -212,6 +212,7 @@ static int variant_flags(void)
 #endif
   return f;
 }
+static double g_last_refine_seconds = 0.0; /* wall time of the last SubhaloSnapshot_t::RefineParticles() call alone */
 static bool variant_ok(int32_t flags) { return (flags & (HBTU_FLAG_NO_STRIPPING | HBTU_FLAG_THERMAL_ENERGY)) == variant_flags(); }
 
 extern "C" {
@@ -228,6 +229,9 @@ void hbtref_set_num_threads(int n)
   omp_set_max_active_levels(1); /* HBT.cpp:22 */
 }
 int hbtref_get_max_threads(void) { return omp_get_max_threads(); }
+/* seconds the last hbtref_refine_particles spent inside SubhaloSnapshot_t::RefineParticles() itself (in the drop-in build: pack +
+ * H2D + kernels + D2H + permutation of vector<Particle_t>), without the harness' construction of the snapshot */
+double hbtref_last_refine_seconds(void) { return g_last_refine_seconds; }
 void hbtref_seed(unsigned s)
 {
   srand(s);
@@ -376,7 +380,9 @@ int hbtref_refine_particles(const hbtu_params *params, const hbtu_epoch *epoch, 
   }
   try
   {
+    const double t0 = omp_get_wtime();
     snap.RefineParticles();
+    g_last_refine_seconds = omp_get_wtime() - t0;
   }
   catch (const std::exception &ex)
   { /* only the drop-in build can throw (the reference path cannot fail) */
