@@ -58,7 +58,7 @@ class Workload:
     def describe(self, particles: float) -> str:
         return self.desc.format(P=particles, box=self.box, eps=self.eps)
 
-    def make(self, particles: float, dev, rank: int):
+    def make(self, particles: float, dev, rank: int, world: int = 1):
         sizes, parent = self.sizes(particles)
         return synth.make_snapshot_torch(sizes, device=dev, seed=self.seed + rank, box_size=self.box, particle_mass=self.mass, parent=parent,
                                          centre=self.centres(sizes, parent), wrap=self.periodic, pin=True)
@@ -150,6 +150,67 @@ class DynamicMerger(Workload):
         return c
 
 
+class Eagle(Workload):
+    """SURVEY 8(d) cfg 4.  ONE snapshot of particles x world grouped particles (full size: 1.36e9 = 40 % of 1504^3 on 8 GPUs,
+    1.7e8 per GPU), never materialised on one host: every rank draws the same global size list and nest forest from the fixed
+    seed, the hierarchies (FoF groups with their satellites) are dealt to the ranks by the cost-weighted longest-processing-
+    time-first queue (sched.lpt_partition, cost = sum n log2 n), and a rank generates only the particles of its own shard."""
+
+    def sizes(self, particles):
+        rng = np.random.default_rng(self.seed)
+        f = min(1.0, particles / self.full_particles)
+        ngroups, nsat = max(50, int(3e6 * f)), max(20, int(1e6 * f))
+        n_max = int(max(3e7 * f, 5000))
+        groups = synth.subhalo_sizes(rng, ngroups, 20, n_max)
+        sats = synth.subhalo_sizes(rng, nsat, 20, max(n_max // 8, 400))
+        for _ in range(4):  # rescale to the wanted particle total (satellites hold ~1/8 of it)
+            groups = np.clip((groups * (0.875 * particles / groups.sum())).astype(np.int64), 20, n_max)
+            sats = np.clip((sats * (0.125 * particles / sats.sum())).astype(np.int64), 20, max(n_max // 8, 400))
+        # every satellite hangs off a group (90 %) or off another satellite (10 %, depth 2) at least 4x its own size
+        gsort = np.argsort(groups, kind="stable")
+        elig = len(groups) - np.searchsorted(groups[gsort], 4 * sats, side="left")
+        pick = (rng.random(nsat) * np.maximum(elig, 1)).astype(np.int64)
+        par = gsort[len(groups) - 1 - np.minimum(pick, len(groups) - 1)]
+        ssort = np.argsort(sats, kind="stable")
+        elig2 = nsat - np.searchsorted(sats[ssort], 4 * sats, side="left")
+        deep = (rng.random(nsat) < 0.1) & (elig2 > 0)
+        pick2 = (rng.random(nsat) * np.maximum(elig2, 1)).astype(np.int64)
+        par2 = ssort[nsat - 1 - np.minimum(pick2, nsat - 1)]
+        deep &= ~deep[par2]  # a depth-2 satellite hangs off a depth-1 one
+        parent = np.concatenate([np.full(ngroups, -1, np.int64), np.where(deep, ngroups + par2, par)])
+        return np.concatenate([groups, sats]).astype(np.int64), parent
+
+    def centres(self, sizes, parent):
+        return None  # groups uniformly in the periodic box
+
+    def shard(self, particles, rank, world):
+        """(sizes, parent, global index) of the subhaloes rank `rank` of `world` owns."""
+        from hbtplus_b200 import sched
+
+        sizes, parent = self.sizes(particles * world)
+        if world == 1:
+            return sizes, parent, np.arange(len(sizes))
+        root = sched.roots_of(parent)
+        cap = sizes.astype(np.float64)
+        cost_sub = cap * np.log2(np.maximum(cap, 2.0))
+        roots = np.nonzero(parent < 0)[0]
+        cost = np.zeros(len(sizes))
+        np.add.at(cost, root, cost_sub)
+        owner = np.full(len(sizes), -1, np.int64)
+        owner[roots] = sched.lpt_partition(cost[roots], world)
+        mine = np.nonzero(owner[root] == rank)[0]
+        local = np.full(len(sizes), -1, np.int64)
+        local[mine] = np.arange(len(mine))
+        par = np.where(parent[mine] >= 0, local[np.maximum(parent[mine], 0)], -1)
+        return sizes[mine], par, mine
+
+    def make(self, particles, dev, rank, world: int = 1):
+        sizes, parent, _ = self.shard(particles, rank, world)
+        return synth.make_snapshot_torch(sizes, device=dev, seed=self.seed + 17 * rank, box_size=self.box, particle_mass=self.mass, parent=parent,
+                                         centre=None, wrap=True, pin=True)
+
+
+
 WORKLOADS = {
     "cfg2": AqA2("cfg2", 20240002, 100.0, 4.8e-5, False, 1e-6, 1.8e8,
                  "BASELINE configs[1] / SURVEY 8(d) cfg 2: AqA2-shaped synthetic Milky-Way halo per GPU: central source 0.72*P + subhaloes dN/dn~n^-1.9 on "
@@ -157,6 +218,10 @@ WORKLOADS = {
     "cfg3": MilliMill("cfg3", 20240003, 62.5, 5e-3, True, 0.086, 8.9e6,
                       "BASELINE configs[2] / SURVEY 8(d) cfg 3: MilliMill-shaped 270^3 box per GPU: P={P:.3g} grouped particles (45 % of 1.97e7) in ~2e4 FoF groups + ~5e3 "
                       "satellites, dN/dn~n^-1.9 on [20,5e5], nest depth<=3, BoxSize {box}, eps {eps}, periodic on, exact potential, theta 0.45"),
+    "cfg4": Eagle("cfg4", 20240004, 67.77, 1.80239e-3, True, 6.57e-4, 1.7e8,
+                  "BASELINE configs[3] / SURVEY 8(d) cfg 4: EagleL100N1504-shaped DM-only snapshot, P={P:.3g} grouped particles PER GPU (full size 1.7e8 x 8 GPUs = "
+                  "1.36e9 = 40 % of 1504^3) in FoF groups dN/dn~n^-1.9 on [20,3e7] + satellites (depth<=2), hierarchies dealt to the ranks by the cost-weighted "
+                  "LPT queue and generated shard-locally, BoxSize {box}, eps {eps}, periodic on, exact potential, theta 0.45"),
     "cfg5": DynamicMerger("cfg5", 20240005, 250.0, 2.1e-3, False, 0.086, 1.0e7 + 1.1e7,
                           "BASELINE configs[4] / SURVEY 8(d) cfg 5: DynamicMerger-shaped: two 5e6-particle haloes at 1 Mpc/h separation + 1e5 tiny subhaloes "
                           "n in [20,200] nested in them (small-subhalo batched path), P={P:.3g} particles, BoxSize {box}, eps {eps}, periodic off, exact potential, theta 0.45"),
@@ -505,6 +570,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="particles in the bounded CPU sample (10-30 s on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps)")
     ap.add_argument("--dropin-particles", type=float, default=4e7, help="size of the in-memory SubhaloSnapshot_t of the drop-in e2e row (RefineParticles via libhbtdropin)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one snapshot per GPU (whole hierarchies never span ranks); strong = ONE snapshot on all GPUs, every round's "
+                         "walk targets dealt over the ranks (hbtu_set_walk_split), one NCCL all-reduce of 4 B per target per round")
     ap.add_argument("--profile", action="store_true", help="for ncu: no counting pass, no e2e, no CPU leg (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -549,10 +617,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    snap = wl.make(args.particles, dev, rank)  # same shape on every rank (weak scaling), own particle realisation
+    strong = args.scaling == "strong" and world > 1
+    # weak: same shape on every rank, own particle realisation; strong: the SAME snapshot on every rank
+    snap = wl.make(args.particles, dev, 0 if strong else rank, 1 if strong else world)
     torch.cuda.empty_cache()
     n_local = snap.npart
     ctx = UnbindContext(wl.params(local_rank))
+    if strong:
+        from hbtplus_b200 import sched
+
+        ctx.set_walk_split(rank, world, sched.torch_allreduce(dev))
     e = capi.make_epoch(1.0)
     flags = capi.HBTU_FLAG_TRUNCATE_SOURCE
 
@@ -604,10 +678,12 @@ def main():
     if res is None:
         res = ctx.fetch(want_energy=False)
         e2e_wall = []
-    tot = torch.tensor([float(n_local), float(res.io["nbound"].sum()), float(st0.pair_interactions)], dtype=torch.float64, device=dev)
+    once = 1.0 if (not strong or rank == 0) else 0.0  # strong scaling: one snapshot, every rank holds all of its records
+    tot = torch.tensor([once * n_local, once * float(res.io["nbound"].sum()), float(st0.pair_interactions)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if world > 1 and not strong:
         # the path's only collective: gather the per-subhalo result records (~150 B each) of all ranks
         from hbtplus_b200 import sched
 
@@ -640,7 +716,7 @@ def main():
             traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("kernel")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_exec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t_exec * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "workload_id": wl.name, "particles_per_gpu": n_local, "subhaloes_per_gpu": snap.nsub, "sum_nbound": nb_all,
                        "l2_policy": f"inputs ({n_local * 32 / 1e9:.2f} GB per GPU) are larger than the 126 MB L2; no explicit flush",
@@ -648,6 +724,9 @@ def main():
                        "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
                        "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all,
                        "walk_fallbacks": int(st0.walk_fallbacks),
+                       "multi_gpu": ("strong scaling: ONE snapshot replicated on every GPU, walk targets of every round dealt block-cyclically over the ranks, "
+                                     "one NCCL sum all-reduce of 4 B per walk target per round, everything else replicated") if strong else
+                                    ("weak scaling: one snapshot per GPU, hierarchies never span ranks; the only collective is the NCCL all-gather of the result records"),
                        "phase_rooflines": phase_rooflines(st0, float(np.mean(build_ms)), float(np.mean(other_ms)), peaks)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),

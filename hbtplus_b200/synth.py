@@ -170,6 +170,18 @@ def make_snapshot(
     return Snapshot(part_offset, pos_mass, vel4, nest_offset, nest_list, io)
 
 
+def forest_depth(parent: np.ndarray) -> np.ndarray:
+    """Nesting depth of every subhalo of a parent forest (roots: 0), vectorised."""
+    parent = np.asarray(parent, np.int64)
+    depth = np.zeros(len(parent), np.int64)
+    cur = parent.copy()
+    while (cur >= 0).any():
+        live = cur >= 0
+        depth[live] += 1
+        cur = np.where(live, parent[np.maximum(cur, 0)], -1)
+    return depth
+
+
 def nest_forest(rng: np.random.Generator, sizes: np.ndarray, max_depth: int = 4, p_nest: float = 0.5, root: int | None = 0) -> np.ndarray:
     """Random nesting: every subhalo is nested in a LARGER one (or in `root`), depth <= max_depth.
 
@@ -217,25 +229,19 @@ def make_snapshot_torch(sizes, *, device, seed: int = 20240002, box_size: float 
     bulk = rng.standard_normal((nsub, 3)) * 200.0
     if parent is not None:
         parent = np.asarray(parent, np.int64)
-        depth = np.zeros(nsub, np.int64)
-        for s in range(nsub):
-            q, d = s, 0
-            while parent[q] >= 0:
-                q, d = parent[q], d + 1
-            depth[s] = d
+        depth = forest_depth(parent)
         dirs = rng.standard_normal((nsub, 3))
         dirs /= np.linalg.norm(dirs, axis=1)[:, None]
         tang = np.cross(dirs, rng.standard_normal((nsub, 3)))
         tang /= np.linalg.norm(tang, axis=1)[:, None]
         frac = rng.uniform(0.3, 1.5, nsub)
-        for s in np.argsort(depth, kind="stable"):
-            p = parent[s]
-            if p < 0:
-                continue
-            rad = a_of[p] * frac[s]
-            centres[s] = centres[p] + dirs[s] * rad
+        for d in range(1, int(depth.max()) + 1 if nsub else 0):  # level by level: a subhalo only needs its parent's final centre
+            idx = np.nonzero(depth == d)[0]
+            p = parent[idx]
+            rad = a_of[p] * frac[idx]
+            centres[idx] = centres[p] + dirs[idx] * rad[:, None]
             vc = np.sqrt(G_INTERNAL * mtot[p] * (rad / (rad + a_of[p])) ** 2 / rad)
-            bulk[s] = bulk[p] + tang[s] * vc * 0.8
+            bulk[idx] = bulk[p] + tang[idx] * (vc * 0.8)[:, None]
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     t = lambda x, dt=torch.float32: torch.as_tensor(x, dtype=dt, device=device)

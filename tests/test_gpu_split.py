@@ -72,3 +72,33 @@ def test_walk_split_with_a_python_allreduce():
     ctx.set_walk_split(0, 1, None)
     _same(ctx.unbind_batch(e, snap), want)
     ctx.close()
+
+
+def test_torch_allreduce_wraps_the_device_pointer():
+    """sched.torch_allreduce (the NCCL callback of bench.py --scaling strong) on a one-rank process group: the raw device pointer
+    becomes a tensor without a copy and the collective runs on it in place."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from hbtplus_b200 import sched
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        dev = torch.device("cuda", 0)
+        x = torch.arange(1000, dtype=torch.float32, device=dev)
+        fn = sched.torch_allreduce(dev)
+        fn(x.data_ptr(), 1000, 0)
+        assert torch.equal(x, torch.arange(1000, dtype=torch.float32, device=dev))
+        y = torch.as_tensor(sched._DevicePtr(x.data_ptr(), 1000), device=dev)
+        y += 1  # same memory
+        assert float(x[0]) == 1.0 and float(x[999]) == 1000.0
+    finally:
+        if created:
+            dist.destroy_process_group()
