@@ -62,6 +62,38 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c)
   return *reinterpret_cast<float2 *>(&d);
 }
 
+// One half of a deciding pair-element of the masked walk: the target (lane, slice) takes part iff its bit is in `mask`; it OPENS
+// the node iff lenq > r2 (reference criterion, src/gravity_tree.cpp:135), otherwise it accepts it: acc += w * rinv.  Returns the
+// ballot of the opening lanes.  Inline PTX so that the accept is ONE predicated FFMA fed by the same two compares that feed the
+// vote (the compiler's own sequence: FFMA + FSEL + two more FSETP).  r2 and lenq are finite, so !(lenq > r2) == (lenq <= r2).
+template <bool COUNT>
+__device__ __forceinline__ unsigned decide_half(unsigned mask, unsigned lanebit, float lenq, float r2, float w, float rinv, float &acc,
+                                                unsigned &n_acc)
+{
+  unsigned openers;
+  if (COUNT)
+  {
+    unsigned accepted;
+    asm volatile("{\n\t.reg .pred pin, pop, pac;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %3, %4;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "setp.gt.and.f32 pop, %5, %6, pin;\n\tsetp.le.and.f32 pac, %5, %6, pin;\n\t"
+                 "@pac fma.rn.f32 %0, %7, %8, %0;\n\tselp.u32 %2, 1, 0, pac;\n\t"
+                 "vote.sync.ballot.b32 %1, pop, 0xffffffff;\n\t}"
+                 : "+f"(acc), "=r"(openers), "=r"(accepted)
+                 : "r"(mask), "r"(lanebit), "f"(lenq), "f"(r2), "f"(w), "f"(rinv));
+    n_acc += accepted;
+  }
+  else
+    asm volatile("{\n\t.reg .pred pin, pop, pac;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %2, %3;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "setp.gt.and.f32 pop, %4, %5, pin;\n\tsetp.le.and.f32 pac, %4, %5, pin;\n\t"
+                 "@pac fma.rn.f32 %0, %6, %7, %0;\n\t"
+                 "vote.sync.ballot.b32 %1, pop, 0xffffffff;\n\t}"
+                 : "+f"(acc), "=r"(openers)
+                 : "r"(mask), "r"(lanebit), "f"(lenq), "f"(r2), "f"(w), "f"(rinv));
+  return openers;
+}
+
 // squared distances of node n to the T targets of a lane: (dx*dx + dy*dy) + dz*dz as FMUL, FFMA, FFMA - two targets per
 // instruction where the layout allows it (non-periodic, even T; the sign of dx is irrelevant)
 template <int T, bool PERIODIC>

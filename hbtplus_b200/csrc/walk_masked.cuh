@@ -85,8 +85,9 @@ struct __align__(16) DecidingElem
 {
   float4 nxm;      // -x, -y, -z, -m: operands of the packed adds and of the accumulate
   float lenq;      // len^2/theta^2 (0 for a particle: every target of the mask accepts)
-  int slot;        // index of the children's chain in `pending` (kMCap = none: scratch entry)
-  unsigned ma, mb; // targets taking part (bit = lane; first / second slice of the pair)
+  int pad;
+  unsigned ma, mb; // in: targets taking part (bit = lane; first / second slice of the pair); out: the targets that OPENED the
+                   // node (written by the evaluation; the drain copies them into the pending chain of the node's children)
 };
 template <int STACK, int NP = 2> // chain entries per warp, slice pairs per warp
 struct MaskedSmemT
@@ -98,7 +99,7 @@ struct MaskedSmemT
   DecidingElem d[NP][kMCap];  // deciding elements per pair
   float4 a_xm[NP][kACap];     // accept-all elements per pair: -x, -y, -z, -m
   uint2 a_m[NP][kACap];       //   their masks
-  ChainEntryT<NP> pending[kMCap + 1];
+  ChainEntryT<NP> pending[kMCap];
   ChainEntryT<NP> stack[STACK];
 };
 
@@ -201,7 +202,8 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
 
 // evaluate the deciding list of slice pair R (slices K = 2R, K+1): elements [0, cnt) take the bare pair kernel + the
 // criterion in a branch-free loop, the elements that need the exact kernel were queued from the far end,
-// [kMCap - cntx, kMCap).  The targets that open an element are written into the pending chain of the node's children.
+// [kMCap - cntx, kMCap).  The targets that open an element replace its masks in place (one 8-byte store at a fixed offset);
+// the drain hands them to the pending chain of the node's children.
 template <int K, bool PERIODIC, bool COUNT, int T, class MaskedSmem>
 __device__ __forceinline__ void masked_eval_split(MaskedSmem &sm, int cnt, int cntx, int lane, unsigned lanebit, const float (&px)[T],
                                                   const float (&py)[T], const float (&pz)[T], double (&accd)[T], float box_size, float box_half,
@@ -213,32 +215,30 @@ __device__ __forceinline__ void masked_eval_split(MaskedSmem &sm, int cnt, int c
   HBT_M_PRAGMA_UNROLL(HBT_M_UNROLL_D)
   for (int i = 0; i < cnt; i++)
   {
-    const DecidingElem &e = sm.d[R][i];
+    DecidingElem &e = sm.d[R][i];
     const float4 n = e.nxm;
     const float lenq = e.lenq;
-    const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
+    const uint2 m = *reinterpret_cast<const uint2 *>(&e.ma);
     const float2 dx = f2_add(pxx, make_float2(n.x, n.x));
     const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
     const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
     const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
     const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
-    const bool opena = lenq > r2.x, openb = lenq > r2.y; // reference criterion, per target (src/gravity_tree.cpp:135)
-    if (ina && !opena) acca = fmaf(n.w, ra, acca);
-    if (inb && !openb) accb = fmaf(n.w, rb, accb);
-    const unsigned oa = __ballot_sync(kFull, ina && opena);
-    const unsigned ob = __ballot_sync(kFull, inb && openb);
-    if (COUNT) n_acc += (unsigned)(ina && !opena) + (unsigned)(inb && !openb);
-    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[e.slot].m[K]) = make_uint2(oa, ob); // the openers walk the node's children
+    // reference criterion, per target (src/gravity_tree.cpp:135): in the mask and lenq > r2 -> opener, else accumulate
+    const unsigned oa = decide_half<COUNT>(m.x, lanebit, lenq, r2.x, n.w, ra, acca, n_acc);
+    const unsigned ob = decide_half<COUNT>(m.y, lanebit, lenq, r2.y, n.w, rb, accb, n_acc);
+    if (lane == 0) *reinterpret_cast<uint2 *>(&e.ma) = make_uint2(oa, ob); // the openers walk the node's children
   }
   for (int i = kMCap - cntx; i < kMCap; i++)
   {
-    const DecidingElem &e = sm.d[R][i];
+    DecidingElem &e = sm.d[R][i];
     const float4 n = e.nxm;
     const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
     unsigned oa, ob;
     masked_exact<PERIODIC, COUNT>(n, e.lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
     masked_exact<PERIODIC, COUNT>(n, e.lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
-    if (lane == 0) *reinterpret_cast<uint2 *>(&sm.pending[e.slot].m[K]) = make_uint2(oa, ob);
+    __syncwarp(); // every lane has read the masks before lane 0 replaces them
+    if (lane == 0) *reinterpret_cast<uint2 *>(&e.ma) = make_uint2(oa, ob);
   }
   accd[K] += (double)acca;
   accd[K + 1] += (double)accb;
@@ -414,15 +414,20 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
 #pragma unroll
       for (int k = 0; k < T; k++) c.m[k] = cm[k];
     }
-    int slot = kMCap; // scratch entry: particles have no children chain
+    int eidx[NP]; // position of the lane's deciding element in the list of pair r
+#pragma unroll
+    for (int r = 0; r < NP; r++) eidx[r] = bare ? nd[r] + __popc(mD[r] & lt) : kMCap - 1 - nx[r] - __popc(mX[r] & lt);
     if (toP)
-    {
-      slot = np + __popc(mP & lt);
-      ChainEntry &c = sm.pending[slot];
+    { // the chain of the children waits for the openers: it remembers where its element sits in every pair's list
+      ChainEntry &c = sm.pending[np + __popc(mP & lt)];
       c.cur = cur + 1;
       c.pend = kend;
 #pragma unroll
-      for (int k = 0; k < T; k++) c.m[k] = 0u; // filled in by the evaluation of the element
+      for (int r = 0; r < NP; r++)
+      {
+        c.m[2 * r] = hp[r] ? (unsigned)eidx[r] : 0xffffffffu;
+        c.m[2 * r + 1] = 0u;
+      }
     }
     if (toAcc)
     {
@@ -442,14 +447,14 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       DecidingElem e;
       e.nxm = make_float4(-p.x, -p.y, -p.z, -p.w);
       e.lenq = lenq;
-      e.slot = slot;
+      e.pad = 0;
 #pragma unroll
       for (int r = 0; r < NP; r++)
         if (hp[r])
         {
           e.ma = cm[2 * r];
           e.mb = cm[2 * r + 1];
-          sm.d[r][bare ? nd[r] + __popc(mD[r] & lt) : kMCap - 1 - nx[r] - __popc(mX[r] & lt)] = e;
+          sm.d[r][eidx[r]] = e;
         }
     }
 #ifdef HBT_MASKED_STAT_ON
@@ -515,7 +520,19 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
         c.pend = 0;
 #pragma unroll
         for (int k = 0; k < T; k++) c.m[k] = 0u;
-        if (i < np) c = sm.pending[i];
+        if (i < np)
+        {
+          c = sm.pending[i];
+#pragma unroll
+          for (int r = 0; r < NP; r++)
+          { // the openers of the chain's element in pair r (none if the chain had no targets there)
+            const unsigned idx = c.m[2 * r];
+            uint2 o = make_uint2(0u, 0u);
+            if (idx != 0xffffffffu) o = *reinterpret_cast<const uint2 *>(&sm.d[r][idx].ma);
+            c.m[2 * r] = o.x;
+            c.m[2 * r + 1] = o.y;
+          }
+        }
         unsigned any = 0u;
 #pragma unroll
         for (int k = 0; k < T; k++) any |= c.m[k];

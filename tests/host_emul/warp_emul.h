@@ -148,6 +148,17 @@ static inline float rsqrt_raw(float x) { return 1.0f / std::sqrt(x); }
 static inline float2 f2_add(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 static inline float2 f2_mul(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 static inline float2 f2_fma(float2 a, float2 b, float2 c) { return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
+template <bool COUNT>
+static inline unsigned decide_half(unsigned mask, unsigned lanebit, float lenq, float r2, float w, float rinv, float &acc, unsigned &n_acc)
+{ // host twin of walk_common.cuh::decide_half
+  const bool in = (mask & lanebit) != 0u, open = lenq > r2;
+  if (in && !open)
+  {
+    acc = std::fma(w, rinv, acc);
+    if (COUNT) n_acc++;
+  }
+  return __ballot_sync(kFull, in && open);
+}
 namespace hbt
 {
 static inline float nearest_f(float x, float box, float half) { return x > half ? x - box : (x < -half ? x + box : x); }
