@@ -26,6 +26,7 @@ def test_full_size_properties(make_ctx):
     import cases_bench
 
     wl = bench.WORKLOADS["cfg2"]
+    _, parent = wl.sizes(1.8e8)
     snap = wl.make(1.8e8, torch.device("cuda", 0), 0)
     torch.cuda.empty_cache()
     p = wl.params(0)
