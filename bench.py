@@ -46,8 +46,11 @@ class Workload:
     def __init__(self, name, seed, box, eps, periodic, mass, full_particles, desc):
         self.name, self.seed, self.box, self.eps, self.periodic, self.mass, self.full_particles, self.desc = name, seed, box, eps, periodic, mass, full_particles, desc
 
+    max_sample = 0  # MaxSampleSizeOfPotentialEstimate: 0 = exact potential (the parity and headline mode); --max-sample sets it
+
     def params(self, device: int = 0) -> capi.Params:
-        return capi.make_params(box_size=self.box, softening=self.eps, periodic=self.periodic, max_sample_size=0, device=device)
+        return capi.make_params(box_size=self.box, softening=self.eps, periodic=self.periodic, max_sample_size=Workload.max_sample, device=device,
+                                shuffle_seed=20240001)
 
     def sizes(self, particles: float):
         raise NotImplementedError
@@ -248,12 +251,13 @@ def run_cpu(snap, threads: int | None = None, workload: str = "cfg2"):
     p = params_for(0, workload)
     e = capi.make_epoch(1.0)
     ncpu = threads or os.cpu_count() or 1
-    if po.have_ref():
+    if po.have_ref() and p.max_sample_size == 0:
         lib, prefix, kind = po.load_ref(), "hbtref", "reference"
-    else:
+    else:  # sampled mode: the reference's random_shuffle on libc rand() cannot be shared with a GPU; the port takes the library's permutation
         if not os.path.exists(po.ORACLE_PATH):
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
         lib, prefix, kind = po.load_oracle(), "hbto", "port"
+        lib.hbto_set_shuffle_mode(1 if p.max_sample_size > 0 else 0)
     getattr(lib, prefix + "_set_num_threads")(ncpu)
     t0 = time.perf_counter()
     r = po.run_batch(lib, prefix, p, e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE, want_energy=False)
@@ -566,6 +570,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="cfg2 = BASELINE configs[1] (the headline); cfg3 / cfg5 = SURVEY 8(d) cfg 3 / 5")
+    ap.add_argument("--max-sample", type=int, default=0, help="MaxSampleSizeOfPotentialEstimate (0 = exact potential, the headline; 1000 = the reference's default "
+                    "sampled mode; the CPU legs then run the oracle port with the library's counter-based permutation)")
     ap.add_argument("--particles", type=float, default=None, help="particles per GPU (default: the configuration's full size; cfg2: 1.8e8)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000, help="particles in the bounded CPU sample (10-30 s on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default: --steps)")
@@ -579,11 +585,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    Workload.max_sample = args.max_sample
     if args.particles is None:
         args.particles = wl.full_particles
     if args.e2e_steps is None:
         args.e2e_steps = args.steps
     workload = wl.describe(args.particles)
+    if args.max_sample > 0:
+        workload = workload.replace("exact potential (MaxSample 0)", f"SAMPLED potential (MaxSampleSizeOfPotentialEstimate {args.max_sample})").replace(
+            "exact potential", f"SAMPLED potential (MaxSampleSizeOfPotentialEstimate {args.max_sample})")
 
     if args.impl == "reference":
         if rank != 0:

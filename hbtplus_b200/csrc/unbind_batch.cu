@@ -307,19 +307,47 @@ __global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubS
 __global__ void __launch_bounds__(kBlock) count_bound_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg,
                                                               const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
                                                               SubState *__restrict__ subs)
-{
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = t < T;
-  int a = valid ? tgt_seg[t] : -1;
-  bool bound = valid && (E[tgt_slot[t]] < 0.f);
-  int a0 = __shfl_sync(0xffffffffu, a, 0);
-  if (__all_sync(0xffffffffu, a == a0))
+{ // 4 targets per thread; a block that lies inside one segment (the rule for large subhaloes) issues ONE atomic
+  __shared__ int s_cnt[kBlock / 32];
+  const int base = blockIdx.x * (kBlock * 4);
+  const int last = min(base + kBlock * 4, T) - 1;
+  const int a_first = tgt_seg[base], a_last = tgt_seg[last];
+  if (a_first == a_last)
   {
-    unsigned m = __ballot_sync(0xffffffffu, bound);
-    if ((threadIdx.x & 31) == 0 && m && a0 >= 0) atomicAdd(&subs[segs[a0].sub].count_bound, __popc(m));
+    int c = 0;
+#pragma unroll
+    for (int it = 0; it < 4; it++)
+    {
+      const int t = base + it * kBlock + threadIdx.x;
+      if (t < T) c += (E[tgt_slot[t]] < 0.f) ? 1 : 0;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) tot += s_cnt[w];
+      if (tot) atomicAdd(&subs[segs[a_first].sub].count_bound, tot);
+    }
+    return;
   }
-  else if (bound)
-    atomicAdd(&subs[segs[a].sub].count_bound, 1);
+  for (int it = 0; it < 4; it++)
+  { // the block straddles segment boundaries: warp-uniform or per-lane atomics
+    const int t = base + it * kBlock + threadIdx.x;
+    const bool valid = t < T;
+    const int a = valid ? tgt_seg[t] : -1;
+    const bool bound = valid && (E[tgt_slot[t]] < 0.f);
+    const int a0 = __shfl_sync(0xffffffffu, a, 0);
+    if (__all_sync(0xffffffffu, a == a0))
+    {
+      const unsigned m = __ballot_sync(0xffffffffu, bound);
+      if ((threadIdx.x & 31) == 0 && m && a0 >= 0) atomicAdd(&subs[segs[a0].sub].count_bound, __popc(m));
+    }
+    else if (bound)
+      atomicAdd(&subs[segs[a].sub].count_bound, 1);
+  }
 }
 
 // PartitionBindingEnergy result -> disruption / CorrectionLoop / convergence (src/subhalo_unbind.cpp:357-403)
@@ -890,7 +918,7 @@ static void run_round(Context &c, std::vector<int> &active)
   }
   HBT_CUDA(cudaEventRecord(c.ev[2], st));
 
-  count_bound_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);
+  count_bound_kernel<<<grid_for(T, kBlock * 4), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);
   HBT_CHECK_LAUNCH();
   state1_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_pos, c.cfg);
   HBT_CHECK_LAUNCH();
