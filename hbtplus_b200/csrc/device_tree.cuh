@@ -102,13 +102,12 @@ struct TreeArrays
   int8_t *cell_depth = nullptr;
   uint32_t *depthmask = nullptr;
   int *cellcount = nullptr;
-  double4s *msum = nullptr;
   float4 *node_xm = nullptr;
   float2 *node_aux = nullptr;
   SegRoot *roots = nullptr;
   uint32_t *bbox = nullptr; // 6 ordered-uint per segment
   const int *tree_off = nullptr; // [nseg+1] device
-  const int *h_tree_off = nullptr; // the same on the host (tile table of the deterministic moment scan)
+  const int *h_tree_off = nullptr; // the same on the host
 };
 
 struct LaunchStats

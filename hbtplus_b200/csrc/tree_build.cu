@@ -8,8 +8,9 @@
 //   keys (K1)      63-bit octal key by the reference's own double-precision descent            HBM
 //   sort (K2)      CUB radix sort by key, then stable by segment                               HBM
 //   cells (K3)     one thread per adjacent pair: gallop+bisect for the cell range              latency/L2
-//   scans          cell counts (int, CUB) and segmented moment prefix sums (double4, det_scan.cuh)  HBM
-//   emit (K3/K4)   pre-order node array: particles and cells with mass, CoM, len^2/theta^2, end HBM
+//   scan           cell counts (int, CUB)                                                       HBM
+//   emit (K3/K4)   pre-order node array: particles, cell links (len^2/theta^2, end), then cell mass and centre of mass bottom-up,
+//                  one launch per tree depth, with the reference's own (hierarchically rounded) summation   HBM
 //
 // Every pass is a streaming, coalesced read of 4..32 B per source particle; grids are sized in
 // multiples of the SM count by the launch helpers.
@@ -18,7 +19,6 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include "device_tree.cuh"
-#include "det_scan.cuh"
 
 namespace hbt
 {
@@ -221,27 +221,6 @@ struct PopcOp
   }
 };
 
-struct MomentOp
-{ // value of sorted particle k: m and m*(x - root centre) in double (src/gravity_tree.cpp:27-30 accumulates in double)
-  const float4 *spos;
-  const int *ts_seg;
-  const SegRoot *roots;
-  __device__ double4s operator()(int64_t k) const
-  {
-    float4 p = spos[k];
-    const SegRoot &r = roots[ts_seg[k]];
-    double m = (double)p.w;
-    return double4s{m, m * ((double)p.x - r.cx), m * ((double)p.y - r.cy), m * ((double)p.z - r.cz)};
-  }
-};
-struct Double4Plus
-{
-  __host__ __device__ double4s operator()(const double4s &a, const double4s &b) const
-  {
-    return double4s{a.m + b.m, a.x + b.x, a.y + b.y, a.z + b.z};
-  }
-};
-
 __global__ void __launch_bounds__(kBlock) emit_particles_kernel(const float4 *__restrict__ spos, const int *__restrict__ cellcount, int S,
                                                                  float4 *__restrict__ node_xm, float2 *__restrict__ node_aux)
 {
@@ -252,11 +231,11 @@ __global__ void __launch_bounds__(kBlock) emit_particles_kernel(const float4 *__
   node_aux[pos] = make_float2(0.f, __int_as_float((int)(pos + 1)));
 }
 
-__global__ void __launch_bounds__(kBlock) emit_cells_kernel(const int2 *__restrict__ cell_lr, const int8_t *__restrict__ cell_depth,
-                                                             const uint32_t *__restrict__ depthmask, const int *__restrict__ cellcount,
-                                                             const double4s *__restrict__ msum, const int *__restrict__ ts_seg,
-                                                             const int *__restrict__ tree_off, const SegRoot *__restrict__ roots, float theta2,
-                                                             int S, float4 *__restrict__ node_xm, float2 *__restrict__ node_aux)
+// cells, pass 1: geometry and links of every cell (len^2/theta^2 and `end`), and where it sits in the pre-order array
+__global__ void __launch_bounds__(kBlock) emit_cell_links_kernel(const int2 *__restrict__ cell_lr, const int8_t *__restrict__ cell_depth,
+                                                                  const uint32_t *__restrict__ depthmask, const int *__restrict__ cellcount,
+                                                                  const int *__restrict__ ts_seg, const SegRoot *__restrict__ roots, float theta2, int S,
+                                                                  float2 *__restrict__ node_aux, int *__restrict__ cell_pos)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
@@ -265,18 +244,51 @@ __global__ void __launch_bounds__(kBlock) emit_cells_kernel(const int2 *__restri
   CellRange c;
   int2 lr = cell_lr[k];
   c.l = lr.x; c.r = lr.y; c.depth = depth; c.is_rep = 1;
-  int a = ts_seg[k];
-  const SegRoot root = roots[a];
-  double4s hi = msum[c.r];
-  double4s lo = (c.l > tree_off[a]) ? msum[c.l - 1] : double4s{0., 0., 0., 0.};
-  double M = hi.m - lo.m;
-  float lenf = cell_len(root, depth);
+  float lenf = cell_len(roots[ts_seg[k]], depth);
   // reference MAC: (float)(len*len) > r2*theta2 (src/gravity_tree.cpp:135); stored as len^2/theta^2
   float lenq = __fdiv_rn(__fmul_rn(lenf, lenf), theta2);
   int64_t pos = cell_node_pos(c, cellcount, depthmask);
-  node_xm[pos] = make_float4((float)(root.cx + (hi.x - lo.x) / M), (float)(root.cy + (hi.y - lo.y) / M),
-                             (float)(root.cz + (hi.z - lo.z) / M), (float)M);
   node_aux[pos] = make_float2(lenq, __int_as_float((int)cell_node_end(c, cellcount)));
+  cell_pos[k] = (int)pos;
+}
+
+// cells, pass 2 (one launch per depth, deepest first): mass and centre of mass exactly as the reference computes them
+// (GravityTree_t::UpdateInternalNodes / ProcessNode / FillNodeCenter, src/gravity_tree.cpp:18-77): a cell sums its CHILDREN's
+// stored HBTReal = float mass and centre (a particle's position, a child cell's already rounded centre) in son order, in double,
+// and rounds the results to float once more.  Rounding therefore accumulates level by level; summing the particles directly
+// (one rounding) gives centres that differ from the reference's by up to an ulp of the COORDINATE - 4e-6 at x ~ 50, which is
+// 1e-3 of the node distances inside an AqA2-sized subhalo and showed up as a 1e-5 mean potential difference (and with it a
+// few E ~ 0 membership flips per thousand subhaloes).  With the reference's own summation the potentials agree to 1e-8.
+// Children have more shared key digits than their parent, so depth order is dependency order; cells of one depth are independent.
+__global__ void __launch_bounds__(kBlock) cell_moments_level_kernel(const int8_t *__restrict__ cell_depth, const int *__restrict__ cell_pos, int S,
+                                                                     int depth, const float2 *__restrict__ node_aux, float4 *__restrict__ node_xm)
+{
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (k0 >= S) return;
+  // 16 depth bytes per thread (S is padded to a multiple of 16 by the caller's allocation)
+  const uint4 d16 = *reinterpret_cast<const uint4 *>(cell_depth + k0);
+  const unsigned w[4] = {d16.x, d16.y, d16.z, d16.w};
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+  {
+    const int d = (int)(int8_t)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+    if (d != depth || k0 + q >= S) continue;
+    const int pos = cell_pos[k0 + q];
+    const int end = __float_as_int(node_aux[pos].y);
+    double M = 0., cx = 0., cy = 0., cz = 0.;
+    for (int c = pos + 1; c < end;)
+    {
+      const float4 xm = node_xm[c];
+      const int nxt = __float_as_int(node_aux[c].y);
+      const double m = (double)xm.w;
+      M = __dadd_rn(M, m);
+      cx = __dadd_rn(cx, __dmul_rn((double)xm.x, m)); // VectorAdd(CoM, pos, thismass): the product is exact in double
+      cy = __dadd_rn(cy, __dmul_rn((double)xm.y, m));
+      cz = __dadd_rn(cz, __dmul_rn((double)xm.z, m));
+      c = nxt;
+    }
+    node_xm[pos] = make_float4((float)__ddiv_rn(cx, M), (float)__ddiv_rn(cy, M), (float)__ddiv_rn(cz, M), (float)M);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -338,7 +350,7 @@ void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t
 
   // cells ---------------------------------------------------------------------------------------------
   t.cell_lr = arena.alloc<int2>(S);
-  t.cell_depth = arena.alloc<int8_t>(S);
+  t.cell_depth = arena.alloc<int8_t>(S + 16); // read 16 bytes at a time by cell_moments_level_kernel
   t.depthmask = arena.alloc<uint32_t>(S);
   t.cellcount = arena.alloc<int>(S);
   HBT_CUDA(cudaMemsetAsync(t.depthmask, 0, sizeof(uint32_t) * (size_t)S, stream));
@@ -353,26 +365,22 @@ void build_trees(TreeArrays &t, Arena &arena, const DevConfig &cfg, cudaStream_t
     HBT_CUDA(cub::DeviceScan::InclusiveSum(tm, b, in, t.cellcount, S, stream));
     ls.launches += 2;
   }
-  t.msum = arena.alloc<double4s>(S);
-  { // per-tree prefix sums of m, m*(x - centre) in double with a FIXED combination tree aligned to each tree (det_scan.cuh):
-    // node masses and centres of mass - and with them every potential - are the same bits on every run and in every batch
-    std::vector<int> tile_off;
-    const int ntiles = scan_tile_table(t.h_tree_off, nseg, tile_off);
-    int *d_tile_off = arena.alloc<int>(nseg + 1);
-    HBT_CUDA(cudaMemcpyAsync(d_tile_off, tile_off.data(), sizeof(int) * (size_t)(nseg + 1), cudaMemcpyHostToDevice, stream));
-    det_inclusive_scan_segments<double4s, Double4Plus>(arena, stream, t.tree_off, d_tile_off, nseg, ntiles, MomentOp{t.spos, t.ts_seg, t.roots},
-                                                       double4s{0., 0., 0., 0.}, t.msum, ls.launches);
-    HBT_CUDA(cudaStreamSynchronize(stream)); // tile_off is a host temporary
-  }
   // nodes ---------------------------------------------------------------------------------------------
   t.node_xm = arena.alloc<float4>(2 * (int64_t)S + 64); // +pad: the walk stages 32 nodes without a bounds check
   t.node_aux = arena.alloc<float2>(2 * (int64_t)S + 64);
+  int *cell_pos = arena.alloc<int>(S);
   emit_particles_kernel<<<grid_for(S), kBlock, 0, stream>>>(t.spos, t.cellcount, S, t.node_xm, t.node_aux);
   HBT_CHECK_LAUNCH();
-  emit_cells_kernel<<<grid_for(S), kBlock, 0, stream>>>(t.cell_lr, t.cell_depth, t.depthmask, t.cellcount, t.msum, t.ts_seg, t.tree_off,
-                                                        t.roots, cfg.theta2, S, t.node_xm, t.node_aux);
+  emit_cell_links_kernel<<<grid_for(S), kBlock, 0, stream>>>(t.cell_lr, t.cell_depth, t.depthmask, t.cellcount, t.ts_seg, t.roots, cfg.theta2, S,
+                                                             t.node_aux, cell_pos);
   HBT_CHECK_LAUNCH();
   ls.launches += 2;
+  for (int depth = kMaxDepth; depth >= 0; depth--)
+  { // the reference's bottom-up moments, level by level (see cell_moments_level_kernel)
+    cell_moments_level_kernel<<<grid_for(div_up(S, 16)), kBlock, 0, stream>>>(t.cell_depth, cell_pos, S, depth, t.node_aux, t.node_xm);
+    HBT_CHECK_LAUNCH();
+  }
+  ls.launches += kMaxDepth + 1;
 }
 
 } // namespace hbt

@@ -462,6 +462,21 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       int sa = 0, sd = 0;
       for (int r = 0; r < NP; r++) { sa += __popc(mAc[r]); sd += __popc(mD[r]); }
       HBT_MASKED_STAT(0, __popc(mA)); HBT_MASKED_STAT(1, sa); HBT_MASKED_STAT(2, sd); HBT_MASKED_STAT(3, __popc(mP)); HBT_MASKED_STAT(4, cO);
+      // pair-elements with targets in only ONE slice of the pair, and the lanes (of 64 lane-slots) inside the masks
+      for (int r = 0; r < NP; r++)
+      {
+        const bool single = hp[r] && (cm[2 * r] == 0u || cm[2 * r + 1] == 0u);
+        const unsigned sA = __ballot_sync(kFull, toAcc && single), sD = __ballot_sync(kFull, toD && bare && single);
+        HBT_MASKED_STAT(5, __popc(sA)); HBT_MASKED_STAT(6, __popc(sD));
+        int bitsA = 0, bitsD = 0;
+        for (int l = 0; l < 32; l++)
+        {
+          const unsigned b0 = __shfl_sync(kFull, cm[2 * r], l), b1 = __shfl_sync(kFull, cm[2 * r + 1], l);
+          if ((mAc[r] >> l) & 1u) bitsA += __popc(b0) + __popc(b1);
+          if ((mD[r] >> l) & 1u) bitsD += __popc(b0) + __popc(b1);
+        }
+        HBT_MASKED_STAT(7, bitsA); HBT_MASKED_STAT(8, bitsD);
+      }
     }
 #endif
     na += __popc(mA);

@@ -213,12 +213,27 @@ struct Batch
     std::vector<Particle_t> all(N); // the reference's Unbind also makes one full copy (subhalo_unbind.cpp:409-415)
     float *pos_mass = dev->pos_mass.get(4 * (size_t)N), *vel = dev->vel.get(4 * (size_t)N);
     std::vector<hbtu_sub_io> io(nsub);
-#pragma omp parallel for schedule(dynamic, 16)
+    // work items of the pack / unpack loops: (subhalo, chunk of <= kChunk particles), so that a dominant subhalo (an AqA2
+    // central holds 72 % of the particles) is packed by all threads instead of one
+    constexpr int64_t kChunk = 1 << 16;
+    std::vector<int64_t> item_sub, item_begin;
     for (int64_t s = 0; s < nsub; s++)
     {
-      const Subhalo_t &sub = *subs[s];
-      int64_t b = part_offset[s];
-      for (size_t i = 0; i < sub.Particles.size(); i++)
+      const int64_t n = part_offset[s + 1] - part_offset[s];
+      for (int64_t b0 = 0; b0 < n || b0 == 0; b0 += kChunk)
+      {
+        item_sub.push_back(s);
+        item_begin.push_back(b0);
+      }
+    }
+    const int64_t nitems = (int64_t)item_sub.size();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t it = 0; it < nitems; it++)
+    {
+      const Subhalo_t &sub = *subs[item_sub[it]];
+      const int64_t b = part_offset[item_sub[it]];
+      const int64_t i1 = std::min<int64_t>(item_begin[it] + kChunk, (int64_t)sub.Particles.size());
+      for (int64_t i = item_begin[it]; i < i1; i++)
       {
         const Particle_t &p = sub.Particles[i];
         all[b + i] = p;
@@ -231,6 +246,11 @@ struct Batch
         v[3] = 0.f;
 #endif
       }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < nsub; s++)
+    {
+      const Subhalo_t &sub = *subs[s];
       hbtu_sub_io &o = io[s];
       std::memset(&o, 0, sizeof(o));
       for (int j = 0; j < 3; j++)
@@ -270,14 +290,32 @@ struct Batch
     call_library_locked(dev, "hbtu_unbind_batch", [&](hbtu_ctx *ctx) {
       return hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass, vel, no, nl, io.data(), flags, cap, order_offset.data(), order, pe);
     });
+    // unpack: the new particle lists (a list can hold particles of nested subhaloes: gather from the batch-wide copy), in chunks
+    // like the pack; the vectors are resized first (serially per subhalo, cheap) so that the chunks can write independently
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t s = 0; s < nsub; s++) subs[s]->Particles.resize(io[s].nsource);
+    std::vector<int64_t> out_sub, out_begin;
+    for (int64_t s = 0; s < nsub; s++)
+      for (int64_t b0 = 0; b0 < io[s].nsource; b0 += kChunk)
+      {
+        out_sub.push_back(s);
+        out_begin.push_back(b0);
+      }
+    const int64_t nout = (int64_t)out_sub.size();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t it = 0; it < nout; it++)
+    {
+      const int64_t s = out_sub[it];
+      Subhalo_t &sub = *subs[s];
+      const int32_t *ord = &order[order_offset[s]];
+      const int64_t i1 = std::min<int64_t>(out_begin[it] + kChunk, io[s].nsource);
+      for (int64_t i = out_begin[it]; i < i1; i++) sub.Particles[i] = all[ord[i]];
+    }
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t s = 0; s < nsub; s++)
     {
       Subhalo_t &sub = *subs[s];
       const hbtu_sub_io &o = io[s];
-      sub.Particles.resize(o.nsource);
-      const int32_t *ord = &order[order_offset[s]];
-      for (int64_t i = 0; i < o.nsource; i++) sub.Particles[i] = all[ord[i]];
       for (int j = 0; j < 3; j++)
       {
         sub.ComovingAveragePosition[j] = o.avg_pos[j];

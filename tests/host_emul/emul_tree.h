@@ -75,5 +75,29 @@ static int emul_build_nodes(const hbtu_params *p, int64_t n, const float *src, s
                         (float)(root.cz + (S[4 * (c.r + 1) + 3] - S[4 * c.l + 3]) / M), (float)M, lenq, (int)cell_node_end(c, cinc.data())};
     }
   for (int64_t i = 0; i < nn; i++) if (!written[i]) return -102;
+  // Node masses and centres as the REFERENCE computes them (src/gravity_tree.cpp:18-77): a cell sums its CHILDREN's stored
+  // HBTReal = float mass and centre (not the particles), in son order, in double, and rounds to float once more - so rounding
+  // accumulates level by level.  Children have more shared digits than their parent: deepest cells first.
+  if (!getenv("EMUL_FLAT_MOMENTS"))
+    for (int d = kMaxDepth; d >= 0; d--)
+      for (int64_t i = 0; i + 1 < n; i++)
+        if (cells[i].is_rep && cells[i].depth == d)
+        {
+          const int64_t pos = cell_node_pos(cells[i], cinc.data(), mask.data());
+          const int end = nodes[pos].end;
+          double M = 0., cx = 0., cy = 0., cz = 0.;
+          for (int64_t c = pos + 1; c < end; c = nodes[c].end)
+          {
+            const double m = (double)nodes[c].m;
+            M += m;
+            cx += (double)nodes[c].x * m;
+            cy += (double)nodes[c].y * m;
+            cz += (double)nodes[c].z * m;
+          }
+          nodes[pos].x = (float)(cx / M);
+          nodes[pos].y = (float)(cy / M);
+          nodes[pos].z = (float)(cz / M);
+          nodes[pos].m = (float)M;
+        }
   return 0;
 }

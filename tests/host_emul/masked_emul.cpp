@@ -7,7 +7,7 @@
 using hbt::float_to_ordered;
 using hbt::ordered_to_float;
 static int g_max_ncs = 0;
-static int64_t g_hist[8];
+static int64_t g_hist[16];
 #define HBT_MASKED_STAT_ON 1
 #define HBT_MASKED_STAT(what, n) do { if (wemu::g_cur == 0) g_hist[what] += (n); } while (0)
 #define HBT_MASKED_TRACK(ncs) do { if ((ncs) > g_max_ncs) g_max_ncs = (ncs); } while (0)
@@ -125,7 +125,8 @@ extern "C" int emul_masked_walk(const hbtu_params *p, int64_t n, const float *sr
     acc_scalar[t] = acc;
   }
   if (getenv("EMUL_VERBOSE")) fprintf(stderr, "per group: dense-ring nodes %.0f accept-all elements %.0f deciding elements (bare) %.0f pending chains %.0f open cells %.0f\n", (double)g_hist[0] / groups, (double)g_hist[1] / groups, (double)g_hist[2] / groups, (double)g_hist[3] / groups, (double)g_hist[4] / groups);
-  for (int q = 0; q < 8; q++) g_hist[q] = 0;
+  if (getenv("EMUL_VERBOSE")) fprintf(stderr, "  single-slice pair-elements: accept-all %.0f deciding %.0f; targets inside the masks per pair-element: accept-all %.1f deciding %.1f (of 64)\n", (double)g_hist[5] / groups, (double)g_hist[6] / groups, (double)g_hist[7] / std::max<int64_t>(1, g_hist[1]), (double)g_hist[8] / std::max<int64_t>(1, g_hist[2]));
+  for (int q = 0; q < 16; q++) g_hist[q] = 0;
   if (stats) { stats[0] = overflows; stats[1] = iters; stats[2] = (int64_t)wemu::g_ncollectives; stats[3] = groups; }
   return 0;
 }

@@ -135,6 +135,13 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v)
   wemu::barrier();
   return r;
 }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src)
+{
+  wemu::exchange(5, v);
+  const unsigned r = (unsigned)wemu::g_slot[src & 31];
+  wemu::barrier();
+  return r;
+}
 static inline void __syncwarp()
 {
   wemu::exchange(4, 0);
