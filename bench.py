@@ -668,7 +668,7 @@ def main():
             other_ms.append(st.other_ms)
         barrier()
         # end to end through the ABI call, pinned host buffers in, host arrays out
-        e2e_wall, e2e_h2d, e2e_d2h = [], 0, 0
+        e2e_wall, e2e_h2d, e2e_d2h, e2e_parts = [], 0, 0, None
         res = None
         cap = capi.order_capacity(snap.part_offset, snap.nest_offset, snap.nest_list)
         order_pinned = torch.empty(max(cap, 1), dtype=torch.int32, pin_memory=True).numpy()  # caller-owned output buffer, as a host shim would keep
@@ -681,6 +681,7 @@ def main():
                 e2e_wall.append(dt)
             st = ctx.stats()
             e2e_h2d, e2e_d2h = st.h2d_bytes, st.d2h_bytes
+            e2e_parts = {"h2d_ms_async": st.h2d_ms, "execute_ms": st.execute_ms, "d2h_ms": st.d2h_ms, "wall_ms": dt * 1e3}
     clocks = clk.summary()
     launches = ctx.stats().kernel_launches
 
@@ -740,7 +741,9 @@ def main():
                        "phase_rooflines": phase_rooflines(st0, float(np.mean(build_ms)), float(np.mean(other_ms)), peaks)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h),
-                    "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "steps": len(e2e_wall), "api": "hbtu_unbind_batch from pinned host buffers"},
+                    "ms_per_step": t_e2e * 1e3 / max(len(e2e_wall), 1), "steps": len(e2e_wall), "api": "hbtu_unbind_batch from pinned host buffers",
+                    "last_call_breakdown": e2e_parts,
+                    "overlap": "uploads on a copy stream in two waves: everything but the dominant root first, the dominant root behind the kernels of the deeper levels"},
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "fp32_issue", "achieved": inter_rate * FLOP_PER_INTERACTION / 1e12, "peak": peak_inter * FLOP_PER_INTERACTION / 1e12,
                          "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "traffic_kernel": traffic_note,

@@ -180,13 +180,13 @@ int walk_class_tpl(int index); // targets_per_lane value of class `index` (the g
 
 // kernel routing knobs (process-wide; defaults = measured best, HBTU_* environment variables and hbtu_set_tuning override)
 #ifndef HBT_MASKED_DEFAULT_PAIRS
-#define HBT_MASKED_DEFAULT_PAIRS 2
+#define HBT_MASKED_DEFAULT_PAIRS 1 // measured on the bench (profiles/r02_walk_notes.md): 64-target groups at 7 CTAs/SM beat 128-target groups at 5
 #endif
 #ifndef HBT_MASKED_DEFAULT_BLOCKS_NP2
 #define HBT_MASKED_DEFAULT_BLOCKS_NP2 5
 #endif
 #ifndef HBT_MASKED_DEFAULT_BLOCKS_NP1
-#define HBT_MASKED_DEFAULT_BLOCKS_NP1 8
+#define HBT_MASKED_DEFAULT_BLOCKS_NP1 7
 #endif
 #ifndef HBT_SMALL_DEFAULT_MAX
 #define HBT_SMALL_DEFAULT_MAX 0
