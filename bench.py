@@ -681,7 +681,8 @@ def main():
                 e2e_wall.append(dt)
             st = ctx.stats()
             e2e_h2d, e2e_d2h = st.h2d_bytes, st.d2h_bytes
-            e2e_parts = {"h2d_ms_async": st.h2d_ms, "execute_ms": st.execute_ms, "d2h_ms": st.d2h_ms, "wall_ms": dt * 1e3}
+            e2e_parts = {"h2d_ms_async": st.h2d_ms, "execute_ms": st.execute_ms, "d2h_ms": st.d2h_ms, "wall_ms": dt * 1e3,
+                         "stage_wall_ms": st.stage_wall_ms, "execute_wall_ms": st.execute_wall_ms, "fetch_wall_ms": st.fetch_wall_ms}
     clocks = clk.summary()
     launches = ctx.stats().kernel_launches
 

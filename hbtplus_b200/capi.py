@@ -102,6 +102,9 @@ class Stats(C.Structure):
         ("execute_ms", C.c_double),
         ("tree_sources", C.c_int64),
         ("walk_fallbacks", C.c_int64),
+        ("stage_wall_ms", C.c_double),
+        ("execute_wall_ms", C.c_double),
+        ("fetch_wall_ms", C.c_double),
     ]
 
 

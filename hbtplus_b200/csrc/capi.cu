@@ -5,6 +5,7 @@
 // sm_100 device is usable hbtu_create fails with HBTU_ERR_NODEVICE.
 #include <cub/cub.cuh>
 
+#include <chrono>
 #include <cstring>
 #include <new>
 
@@ -15,6 +16,14 @@ using namespace hbt;
 namespace
 {
 thread_local std::string g_create_error;
+
+struct WallTimer
+{ // host wall clock of an entry point, added to a hbtu_stats field when it goes out of scope
+  double &slot;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit WallTimer(double &s) : slot(s) {}
+  ~WallTimer() { slot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 template <class T>
 void grow(T *&p, int64_t &cap, int64_t need)
@@ -480,16 +489,23 @@ int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int6
 int hbtu_stage(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
                const float *vel, const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags)
 {
-  return guarded(ctx, [&](Context &c) { stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags); });
+  return guarded(ctx, [&](Context &c) {
+    WallTimer wt(c.stats.stage_wall_ms);
+    stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags);
+  });
 }
 int hbtu_execute(hbtu_ctx *ctx)
 {
-  return guarded(ctx, [&](Context &c) { execute_batch(c); });
+  return guarded(ctx, [&](Context &c) {
+    WallTimer wt(c.stats.execute_wall_ms);
+    execute_batch(c);
+  });
 }
 int hbtu_fetch(hbtu_ctx *ctx, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
 {
   return guarded(ctx, [&](Context &c) {
     if (!io || !order_offset || (!order_out && order_capacity > 0)) throw CudaError{HBTU_ERR_INVALID, "null output"};
+    WallTimer wt(c.stats.fetch_wall_ms);
     fetch_batch(c, io, order_capacity, order_offset, order_out, energy_out);
   });
 }
@@ -499,7 +515,10 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
 {
   // stage with the uploads on the copy stream (they overlap the kernels of the deeper nesting levels when the source arrays
   // are pinned - hbtu_host_alloc - and are plain staged copies otherwise), then execute + fetch
-  int rc = guarded(ctx, [&](Context &c) { stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags, true); });
+  int rc = guarded(ctx, [&](Context &c) {
+    WallTimer wt(c.stats.stage_wall_ms);
+    stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags, true);
+  });
   if (rc == HBTU_OK) rc = hbtu_execute(ctx);
   if (rc != HBTU_OK)
   { // never leave copies from the caller's buffers in flight behind an error return

@@ -1158,7 +1158,9 @@ void execute_batch(Context &c)
   cudaStream_t st = c.stream;
   const int nsub = (int)c.nsub;
   c.ls.launches = 0;
-  std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms));
+  std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms)); // the copy statistics of the staging call survive
+  c.stats.tree_sources = 0;
+  c.stats.walk_fallbacks = 0;
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
   if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, kWalkCounters * sizeof(unsigned long long), st));
 

@@ -33,13 +33,18 @@
 #define HBT_M_UNROLL 4 // unroll factor of the dense / accept-all list loops (2 -> 4: 1045 -> 992 ms, profiles/r01_walk_notes.md)
 #endif
 #ifndef HBT_M_UNROLL_D
-#define HBT_M_UNROLL_D 2 // unroll factor of the branch-free deciding loop
+#define HBT_M_UNROLL_D 4 // unroll factor of the branch-free deciding loop (2 -> 4: 956 -> 926 ms, profiles/r02_walk_notes.md)
 #endif
 #ifndef HBT_M_PEND
 #define HBT_M_PEND 8 // deciding elements / pending chains are drained when more than this many wait ...
 #endif
 #ifndef HBT_A_PEND
 #define HBT_A_PEND 16 // accept-all elements are evaluated when more than this many wait
+#endif
+#ifndef HBT_M_PREFETCH
+#define HBT_M_PREFETCH 1 // a lane that stays on its chain loads its NEXT node right after classifying the current one, so that the
+                         // L2 latency of the node arrays hides behind the list evaluations (ncu: 8 % of all stall samples sat on the
+                         // first use of the loaded node, profiles/r02_walk_notes.md)
 #endif
 #define HBT_M_PRAGMA_(x) _Pragma(#x)
 #define HBT_M_PRAGMA_UNROLL(n) HBT_M_PRAGMA_(unroll n)
@@ -315,6 +320,11 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
 #pragma unroll
   for (int k = 0; k < T; k++) cm[k] = 0u;
   bool full = false; // ... it is the whole group
+#if HBT_M_PREFETCH
+  float4 pre_xm = make_float4(0.f, 0.f, 0.f, 0.f); // the node the lane will stand on next, loaded ahead
+  float2 pre_ax = make_float2(0.f, 0.f);
+  bool pre = false;
+#endif
   while (true)
   {
     const unsigned mI = __ballot_sync(kFull, !(cur < pend));
@@ -337,6 +347,9 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
           bits += __popc(cm[k]);
         }
         full = bits == n0;
+#if HBT_M_PREFETCH
+        pre = false;
+#endif
       }
       ncs -= t;
       __syncwarp();
@@ -355,8 +368,14 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     bool bare = false; // no accepted pair can be softened and the group sees one periodic image of the node
     if (act)
     {
+#if HBT_M_PREFETCH
+      float2 ax;
+      if (pre) { xm = pre_xm; ax = pre_ax; }
+      else { xm = __ldg(&node_xm[cur]); ax = __ldg(&node_aux[cur]); }
+#else
       xm = __ldg(&node_xm[cur]);
       const float2 ax = __ldg(&node_aux[cur]);
+#endif
       lenq = ax.x;
       kend = __float_as_int(ax.y);
       const float4 bc = *reinterpret_cast<const float4 *>(&sm.box[0]), bh = *reinterpret_cast<const float4 *>(&sm.box[4]);
@@ -490,6 +509,14 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       nac[r] += __popc(mAc[r]);
     }
     if (act) cur = kend;
+#if HBT_M_PREFETCH
+    pre = act && cur < pend;
+    if (pre)
+    { // the sibling the lane moves to: its loads overlap the list evaluations below and the next iteration's bookkeeping
+      pre_xm = __ldg(&node_xm[cur]);
+      pre_ax = __ldg(&node_aux[cur]);
+    }
+#endif
     __syncwarp();
     if (na >= 32)
     {

@@ -326,6 +326,9 @@ typedef struct hbtu_stats
   double execute_ms;           /* CUDA-event time of the whole hbtu_execute (host planning gaps included) */
   int64_t tree_sources;        /* source particles over all tree builds (sum over rounds)                */
   int64_t walk_fallbacks;      /* counting on: groups of the masked walk redone per lane (chain stack exhausted) */
+  double stage_wall_ms;        /* host wall clock inside hbtu_stage / the staging part of hbtu_unbind_batch          */
+  double execute_wall_ms;      /* host wall clock inside hbtu_execute                                                */
+  double fetch_wall_ms;        /* host wall clock inside hbtu_fetch                                                  */
 } hbtu_stats;
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted
