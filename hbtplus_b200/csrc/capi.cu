@@ -459,6 +459,7 @@ void hbtu_destroy(hbtu_ctx *ctx)
   cudaFree(c.d_part_offset);
   cudaFree(c.d_slot_base);
   cudaFree(c.d_counters);
+  if (c.h_ring) cudaFreeHost(c.h_ring);
   for (auto &ev : c.ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c.ev_exec)

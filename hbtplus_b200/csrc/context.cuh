@@ -63,12 +63,21 @@ struct Context
   hbtu_allreduce_fn split_fn = nullptr;
   void *split_user = nullptr;
 
+  // Small host tables (segments, offsets, job lists, the initial SubState records) reach the device through a pinned, MAPPED
+  // staging ring and a copy kernel on the compute stream, not through cudaMemcpyAsync: the DMA engine serves host-to-device
+  // copies first-in-first-out across streams, so a 16-byte table copy issued while hbtu_unbind_batch's multi-GB particle
+  // upload is in flight would wait for all of it (measured: 104 ms per step) - the SMs read the ring over PCIe instead.
+  char *h_ring = nullptr, *d_ring = nullptr; // host pointer / device alias of the ring
+  size_t ring_cap = 0, ring_used = 0;
+
   Arena arena;
   LaunchStats ls;
   hbtu_stats stats{};
 };
 
 void execute_batch(Context &c);
+// stage `bytes` of host data in the ring and copy them to `dst` (device) with a kernel on c.stream (context.cuh: h_ring)
+void upload_bytes(Context &c, void *dst, const void *src, size_t bytes);
 // profile.cu: Subhalo_t::CalculateProfileProperties + CalculateShape for a batch of particle lists
 void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io);
 void profile_executed(Context &c, hbtu_profile_io *io);

@@ -748,11 +748,43 @@ __global__ void __launch_bounds__(kBlock) pack_output_kernel(const int64_t *__re
 // ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
-template <class T>
-static T *upload(Arena &arena, const std::vector<T> &v, cudaStream_t stream)
+__global__ void __launch_bounds__(kBlock) ring_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
 {
-  T *d = arena.alloc<T>((int64_t)v.size());
-  if (!v.empty()) HBT_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, stream));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+void upload_bytes(Context &c, void *dst, const void *src, size_t bytes)
+{
+  if (bytes == 0) return;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (c.ring_used + need > c.ring_cap)
+  { // wrap: everything staged so far must have been consumed
+    HBT_CUDA(cudaStreamSynchronize(c.stream));
+    c.ring_used = 0;
+    if (need > c.ring_cap)
+    {
+      if (c.h_ring) cudaFreeHost(c.h_ring);
+      c.h_ring = c.d_ring = nullptr;
+      c.ring_cap = 0;
+      const size_t cap = std::max<size_t>(need * 2, (size_t)16 << 20);
+      HBT_CUDA(cudaHostAlloc((void **)&c.h_ring, cap, cudaHostAllocMapped));
+      HBT_CUDA(cudaHostGetDevicePointer((void **)&c.d_ring, c.h_ring, 0));
+      c.ring_cap = cap;
+    }
+  }
+  std::memcpy(c.h_ring + c.ring_used, src, bytes);
+  const size_t n16 = need / 16;
+  const int grid = (int)std::min<size_t>((n16 + kBlock - 1) / kBlock, 148 * 4);
+  ring_copy_kernel<<<grid, kBlock, 0, c.stream>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(c.d_ring + c.ring_used), n16);
+  HBT_CHECK_LAUNCH();
+  c.ring_used += need;
+}
+
+template <class T>
+static T *upload(Context &c, const std::vector<T> &v)
+{ // arena allocations are 256-byte aligned and padded, so the 16-byte granularity of the copy kernel stays inside them
+  T *d = c.arena.alloc<T>((int64_t)v.size() + 16 / sizeof(T) + 1);
+  if (!v.empty()) upload_bytes(c, d, v.data(), sizeof(T) * v.size());
   return d;
 }
 
@@ -762,8 +794,8 @@ static T *upload(Arena &arena, const std::vector<T> &v, cudaStream_t stream)
 static void run_seg_copy(Context &c, const std::vector<CopyJob> &jobs, const std::vector<int64_t> &job_off, const int *src, int *dst)
 {
   if (jobs.empty() || job_off.back() == 0) return;
-  CopyJob *d_jobs = upload(c.arena, jobs, c.stream);
-  int64_t *d_off = upload(c.arena, job_off, c.stream);
+  CopyJob *d_jobs = upload(c, jobs);
+  int64_t *d_off = upload(c, job_off);
   int64_t total = job_off.back();
   seg_copy_kernel<<<grid_for(total), kBlock, 0, c.stream>>>(d_jobs, d_off, (int)jobs.size(), total, src, dst);
   HBT_CHECK_LAUNCH();
@@ -832,10 +864,10 @@ static void run_round(Context &c, std::vector<int> &active)
   ar.reset();
   ar.reserve(tree_arena_bytes(S, nseg) + T * 68 + (int64_t)nseg * 128);
   cudaStream_t st = c.stream;
-  Segment *d_segs = upload(ar, segs, st);
-  int *d_tree_off = upload(ar, tree_off, st), *d_tgt_off = upload(ar, tgt_off, st);
+  Segment *d_segs = upload(c, segs);
+  int *d_tree_off = upload(c, tree_off), *d_tgt_off = upload(c, tgt_off);
   int *d_warp_off[kWalkClasses];
-  for (int q = 0; q < kWalkClasses; q++) d_warp_off[q] = upload(ar, warp_off[q], st);
+  for (int q = 0; q < kWalkClasses; q++) d_warp_off[q] = upload(c, warp_off[q]);
 
   HBT_CUDA(cudaEventRecord(c.ev[0], st));
   TreeArrays tr;
@@ -975,7 +1007,7 @@ static void run_round(Context &c, std::vector<int> &active)
   static_assert(kBlock == kSegBlock, "seg_reduce.cuh blocks");
   std::vector<int> chunk_off;
   const int nchunk = seg_chunk_table(nseg, [&](int a) { return segs[a].tgt_n; }, chunk_off);
-  int *d_chunk_off = upload(ar, chunk_off, st);
+  int *d_chunk_off = upload(c, chunk_off);
   double *partial = ar.alloc<double>((int64_t)nchunk * 7);
   if (nchunk > 0)
   {
@@ -1002,6 +1034,7 @@ static void run_round(Context &c, std::vector<int> &active)
   std::vector<RoundResult> res(nseg);
   HBT_CUDA(cudaMemcpyAsync(res.data(), d_res, sizeof(RoundResult) * nseg, cudaMemcpyDeviceToHost, st));
   HBT_CUDA(cudaStreamSynchronize(st));
+  c.ring_used = 0; // every staged table of this round has been consumed
   float ms = 0;
   cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
   c.stats.build_ms += ms;
@@ -1086,8 +1119,8 @@ static void run_refine(Context &c, const std::vector<int> &list)
   ar.reset();
   ar.reserve(tree_arena_bytes(S, nseg) + S * 96 + (int64_t)nseg * 128);
   cudaStream_t st = c.stream;
-  Segment *d_segs = upload(ar, segs, st);
-  int *d_off = upload(ar, off, st), *d_woff = upload(ar, woff, st);
+  Segment *d_segs = upload(c, segs);
+  int *d_off = upload(c, off), *d_woff = upload(c, woff);
   TreeArrays tr;
   tr.S = (int)S;
   tr.nseg = nseg;
@@ -1204,7 +1237,7 @@ void execute_batch(Context &c)
     h.iterations = 0;
     h.is_orphan = orphan;
   }
-  HBT_CUDA(cudaMemcpyAsync(c.d_subs, init.data(), sizeof(SubState) * nsub, cudaMemcpyHostToDevice, st));
+  upload_bytes(c, c.d_subs, init.data(), sizeof(SubState) * nsub); // d_subs holds nsub + 1 records: room for the 16-byte granularity
   if (c.N > 0)
   {
     init_ids_kernel<<<grid_for(c.N), kBlock, 0, st>>>(c.d_part_offset, c.d_slot_base, nsub, c.N, c.d_ids);
@@ -1293,7 +1326,7 @@ void execute_batch(Context &c)
       run_seg_copy(c, snap, snap_off, c.d_ids, c.d_ids_orig);
     }
     { // n_src, the entry value of Particles[0] and the active flag on the device
-      LevelInit *d_li = upload(c.arena, li, st);
+      LevelInit *d_li = upload(c, li);
       level_init_kernel<<<grid_for((int64_t)li.size()), kBlock, 0, st>>>(d_li, (int)li.size(), c.d_subs, c.d_ids);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
@@ -1305,8 +1338,8 @@ void execute_batch(Context &c)
       Arena &ar = c.arena;
       ar.reset();
       ar.reserve(total * 40 + (int64_t)shuf.size() * 64 + (64 << 20));
-      ShuffleJob *d_jobs = upload(ar, shuf, st);
-      int64_t *d_off = upload(ar, shuf_off, st);
+      ShuffleJob *d_jobs = upload(c, shuf);
+      int64_t *d_off = upload(c, shuf_off);
       uint64_t *ka = ar.alloc<uint64_t>(total), *kb = ar.alloc<uint64_t>(total);
       int *va = ar.alloc<int>(total), *vb = ar.alloc<int>(total), *tmp = ar.alloc<int>(total);
       shuffle_keys_kernel<<<grid_for(total), kBlock, 0, st>>>(d_jobs, d_off, (int)shuf.size(), total, (uint64_t)c.params.shuffle_seed, ka, va);
@@ -1339,7 +1372,7 @@ void execute_batch(Context &c)
     }
     if (!trivial.empty())
     {
-      int *d_list = upload(c.arena, trivial, st);
+      int *d_list = upload(c, trivial);
       trivial_kernel<<<grid_for((int64_t)trivial.size()), kBlock, 0, st>>>(d_list, (int)trivial.size(), c.d_subs, c.d_ids, c.d_pos, c.cfg, c.d_E);
       HBT_CHECK_LAUNCH();
       c.ls.launches++;
@@ -1369,9 +1402,9 @@ void execute_batch(Context &c)
       if (M > 0 && !jobs.empty())
       {
         Arena &ar = c.arena;
-        CopyJob *d_jobs = upload(ar, jobs, st);
-        int64_t *d_off = upload(ar, job_off, st);
-        int *d_sub = upload(ar, job_sub, st);
+        CopyJob *d_jobs = upload(c, jobs);
+        int64_t *d_off = upload(c, job_off);
+        int *d_sub = upload(c, job_sub);
         restore_front_kernel<<<grid_for(job_off.back()), kBlock, 0, st>>>(d_jobs, d_off, (int)jobs.size(), job_off.back(), d_sub, c.d_subs,
                                                                            c.d_ids_orig, c.d_ids);
         HBT_CHECK_LAUNCH();
@@ -1458,8 +1491,8 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
   {
     c.arena.reset();
     c.arena.reserve(total * 8 + (int64_t)nsub * 24 + (1 << 20));
-    int64_t *d_off = upload(c.arena, out_off, st), *d_sb = upload(c.arena, slot_base, st);
-    int *d_nb = upload(c.arena, nb, st);
+    int64_t *d_off = upload(c, out_off), *d_sb = upload(c, slot_base);
+    int *d_nb = upload(c, nb);
     int *d_out = c.arena.alloc<int>(total);
     float *d_oe = energy_out ? c.arena.alloc<float>(total) : nullptr;
     pack_output_kernel<<<grid_for(total), kBlock, 0, st>>>(d_off, d_sb, d_nb, nsub, total, c.d_ids, c.d_E, d_out, d_oe);

@@ -42,9 +42,9 @@
 #define HBT_A_PEND 16 // accept-all elements are evaluated when more than this many wait
 #endif
 #ifndef HBT_M_PREFETCH
-#define HBT_M_PREFETCH 1 // a lane that stays on its chain loads its NEXT node right after classifying the current one, so that the
-                         // L2 latency of the node arrays hides behind the list evaluations (ncu: 8 % of all stall samples sat on the
-                         // first use of the loaded node, profiles/r02_walk_notes.md)
+#define HBT_M_PREFETCH 0 // 1: a lane that stays on its chain loads its NEXT node right after classifying the current one.  ncu puts
+                         // 8 % of the stall samples on the first use of the loaded node, but the six extra live registers cost more than
+                         // the hidden latency returns: 925 -> 982 ms on the bench (profiles/r02_walk_notes.md).  Kept for the record.
 #endif
 #define HBT_M_PRAGMA_(x) _Pragma(#x)
 #define HBT_M_PRAGMA_UNROLL(n) HBT_M_PRAGMA_(unroll n)
@@ -110,6 +110,7 @@ struct MaskedSmemT
 
 __device__ __forceinline__ double spline_wp(float r2, double hinv_d)
 { // Gadget spline kernel in double (src/gravity_tree.cpp:146-160)
+  if (r2 == 0.f) return -2.8; // the self term (and co-located pairs): no square root (DSQRT takes its slow path for 0)
   const double u = sqrt((double)r2) * hinv_d;
   if (u < 0.5) return -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6));
   return -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
@@ -146,36 +147,42 @@ __device__ __forceinline__ void masked_eval_far(const float4 *__restrict__ ring,
   }
 }
 
-// one slice of an element that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161)
+// both slices of an element that needs the reference's full kernel per target (src/gravity_tree.cpp:141-161): NEAREST per
+// target in periodic runs, the spline in double for the pairs inside the softening.  The fp64 sequence is issued once for the
+// lanes with a softened pair in either slice, and a second time only if some lane has one in both.
 template <bool PERIODIC, bool COUNT>
-__device__ __forceinline__ void masked_exact(const float4 &n, float lenq, bool in, float pxk, float pyk, float pzk, float &accf, double &accd,
-                                             unsigned &op, float box_size, float box_half, float h2, float softening, unsigned &n_acc)
+__device__ __forceinline__ void masked_exact_pair(const float4 &n, float lenq, bool ina, bool inb, float pxa, float pya, float pza, float pxb, float pyb,
+                                                  float pzb, float &accfa, float &accfb, double &accda, double &accdb, unsigned &oa, unsigned &ob,
+                                                  float box_size, float box_half, float h2, float softening, unsigned &n_acc)
 {
-  float dx = pxk + n.x, dy = pyk + n.y, dz = pzk + n.z;
+  float dxa = pxa + n.x, dya = pya + n.y, dza = pza + n.z;
+  float dxb = pxb + n.x, dyb = pyb + n.y, dzb = pzb + n.z;
   if (PERIODIC)
   {
-    dx = nearest_f(dx, box_size, box_half);
-    dy = nearest_f(dy, box_size, box_half);
-    dz = nearest_f(dz, box_size, box_half);
+    dxa = nearest_f(dxa, box_size, box_half); dya = nearest_f(dya, box_size, box_half); dza = nearest_f(dza, box_size, box_half);
+    dxb = nearest_f(dxb, box_size, box_half); dyb = nearest_f(dyb, box_size, box_half); dzb = nearest_f(dzb, box_size, box_half);
   }
-  const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); // FMUL, FFMA, FFMA like the packed path
-  const bool open = lenq > r2;
-  const bool acc = in && !open;
-  const bool soft = acc && r2 < h2;
-  if (__any_sync(kFull, soft))
+  const float r2a = fmaf(dza, dza, fmaf(dya, dya, dxa * dxa)); // FMUL, FFMA, FFMA like the packed path
+  const float r2b = fmaf(dzb, dzb, fmaf(dyb, dyb, dxb * dxb));
+  const bool opena = lenq > r2a, openb = lenq > r2b; // reference criterion, per target (src/gravity_tree.cpp:135)
+  const bool acca = ina && !opena, accb = inb && !openb;
+  const bool softa = acca && r2a < h2, softb = accb && r2b < h2;
+  if (acca && !softa) accfa = fmaf(n.w, rsqrt_raw(r2a), accfa);
+  if (accb && !softb) accfb = fmaf(n.w, rsqrt_raw(r2b), accfb);
+  if (__any_sync(kFull, softa || softb))
   {
-    if (soft)
+    const double hinv_d = 1.0 / (2.8 * (double)softening);
+    if (softa || softb)
     {
-      const double hinv_d = 1.0 / (2.8 * (double)softening);
-      accd += (double)(-n.w) * hinv_d * spline_wp(r2, hinv_d);
+      const double t = (double)(-n.w) * hinv_d * spline_wp(softa ? r2a : r2b, hinv_d);
+      if (softa) accda += t; else accdb += t;
     }
-    else if (acc)
-      accf = fmaf(n.w, rsqrt_raw(r2), accf);
+    if (__any_sync(kFull, softa && softb))
+      if (softa && softb) accdb += (double)(-n.w) * hinv_d * spline_wp(r2b, hinv_d);
   }
-  else if (acc)
-    accf = fmaf(n.w, rsqrt_raw(r2), accf);
-  op = __ballot_sync(kFull, in && open);
-  if (COUNT) n_acc += (unsigned)acc;
+  oa = __ballot_sync(kFull, ina && opena);
+  ob = __ballot_sync(kFull, inb && openb);
+  if (COUNT) n_acc += (unsigned)acca + (unsigned)accb;
 }
 
 // evaluate the `cnt` accept-all elements of slice pair R (slices K = 2R, K+1): the bare pair kernel under the mask
@@ -240,9 +247,8 @@ __device__ __forceinline__ void masked_eval_split(MaskedSmem &sm, int cnt, int c
     const float4 n = e.nxm;
     const bool ina = (e.ma & lanebit) != 0u, inb = (e.mb & lanebit) != 0u;
     unsigned oa, ob;
-    masked_exact<PERIODIC, COUNT>(n, e.lenq, ina, px[K], py[K], pz[K], acca, accd[K], oa, box_size, box_half, h2, softening, n_acc);
-    masked_exact<PERIODIC, COUNT>(n, e.lenq, inb, px[K + 1], py[K + 1], pz[K + 1], accb, accd[K + 1], ob, box_size, box_half, h2, softening, n_acc);
-    __syncwarp(); // every lane has read the masks before lane 0 replaces them
+    masked_exact_pair<PERIODIC, COUNT>(n, e.lenq, ina, inb, px[K], py[K], pz[K], px[K + 1], py[K + 1], pz[K + 1], acca, accb, accd[K], accd[K + 1], oa, ob,
+                                       box_size, box_half, h2, softening, n_acc);
     if (lane == 0) *reinterpret_cast<uint2 *>(&e.ma) = make_uint2(oa, ob);
   }
   accd[K] += (double)acca;

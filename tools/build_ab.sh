@@ -8,8 +8,8 @@ rm -f "$OUT"/*.so
 build() { # name, flags
   make -s -j8 BUILD=build_$1 LIB=$OUT/lib_$1.so EXTRA="$2" > /dev/null && echo "built $1"
 }
-build nopre "-DHBT_M_PREFETCH=0" &
-build d2 "-DHBT_M_UNROLL_D=2" &
+build pre "-DHBT_M_PREFETCH=1" &
+build exold "-DHBT_M_UNROLL_D=4" &
 wait
 build big "-DHBT_A_PEND=24 -DHBT_M_PEND=12" &
 build u8 "-DHBT_M_UNROLL=8" &
