@@ -28,6 +28,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA initialises: the library's upload stream gets its own hardware queue
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

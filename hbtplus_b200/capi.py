@@ -320,27 +320,24 @@ EXPORTS = [
 
 
 def order_capacity(part_offset: np.ndarray, nest_offset, nest_list) -> int:
-    """Host mirror of ``hbtu_order_capacity``: sum over subhaloes of own + all descendants' particles."""
+    """Host mirror of ``hbtu_order_capacity``: sum over subhaloes of own + all descendants' particles (vectorised: it sits
+    inside the timed end-to-end call of bench.py)."""
     nsub = len(part_offset) - 1
     own = np.diff(part_offset).astype(np.int64)
-    if nest_offset is None:
+    if nest_offset is None or nsub == 0:
         return int(own.sum())
     cap = own.copy()
-    # children lists form a forest; accumulate bottom-up by repeated relaxation over depth
     parent = np.full(nsub, -1, np.int64)
-    for s in range(nsub):
-        for k in range(nest_offset[s], nest_offset[s + 1]):
-            parent[nest_list[k]] = s
+    parent[np.asarray(nest_list, np.int64)] = np.repeat(np.arange(nsub), np.diff(np.asarray(nest_offset, np.int64)))
     depth = np.zeros(nsub, np.int64)
-    for s in range(nsub):
-        d, q = 0, s
-        while parent[q] >= 0:
-            q = parent[q]
-            d += 1
-        depth[s] = d
-    for s in np.argsort(-depth, kind="stable"):
-        if parent[s] >= 0:
-            cap[parent[s]] += cap[s]
+    cur = parent.copy()
+    while (cur >= 0).any():  # nesting depth, level by level
+        live = cur >= 0
+        depth[live] += 1
+        cur = np.where(live, parent[np.maximum(cur, 0)], -1)
+    for d in range(int(depth.max()), 0, -1):  # children feed their parents, deepest level first
+        idx = np.nonzero(depth == d)[0]
+        np.add.at(cap, parent[idx], cap[idx])
     return int(cap.sum())
 
 

@@ -6,6 +6,7 @@
 #include <cub/cub.cuh>
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -388,6 +389,7 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
     g_create_error = "only the HBTReal=float ABI variant is built";
     return HBTU_ERR_UNSUPPORTED;
   }
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); // no effect if the process has already created its CUDA context
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev)
@@ -422,8 +424,14 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
   c.cfg.max_sample = p->max_sample_size;
   c.cfg.scale_factor = 1.f;
   int rc = guarded(ctx, [&](Context &cc) {
-    HBT_CUDA(cudaStreamCreateWithFlags(&cc.stream, cudaStreamNonBlocking));
-    HBT_CUDA(cudaStreamCreateWithFlags(&cc.copy_stream, cudaStreamNonBlocking));
+    // the compute stream and the upload stream must not share a hardware work queue: commands of aliased streams are dispatched in
+    // issue order, and the multi-GB particle upload of hbtu_unbind_batch then delays every kernel issued after it (measured: the
+    // whole upload, 104 ms per step).  Different priorities map to different queues; CUDA_DEVICE_MAX_CONNECTIONS (read when the
+    // CUDA context is created: bench.py and the shim set it before the first CUDA call) widens the pool for equal priorities.
+    int prio_least = 0, prio_greatest = 0;
+    HBT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    HBT_CUDA(cudaStreamCreateWithPriority(&cc.stream, cudaStreamNonBlocking, prio_greatest));
+    HBT_CUDA(cudaStreamCreateWithPriority(&cc.copy_stream, cudaStreamNonBlocking, prio_least));
     for (auto &ev : cc.ev_wave) HBT_CUDA(cudaEventCreate(&ev));
     HBT_CUDA(cudaEventCreate(&cc.ev_copy0));
     for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
