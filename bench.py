@@ -163,7 +163,7 @@ class Eagle(Workload):
 
     def sizes(self, particles):
         rng = np.random.default_rng(self.seed)
-        f = min(1.0, particles / self.full_particles)
+        f = min(1.0, particles / (8 * self.full_particles))  # `particles` = the whole snapshot; full size 8 x 1.7e8 = 1.36e9
         ngroups, nsat = max(50, int(3e6 * f)), max(20, int(1e6 * f))
         n_max = int(max(3e7 * f, 5000))
         groups = synth.subhalo_sizes(rng, ngroups, 20, n_max)
@@ -736,6 +736,8 @@ def main():
                        "l2_policy": f"inputs ({n_local * 32 / 1e9:.2f} GB per GPU) are larger than the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the library stream around hbtu_execute, max over ranks", "wall_ms_per_step": float(np.mean(wall)) * 1e3,
                        "phase_ms": {"walk": float(np.mean(walk_ms)), "tree_build": float(np.mean(build_ms)), "partition_sort_reduce": float(np.mean(other_ms))},
+                       "phase_ms_detail": dict(zip(("gather_bbox", "tree_build", "targets", "walk", "count_state_partition", "energy_sort_permute",
+                                                    "frame_reduce", "kinematics_finalize"), [float(x) for x in st.phase_ms])),
                        "rounds": int(st0.rounds), "per_rank_ms_per_step": per_rank, "pair_interactions_per_step": inter_all,
                        "walk_fallbacks": int(st0.walk_fallbacks),
                        "multi_gpu": ("strong scaling: ONE snapshot replicated on every GPU, walk targets of every round dealt block-cyclically over the ranks, "

@@ -105,6 +105,7 @@ class Stats(C.Structure):
         ("stage_wall_ms", C.c_double),
         ("execute_wall_ms", C.c_double),
         ("fetch_wall_ms", C.c_double),
+        ("phase_ms", C.c_double * 8),
     ]
 
 

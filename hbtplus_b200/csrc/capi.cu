@@ -436,6 +436,7 @@ int hbtu_create(const hbtu_params *p, hbtu_ctx **out)
     HBT_CUDA(cudaEventCreate(&cc.ev_copy0));
     for (auto &ev : cc.ev) HBT_CUDA(cudaEventCreate(&ev));
     for (auto &ev : cc.ev_exec) HBT_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : cc.ev_ph) HBT_CUDA(cudaEventCreate(&ev));
     HBT_CUDA(cudaMalloc(&cc.d_counters, kWalkCounters * sizeof(unsigned long long)));
   });
   if (rc != HBTU_OK)
@@ -468,9 +469,12 @@ void hbtu_destroy(hbtu_ctx *ctx)
   cudaFree(c.d_slot_base);
   cudaFree(c.d_counters);
   if (c.h_ring) cudaFreeHost(c.h_ring);
+  if (c.h_back) cudaFreeHost(c.h_back);
   for (auto &ev : c.ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c.ev_exec)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c.ev_ph)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c.ev_wave)
     if (ev) cudaEventDestroy(ev);

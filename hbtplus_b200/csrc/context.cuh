@@ -30,6 +30,7 @@ struct Context
   bool waves_pending = false;                         // the staged batch was uploaded asynchronously (hbtu_unbind_batch)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_exec[2] = {nullptr, nullptr};
+  cudaEvent_t ev_ph[9] = {}; // phase boundaries of a round (hbtu_stats.phase_ms)
   std::string last_error;
 
   // staged batch -------------------------------------------------------------------------------
@@ -69,6 +70,8 @@ struct Context
   // upload is in flight would wait for all of it (measured: 104 ms per step) - the SMs read the ring over PCIe instead.
   char *h_ring = nullptr, *d_ring = nullptr; // host pointer / device alias of the ring
   size_t ring_cap = 0, ring_used = 0;
+  char *h_back = nullptr; // pinned landing buffer of the device-to-host readbacks (round results, final SubState records): a pageable
+  size_t back_cap = 0;    // destination costs a staging pass per copy, which shows with 1e5..1e6 subhaloes per batch
 
   Arena arena;
   LaunchStats ls;
@@ -78,6 +81,8 @@ struct Context
 void execute_batch(Context &c);
 // stage `bytes` of host data in the ring and copy them to `dst` (device) with a kernel on c.stream (context.cuh: h_ring)
 void upload_bytes(Context &c, void *dst, const void *src, size_t bytes);
+// pinned host buffer of at least `bytes` for a readback (grow-only; valid until the next call)
+void *readback_buffer(Context &c, size_t bytes);
 // profile.cu: Subhalo_t::CalculateProfileProperties + CalculateShape for a batch of particle lists
 void profile_batch(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, hbtu_profile_io *io);
 void profile_executed(Context &c, hbtu_profile_io *io);

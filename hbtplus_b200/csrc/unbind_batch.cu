@@ -20,6 +20,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 
@@ -270,6 +273,30 @@ __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restri
   tgt_pm[t] = p;
   tgt_slot[t] = slot;
   tgt_seg[t] = a;
+}
+
+// Sampled mode: the Elist order of a sampled subhalo IS its sample (shuffled on entry, src/subhalo_unbind.cpp:302), so consecutive
+// targets are spatially unrelated and a walk group's bounding box is the whole subhalo.  The WALK therefore visits the targets in
+// key order - 30 key bits in the segment's root cube - through a permuted copy of (position, slot); nothing else changes order.
+__global__ void __launch_bounds__(kBlock) walk_keys_kernel(const float4 *__restrict__ tgt_pm, const int *__restrict__ tgt_seg, int T,
+                                                            const SegRoot *__restrict__ roots, uint64_t *__restrict__ key, int *__restrict__ val)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float4 p = tgt_pm[t];
+  const int a = tgt_seg[t];
+  key[t] = ((uint64_t)a << 30) | (morton_key(p.x, p.y, p.z, roots[a]) >> 33);
+  val[t] = t;
+}
+__global__ void __launch_bounds__(kBlock) walk_gather_kernel(const int *__restrict__ order, const float4 *__restrict__ tgt_pm,
+                                                              const int64_t *__restrict__ tgt_slot, int T, float4 *__restrict__ wpm,
+                                                              int64_t *__restrict__ wslot)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int src = order[t];
+  wpm[t] = tgt_pm[src];
+  wslot[t] = tgt_slot[src];
 }
 
 __global__ void __launch_bounds__(kBlock) fill_tgt_seg_kernel(const int *__restrict__ tgt_off, int nseg, int T, int *__restrict__ tgt_seg)
@@ -780,6 +807,20 @@ void upload_bytes(Context &c, void *dst, const void *src, size_t bytes)
   c.ring_used += need;
 }
 
+void *readback_buffer(Context &c, size_t bytes)
+{
+  if (bytes > c.back_cap)
+  {
+    if (c.h_back) cudaFreeHost(c.h_back);
+    c.h_back = nullptr;
+    c.back_cap = 0;
+    const size_t cap = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 20);
+    HBT_CUDA(cudaHostAlloc((void **)&c.h_back, cap, cudaHostAllocDefault));
+    c.back_cap = cap;
+  }
+  return c.h_back;
+}
+
 template <class T>
 static T *upload(Context &c, const std::vector<T> &v)
 { // arena allocations are 256-byte aligned and padded, so the 16-byte granularity of the copy kernel stays inside them
@@ -862,7 +903,7 @@ static void run_round(Context &c, std::vector<int> &active)
 
   Arena &ar = c.arena;
   ar.reset();
-  ar.reserve(tree_arena_bytes(S, nseg) + T * 68 + (int64_t)nseg * 128);
+  ar.reserve(tree_arena_bytes(S, nseg) + T * (c.cfg.max_sample > 0 ? 132 : 68) + (int64_t)nseg * 128);
   cudaStream_t st = c.stream;
   Segment *d_segs = upload(c, segs);
   int *d_tree_off = upload(c, tree_off), *d_tgt_off = upload(c, tgt_off);
@@ -870,6 +911,7 @@ static void run_round(Context &c, std::vector<int> &active)
   for (int q = 0; q < kWalkClasses; q++) d_warp_off[q] = upload(c, warp_off[q]);
 
   HBT_CUDA(cudaEventRecord(c.ev[0], st));
+  HBT_CUDA(cudaEventRecord(c.ev_ph[0], st));
   TreeArrays tr;
   tr.S = (int)S;
   tr.nseg = nseg;
@@ -883,7 +925,9 @@ static void run_round(Context &c, std::vector<int> &active)
   c.ls.launches++;
   launch_init_bbox(tr.bbox, nseg, st, c.ls);
   launch_bbox(tr.tpos, tr.ts_seg, (int)S, tr.bbox, st, c.ls);
+  HBT_CUDA(cudaEventRecord(c.ev_ph[1], st));
   build_trees(tr, ar, c.cfg, st, c.ls);
+  HBT_CUDA(cudaEventRecord(c.ev_ph[2], st));
   int *const rho = c.cfg.periodic ? c.d_rho : nullptr; // reference Elist order, tracked in periodic runs only
   float4 *tgt_pm = ar.alloc<float4>(T);
   int64_t *tgt_slot = ar.alloc<int64_t>(T);
@@ -906,7 +950,32 @@ static void run_round(Context &c, std::vector<int> &active)
   pre_walk_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.cfg);
   HBT_CHECK_LAUNCH();
   c.ls.launches += 4;
+  const float4 *walk_pm = tgt_pm;
+  const int64_t *walk_slot = tgt_slot;
+  if (any_hoare || (c.cfg.max_sample > 0 && std::any_of(segs.begin(), segs.end(), [](const Segment &g) { return g.keep_order != 0; })))
+  { // sampled subhaloes in this round: walk their (shuffled) targets in key order
+    uint64_t *wk_a = ar.alloc<uint64_t>(T), *wk_b = ar.alloc<uint64_t>(T);
+    int *wv_a = ar.alloc<int>(T), *wv_b = ar.alloc<int>(T);
+    walk_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_pm, tgt_seg, (int)T, tr.roots, wk_a, wv_a);
+    HBT_CHECK_LAUNCH();
+    int bits = 31;
+    while ((1ll << (bits - 30)) < nseg) bits++;
+    cub::DoubleBuffer<uint64_t> dk(wk_a, wk_b);
+    cub::DoubleBuffer<int> dv(wv_a, wv_b);
+    size_t tb = 0;
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)T, 0, bits, st));
+    void *tmp = ar.alloc<char>((int64_t)tb);
+    HBT_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)T, 0, bits, st));
+    float4 *wpm = ar.alloc<float4>(T);
+    int64_t *wslot = ar.alloc<int64_t>(T);
+    walk_gather_kernel<<<grid_for(T), kBlock, 0, st>>>(dv.Current(), tgt_pm, tgt_slot, (int)T, wpm, wslot);
+    HBT_CHECK_LAUNCH();
+    c.ls.launches += 3 + (bits + 7) / 8;
+    walk_pm = wpm;
+    walk_slot = wslot;
+  }
   HBT_CUDA(cudaEventRecord(c.ev[1], st));
+  HBT_CUDA(cudaEventRecord(c.ev_ph[3], st));
 
   WalkArgs wa{};
   wa.node_xm = tr.node_xm;
@@ -915,8 +984,8 @@ static void run_round(Context &c, std::vector<int> &active)
   wa.tree_off = d_tree_off;
   wa.segs = d_segs;
   wa.nseg = nseg;
-  wa.tgt_pm = tgt_pm;
-  wa.tgt_slot = tgt_slot;
+  wa.tgt_pm = walk_pm;
+  wa.tgt_slot = walk_slot;
   wa.ids = c.d_ids;
   wa.vel = c.d_vel;
   wa.E = c.d_E;
@@ -944,11 +1013,12 @@ static void run_round(Context &c, std::vector<int> &active)
   {
     HBT_CUDA(cudaStreamSynchronize(st)); // the exchange may run on another stream (NCCL through the caller's runtime)
     if (c.split_fn(c.split_user, e_stage, T, (void *)st) != 0) throw CudaError{HBTU_ERR_CUDA, "walk split: the all-reduce callback failed"};
-    scatter_stage_kernel<<<grid_for(T), kBlock, 0, st>>>(tgt_slot, (int)T, e_stage, c.d_E);
+    scatter_stage_kernel<<<grid_for(T), kBlock, 0, st>>>(walk_slot, (int)T, e_stage, c.d_E);
     HBT_CHECK_LAUNCH();
     c.ls.launches++;
   }
   HBT_CUDA(cudaEventRecord(c.ev[2], st));
+  HBT_CUDA(cudaEventRecord(c.ev_ph[4], st));
 
   count_bound_kernel<<<grid_for(T, kBlock * 4), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs);
   HBT_CHECK_LAUNCH();
@@ -983,6 +1053,7 @@ static void run_round(Context &c, std::vector<int> &active)
       c.ls.launches++;
     }
   }
+  HBT_CUDA(cudaEventRecord(c.ev_ph[5], st));
   sort_keys_kernel<<<grid_for(T), kBlock, 0, st>>>(d_segs, tgt_seg, tgt_slot, (int)T, c.d_E, c.d_subs, bscan, fpos, rho, key_a, val_a);
   HBT_CHECK_LAUNCH();
   c.ls.launches += 3;
@@ -1004,6 +1075,7 @@ static void run_round(Context &c, std::vector<int> &active)
     HBT_CHECK_LAUNCH();
     c.ls.launches += 2;
   }
+  HBT_CUDA(cudaEventRecord(c.ev_ph[6], st));
   static_assert(kBlock == kSegBlock, "seg_reduce.cuh blocks");
   std::vector<int> chunk_off;
   const int nchunk = seg_chunk_table(nseg, [&](int a) { return segs[a].tgt_n; }, chunk_off);
@@ -1018,6 +1090,7 @@ static void run_round(Context &c, std::vector<int> &active)
   HBT_CHECK_LAUNCH();
   state2_kernel<<<grid_for(nseg), kBlock, 0, st>>>(d_segs, nseg, c.d_subs, c.d_ids, c.d_pos, c.d_vel, c.cfg);
   HBT_CHECK_LAUNCH();
+  HBT_CUDA(cudaEventRecord(c.ev_ph[7], st));
   if (nchunk > 0)
   { // `partial` is reused: state2 has consumed the frame sums
     kinematics_kernel<<<nchunk, kBlock, 0, st>>>(d_segs, nseg, d_chunk_off, c.d_ids, c.d_E, c.d_pos, c.d_vel, c.d_subs, c.cfg, partial);
@@ -1031,8 +1104,9 @@ static void run_round(Context &c, std::vector<int> &active)
   HBT_CHECK_LAUNCH();
   c.ls.launches += 4;
   HBT_CUDA(cudaEventRecord(c.ev[3], st));
-  std::vector<RoundResult> res(nseg);
-  HBT_CUDA(cudaMemcpyAsync(res.data(), d_res, sizeof(RoundResult) * nseg, cudaMemcpyDeviceToHost, st));
+  HBT_CUDA(cudaEventRecord(c.ev_ph[8], st));
+  const RoundResult *res = static_cast<const RoundResult *>(readback_buffer(c, sizeof(RoundResult) * nseg));
+  HBT_CUDA(cudaMemcpyAsync(const_cast<RoundResult *>(res), d_res, sizeof(RoundResult) * nseg, cudaMemcpyDeviceToHost, st));
   HBT_CUDA(cudaStreamSynchronize(st));
   c.ring_used = 0; // every staged table of this round has been consumed
   float ms = 0;
@@ -1042,6 +1116,8 @@ static void run_round(Context &c, std::vector<int> &active)
   c.stats.walk_ms += ms;
   cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
   c.stats.other_ms += ms;
+  for (int k = 0; k < 8; k++)
+    if (cudaEventElapsedTime(&ms, c.ev_ph[k], c.ev_ph[k + 1]) == cudaSuccess) c.stats.phase_ms[k] += ms;
   c.stats.rounds++;
   c.stats.tree_builds += nseg;
   c.stats.walk_targets += T;
@@ -1185,8 +1261,26 @@ static void run_refine(Context &c, const std::vector<int> &list)
   HBT_CUDA(cudaStreamSynchronize(st));
 }
 
+// HBTU_TRACE=1: host timestamps (ms since the start of hbtu_execute) at the stations of a step, on stderr
+static bool trace_on()
+{
+  static const bool on = getenv("HBTU_TRACE") != nullptr;
+  return on;
+}
+#define HBT_TRACE(t0, ...)                                                                                                  \
+  do                                                                                                                        \
+  {                                                                                                                         \
+    if (trace_on())                                                                                                         \
+    {                                                                                                                       \
+      fprintf(stderr, "[hbtu %8.2f ms] ", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - (t0)).count()); \
+      fprintf(stderr, __VA_ARGS__);                                                                                         \
+      fprintf(stderr, "\n");                                                                                                \
+    }                                                                                                                       \
+  } while (0)
+
 void execute_batch(Context &c)
 {
+  const auto trace_t0 = std::chrono::steady_clock::now();
   if (!c.staged) throw CudaError{HBTU_ERR_INVALID, "hbtu_execute before hbtu_stage"};
   cudaStream_t st = c.stream;
   const int nsub = (int)c.nsub;
@@ -1194,6 +1288,7 @@ void execute_batch(Context &c)
   std::memset(&c.stats, 0, offsetof(hbtu_stats, h2d_ms)); // the copy statistics of the staging call survive
   c.stats.tree_sources = 0;
   c.stats.walk_fallbacks = 0;
+  for (double &x : c.stats.phase_ms) x = 0.0;
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
   if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, kWalkCounters * sizeof(unsigned long long), st));
 
@@ -1244,7 +1339,9 @@ void execute_batch(Context &c)
     HBT_CHECK_LAUNCH();
     c.ls.launches++;
   }
+  HBT_TRACE(trace_t0, "state + ids enqueued");
   HBT_CUDA(cudaStreamSynchronize(st));
+  HBT_TRACE(trace_t0, "state + ids on the device (copy stream %s)", cudaStreamQuery(c.copy_stream) == cudaSuccess ? "idle" : "busy");
 
   // asynchronous staging (hbtu_unbind_batch): the first wave of the upload is needed by the first round, the dominant root only
   // by level 0; a re-execution of the same staged batch finds both events completed
@@ -1258,6 +1355,8 @@ void execute_batch(Context &c)
     }
     const std::vector<int> &lv = c.levels[level];
     const int64_t M = c.cfg.max_sample;
+    HBT_TRACE(trace_t0, "level %d: %zu subhaloes, %lld rounds so far (copy stream %s)", level, lv.size(), (long long)c.stats.rounds,
+              cudaStreamQuery(c.copy_stream) == cudaSuccess ? "idle" : "busy");
     c.arena.reset(); // the previous level's rounds are over: the arena holds this level's small job tables until its first round
     // 1. feed children's unbound tails into this level's sources (src/subhalo_unbind.cpp:437-443)
     {
@@ -1422,6 +1521,7 @@ void execute_batch(Context &c)
   }
   HBT_CUDA(cudaEventRecord(c.ev_exec[1], st));
   HBT_CUDA(cudaEventSynchronize(c.ev_exec[1]));
+  HBT_TRACE(trace_t0, "done");
   {
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
@@ -1444,8 +1544,8 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
   const int nsub = (int)c.nsub;
   cudaEvent_t e0 = c.ev[0], e1 = c.ev[1];
   HBT_CUDA(cudaEventRecord(e0, st));
-  std::vector<SubState> fin(nsub);
-  HBT_CUDA(cudaMemcpyAsync(fin.data(), c.d_subs, sizeof(SubState) * nsub, cudaMemcpyDeviceToHost, st));
+  const SubState *fin = static_cast<const SubState *>(readback_buffer(c, sizeof(SubState) * (size_t)std::max(nsub, 1)));
+  HBT_CUDA(cudaMemcpyAsync(const_cast<SubState *>(fin), c.d_subs, sizeof(SubState) * nsub, cudaMemcpyDeviceToHost, st));
   HBT_CUDA(cudaStreamSynchronize(st));
   std::vector<int64_t> out_off(nsub + 1, 0), slot_base(nsub);
   std::vector<int> nb(nsub);

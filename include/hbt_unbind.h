@@ -329,6 +329,10 @@ typedef struct hbtu_stats
   double stage_wall_ms;        /* host wall clock inside hbtu_stage / the staging part of hbtu_unbind_batch          */
   double execute_wall_ms;      /* host wall clock inside hbtu_execute                                                */
   double fetch_wall_ms;        /* host wall clock inside hbtu_fetch                                                  */
+  double phase_ms[8];          /* CUDA-event time of a step by phase, summed over its rounds: 0 source gather + bounding boxes,
+                                  1 tree build (keys, sorts, cells, moments), 2 walk targets, 3 walk, 4 bound count + iteration
+                                  state + partition bookkeeping, 5 energy sort + permutation, 6 frame reductions, 7 kinematics +
+                                  finalisation                                                                           */
 } hbtu_stats;
 int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
 /* diagnostics (no reference counterpart): when on, the walk kernels of subsequent calls count accepted
