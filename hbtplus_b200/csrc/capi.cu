@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 
 #include "context.cuh"
 
@@ -132,6 +133,7 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
 {
   if (!epoch || nsub < 0 || !part_offset || (nsub > 0 && !io)) throw CudaError{HBTU_ERR_INVALID, "null argument"};
   if (nsub > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
+  finish_upload(c); // a previous asynchronous staging that was never executed
   c.staged = c.executed = false;
   const int64_t N = nsub > 0 ? part_offset[nsub] - part_offset[0] : 0;
   if (part_offset[0] != 0) throw CudaError{HBTU_ERR_INVALID, "part_offset[0] must be 0"};
@@ -199,19 +201,53 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
     for (int64_t s = 0; s < nsub; s++)
       if (c.subs[s].parent < 0 && c.subs[s].n_own > N / 4 && (big < 0 || c.subs[s].n_own > c.subs[big].n_own)) big = s;
     if (c.max_depth == 0 || N < (1 << 20)) big = -1; // nothing to hide the upload behind
-    cudaStream_t cs = c.copy_stream;
-    HBT_CUDA(cudaEventRecord(c.ev_copy0, cs));
+    // ranges of wave 1 (everything but the dominant root) and wave 2 (that root)
+    std::vector<std::pair<int64_t, int64_t>> waves[2];
     if (big < 0)
-      copy_range(cs, 0, N);
+      waves[0].push_back({0, N});
     else
     {
-      copy_range(cs, 0, part_offset[big]);
-      copy_range(cs, part_offset[big + 1], N);
+      waves[0].push_back({0, part_offset[big]});
+      waves[0].push_back({part_offset[big + 1], N});
+      waves[1].push_back({part_offset[big], part_offset[big + 1]});
     }
-    HBT_CUDA(cudaEventRecord(c.ev_wave[0], cs));
-    if (big >= 0) copy_range(cs, part_offset[big], part_offset[big + 1]);
-    HBT_CUDA(cudaEventRecord(c.ev_wave[1], cs));
+    // The copies are fed to the copy stream in chunks by a helper thread that waits for every chunk: with the whole upload
+    // enqueued at once, nothing issued afterwards on ANY stream started before the last byte had crossed PCIe (measured: the
+    // first kernel of the step waited the full 104 ms) - the copy engine's reads starve the command fetch; the gaps between
+    // chunks let the kernels of the deeper levels through.
+    const char *env = getenv("HBTU_UPLOAD_CHUNK_MB");
+    const int64_t chunk = std::max<int64_t>(1, env ? atoll(env) : 32) * (int64_t)(1 << 20) / 32; // particles per chunk (32 B each)
+    finish_upload(c);
+    c.up_wave_done = 0;
+    c.up_error.clear();
     c.waves_pending = true;
+    const int device = c.device;
+    cudaStream_t cs = c.copy_stream;
+    float4 *d_pos = c.d_pos, *d_vel = c.d_vel;
+    Context *cp = &c;
+    c.uploader = std::thread([=]() {
+      const auto t0 = std::chrono::steady_clock::now();
+      std::string err;
+      if (cudaSetDevice(device) != cudaSuccess) err = "cudaSetDevice failed in the upload helper";
+      for (int w = 0; w < 2; w++)
+      {
+        for (const auto &r : waves[w])
+          for (int64_t b = r.first; b < r.second && err.empty(); b += chunk)
+          {
+            const int64_t e = std::min(r.second, b + chunk);
+            cudaError_t e1 = cudaMemcpyAsync(d_pos + b, pos_mass + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs);
+            cudaError_t e2 = cudaMemcpyAsync(d_vel + b, vel + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs);
+            cudaError_t e3 = cudaStreamSynchronize(cs);
+            if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+              err = std::string("particle upload failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+          }
+        std::lock_guard<std::mutex> lk(cp->up_m);
+        if (!err.empty()) cp->up_error = err;
+        cp->up_wave_done = w + 1;
+        if (w == 1) cp->up_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        cp->up_cv.notify_all();
+      }
+    });
   }
   c.staged = true;
 }
@@ -454,6 +490,7 @@ void hbtu_destroy(hbtu_ctx *ctx)
   if (!ctx) return;
   Context &c = ctx->c;
   cudaSetDevice(c.device);
+  finish_upload(c);
   if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
   if (c.stream) cudaStreamSynchronize(c.stream);
   c.arena.release();
@@ -533,11 +570,8 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
     stage(c, epoch, nsub, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags, true);
   });
   if (rc == HBTU_OK) rc = hbtu_execute(ctx);
-  if (rc != HBTU_OK)
-  { // never leave copies from the caller's buffers in flight behind an error return
-    if (ctx) cudaStreamSynchronize(ctx->c.copy_stream);
-    return rc;
-  }
+  if (ctx) finish_upload(ctx->c); // never leave copies from the caller's buffers in flight behind the return
+  if (rc != HBTU_OK) return rc;
   return hbtu_fetch(ctx, io, order_capacity, order_offset, order_out, energy_out);
 }
 

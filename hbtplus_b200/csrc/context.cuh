@@ -1,6 +1,9 @@
 // context.cuh - the hbtu_ctx object: one CUDA device, one stream, one staged batch.
 #pragma once
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_tree.cuh"
@@ -26,6 +29,14 @@ struct Context
   cudaStream_t copy_stream = nullptr;                 // uploads that run behind the kernels of the deeper nesting levels
   cudaEvent_t ev_wave[2] = {nullptr, nullptr};        // [0]: everything but the dominant root is in HBM, [1]: the dominant root too
   cudaEvent_t ev_copy0 = nullptr;                     // start of the uploads on copy_stream (h2d_ms)
+  // asynchronous staging (hbtu_unbind_batch): a helper host thread feeds the particle arrays to the copy stream in chunks and
+  // reports the two waves done; the scheduler waits on the HOST for a wave right before the first round that needs it
+  std::thread uploader;
+  std::mutex up_m;
+  std::condition_variable up_cv;
+  int up_wave_done = 0;   // 0: nothing, 1: everything but the dominant root is in HBM, 2: all of it
+  std::string up_error;   // set by the helper if a copy failed
+  double up_ms = 0.0;     // wall time of the whole upload
   bool staged_async = false;                          // ... and its h2d_ms is read from the copy stream's events after the execution
   bool waves_pending = false;                         // the staged batch was uploaded asynchronously (hbtu_unbind_batch)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -79,6 +90,10 @@ struct Context
 };
 
 void execute_batch(Context &c);
+// block the calling host thread until upload wave `wave` (1 or 2) of an asynchronously staged batch has landed
+void wait_upload_wave(Context &c, int wave);
+// join the upload helper (no-op if none is running)
+void finish_upload(Context &c);
 // stage `bytes` of host data in the ring and copy them to `dst` (device) with a kernel on c.stream (context.cuh: h_ring)
 void upload_bytes(Context &c, void *dst, const void *src, size_t bytes);
 // pinned host buffer of at least `bytes` for a readback (grow-only; valid until the next call)

@@ -57,6 +57,30 @@ __device__ __forceinline__ int find_seg64(const int64_t *__restrict__ off, int n
   return lo;
 }
 
+// The same for a whole warp whose lanes hold NON-DECREASING keys (consecutive elements of a concatenation): lane 0 searches,
+// the others start from its segment and step forward - one load per lane while the warp stays inside one segment instead of
+// log2(n) dependent loads each (with 5e5 segments per batch the per-element searches were a measurable part of every
+// streaming kernel).  Every lane of the warp must call it; lanes past the end pass the last valid key.
+template <class OffT, class KeyT>
+__device__ __forceinline__ int find_seg_warp(const OffT *__restrict__ off, int n, KeyT k)
+{
+  const KeyT k0 = __shfl_sync(0xffffffffu, k, 0);
+  int s = 0;
+  if ((threadIdx.x & 31) == 0)
+  {
+    int lo = 0, hi = n;
+    while (hi - lo > 1)
+    {
+      int mid = (lo + hi) >> 1;
+      if (off[mid] <= k0) lo = mid; else hi = mid;
+    }
+    s = lo;
+  }
+  s = __shfl_sync(0xffffffffu, s, 0);
+  while (s + 1 < n && off[s + 1] <= k) s++;
+  return s;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // batch set-up kernels
 // ---------------------------------------------------------------------------------------------------
@@ -64,9 +88,10 @@ __global__ void __launch_bounds__(kBlock) init_ids_kernel(const int64_t *__restr
                                                            int nsub, int64_t N, int *__restrict__ ids)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  int s = find_seg64(part_offset, nsub, i);
-  ids[slot_base[s] + (i - part_offset[s])] = (int)i;
+  const bool valid = i < N;
+  if (!valid) i = N - 1;
+  int s = find_seg_warp(part_offset, nsub, i);
+  if (valid) ids[slot_base[s] + (i - part_offset[s])] = (int)i;
 }
 
 struct CopyJob
@@ -78,10 +103,11 @@ __global__ void __launch_bounds__(kBlock) seg_copy_kernel(const CopyJob *__restr
                                                            int64_t total, const int *__restrict__ src, int *__restrict__ dst)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int j = find_seg64(job_off, njobs, i);
+  const bool valid = i < total;
+  if (!valid) i = total - 1;
+  int j = find_seg_warp(job_off, njobs, i);
   int64_t o = i - job_off[j];
-  dst[jobs[j].dst + o] = src[jobs[j].src + o];
+  if (valid) dst[jobs[j].dst + o] = src[jobs[j].src + o];
 }
 
 struct LevelInit
@@ -196,8 +222,10 @@ __global__ void __launch_bounds__(kBlock) gather_src_kernel(const Segment *__res
                                                              float4 *__restrict__ tpos, int *__restrict__ ts_seg)
 {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= S) return;
-  int a = find_seg(tree_off, nseg, k);
+  const bool valid = k < S;
+  if (!valid) k = S - 1;
+  int a = find_seg_warp(tree_off, nseg, k);
+  if (!valid) return;
   const Segment sg = segs[a];
   int64_t slot = sg.slot_base + sg.tree_first + (k - sg.tree_off);
   float4 p = pos[ids[slot]];
@@ -255,8 +283,10 @@ __global__ void __launch_bounds__(kBlock) targets_kernel(const Segment *__restri
                                                           int64_t *__restrict__ tgt_slot, int *__restrict__ tgt_seg)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  int a = find_seg(tgt_off, nseg, t);
+  const bool valid = t < T;
+  if (!valid) t = T - 1;
+  int a = find_seg_warp(tgt_off, nseg, t);
+  if (!valid) return;
   const Segment sg = segs[a];
   int j = t - sg.tgt_off;
   int64_t slot = sg.slot_base + j;
@@ -302,7 +332,9 @@ __global__ void __launch_bounds__(kBlock) walk_gather_kernel(const int *__restri
 __global__ void __launch_bounds__(kBlock) fill_tgt_seg_kernel(const int *__restrict__ tgt_off, int nseg, int T, int *__restrict__ tgt_seg)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) tgt_seg[t] = find_seg(tgt_off, nseg, t);
+  const bool valid = t < T;
+  const int a = find_seg_warp(tgt_off, nseg, valid ? t : T - 1);
+  if (valid) tgt_seg[t] = a;
 }
 
 __global__ void pre_walk_kernel(const Segment *__restrict__ segs, int nseg, SubState *__restrict__ subs, DevConfig cfg)
@@ -435,19 +467,50 @@ __global__ void __launch_bounds__(kBlock) hoare_flags_kernel(const Segment *__re
                                                               const int64_t *__restrict__ tgt_slot, int T, const float *__restrict__ E,
                                                               SubState *__restrict__ subs, const int *__restrict__ rho,
                                                               int *__restrict__ uflag, int *__restrict__ bflag)
-{ // uflag/bflag are pre-cleared; every entry writes the flags of ITS reference index
+{ // uflag/bflag are pre-cleared; every entry writes the flags of ITS reference index.  hoare_last (the largest reference index
+  // of a bound entry inside [1, Nb)) is a max over up to 1e8 entries of ONE subhalo: reduced per block before the atomic
+  __shared__ int s_max[kBlock / 32];
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const Segment sg = segs[tgt_seg[t]];
-  if (!hoare_segment(sg, rho)) return;
-  SubState &st = subs[sg.sub];
-  if (st.status == kDisrupted) return;
-  const int r = rho ? rho[tgt_slot[t]] : t - sg.tgt_off;
-  const bool bound = E[tgt_slot[t]] < 0.f;
-  uflag[sg.tgt_off + r] = (!bound && r >= 1 && r < st.hoare_nb);
-  bflag[sg.tgt_off + r] = (bound && r >= st.hoare_nb);
-  if (bound && r == 0) st.hoare_first_bound = 1;
-  if (bound && r >= 1 && r < st.hoare_nb) atomicMax(&st.hoare_last, r);
+  const int t_first = blockIdx.x * blockDim.x, t_last = min(t_first + (int)blockDim.x, T) - 1;
+  const bool uniform = tgt_seg[t_first] == tgt_seg[t_last]; // tgt_seg is non-decreasing: the whole block is one segment
+  int cand = 0;                                             // this thread's candidate for hoare_last (0 = none)
+  int sub = -1;
+  if (t < T)
+  {
+    const Segment sg = segs[tgt_seg[t]];
+    if (hoare_segment(sg, rho))
+    {
+      SubState &st = subs[sg.sub];
+      if (st.status != kDisrupted)
+      {
+        const int r = rho ? rho[tgt_slot[t]] : t - sg.tgt_off;
+        const bool bound = E[tgt_slot[t]] < 0.f;
+        uflag[sg.tgt_off + r] = (!bound && r >= 1 && r < st.hoare_nb);
+        bflag[sg.tgt_off + r] = (bound && r >= st.hoare_nb);
+        if (bound && r == 0) st.hoare_first_bound = 1;
+        if (bound && r >= 1 && r < st.hoare_nb)
+        {
+          cand = r;
+          sub = sg.sub;
+        }
+      }
+    }
+  }
+  if (!uniform)
+  {
+    if (cand > 0) atomicMax(&subs[sub].hoare_last, cand);
+    return;
+  }
+  const int wmax = __reduce_max_sync(0xffffffffu, cand);
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int m = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) m = max(m, s_max[w]);
+    if (m > 0) atomicMax(&subs[segs[tgt_seg[t_first]].sub].hoare_last, m);
+  }
 }
 __global__ void __launch_bounds__(kBlock) hoare_fpos_kernel(const Segment *__restrict__ segs, const int *__restrict__ tgt_seg, int T,
                                                              const int *__restrict__ uflag, const int *__restrict__ uscan, int *__restrict__ fpos)
@@ -765,8 +828,10 @@ __global__ void __launch_bounds__(kBlock) pack_output_kernel(const int64_t *__re
                                                               int *__restrict__ out_ids, float *__restrict__ out_E)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int s = find_seg64(out_off, nsub, i);
+  const bool valid = i < total;
+  if (!valid) i = total - 1;
+  int s = find_seg_warp(out_off, nsub, i);
+  if (!valid) return;
   int64_t o = i - out_off[s];
   out_ids[i] = ids[slot_base[s] + o];
   if (out_E) out_E[i] = (o < nbound[s]) ? E[slot_base[s] + o] : 0.f;
@@ -1278,6 +1343,17 @@ static bool trace_on()
     }                                                                                                                       \
   } while (0)
 
+void wait_upload_wave(Context &c, int wave)
+{
+  std::unique_lock<std::mutex> lk(c.up_m);
+  c.up_cv.wait(lk, [&] { return c.up_wave_done >= wave || !c.uploader.joinable(); });
+  if (!c.up_error.empty()) throw CudaError{HBTU_ERR_CUDA, c.up_error};
+}
+void finish_upload(Context &c)
+{
+  if (c.uploader.joinable()) c.uploader.join();
+}
+
 void execute_batch(Context &c)
 {
   const auto trace_t0 = std::chrono::steady_clock::now();
@@ -1345,13 +1421,15 @@ void execute_batch(Context &c)
 
   // asynchronous staging (hbtu_unbind_batch): the first wave of the upload is needed by the first round, the dominant root only
   // by level 0; a re-execution of the same staged batch finds both events completed
-  if (c.waves_pending) HBT_CUDA(cudaStreamWaitEvent(st, c.ev_wave[0], 0));
+  if (c.waves_pending) wait_upload_wave(c, 1);
+  HBT_TRACE(trace_t0, "upload wave 1 landed");
   for (int level = c.max_depth; level >= 0; level--)
   {
     if (level == 0 && c.waves_pending)
     {
-      HBT_CUDA(cudaStreamWaitEvent(st, c.ev_wave[1], 0));
+      wait_upload_wave(c, 2);
       c.waves_pending = false;
+      HBT_TRACE(trace_t0, "upload wave 2 landed");
     }
     const std::vector<int> &lv = c.levels[level];
     const int64_t M = c.cfg.max_sample;
@@ -1527,11 +1605,10 @@ void execute_batch(Context &c)
     cudaEventElapsedTime(&ms, c.ev_exec[0], c.ev_exec[1]);
     c.stats.execute_ms = ms;
   }
-  if (c.staged_async && cudaEventQuery(c.ev_wave[1]) == cudaSuccess)
-  { // duration of the asynchronous uploads (they ran behind the kernels)
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c.ev_copy0, c.ev_wave[1]) == cudaSuccess) c.stats.h2d_ms = ms;
-    cudaGetLastError();
+  if (c.staged_async)
+  { // duration of the asynchronous upload (it ran behind the kernels of the deeper levels)
+    finish_upload(c);
+    c.stats.h2d_ms = c.up_ms;
   }
   c.stats.kernel_launches = c.ls.launches;
   c.executed = true;
