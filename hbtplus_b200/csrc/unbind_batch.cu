@@ -1617,6 +1617,7 @@ void execute_batch(Context &c)
 void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
 {
   if (!c.executed) throw CudaError{HBTU_ERR_INVALID, "hbtu_fetch before hbtu_execute"};
+  const auto trace_t0 = std::chrono::steady_clock::now();
   cudaStream_t st = c.stream;
   const int nsub = (int)c.nsub;
   cudaEvent_t e0 = c.ev[0], e1 = c.ev[1];
@@ -1662,6 +1663,7 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
     o.flags = c.io_in[s].flags;
   }
   const int64_t total = out_off[nsub];
+  HBT_TRACE(trace_t0, "fetch: records read back and converted (%d subhaloes)", nsub);
   if (total > order_capacity) throw CudaError{HBTU_ERR_CAPACITY, "order_out too small"};
   std::memcpy(order_offset, out_off.data(), sizeof(int64_t) * (nsub + 1));
   if (total > 0)
@@ -1674,12 +1676,18 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
     float *d_oe = energy_out ? c.arena.alloc<float>(total) : nullptr;
     pack_output_kernel<<<grid_for(total), kBlock, 0, st>>>(d_off, d_sb, d_nb, nsub, total, c.d_ids, c.d_E, d_out, d_oe);
     HBT_CHECK_LAUNCH();
+    if (trace_on())
+    {
+      HBT_CUDA(cudaStreamSynchronize(st));
+      HBT_TRACE(trace_t0, "fetch: particle orders packed on the device (%lld entries)", (long long)total);
+    }
     HBT_CUDA(cudaMemcpyAsync(order_out, d_out, sizeof(int) * total, cudaMemcpyDeviceToHost, st));
     if (energy_out) HBT_CUDA(cudaMemcpyAsync(energy_out, d_oe, sizeof(float) * total, cudaMemcpyDeviceToHost, st));
     c.stats.d2h_bytes = total * (energy_out ? 8 : 4) + (int64_t)nsub * sizeof(SubState);
   }
   HBT_CUDA(cudaEventRecord(e1, st));
   HBT_CUDA(cudaStreamSynchronize(st));
+  HBT_TRACE(trace_t0, "fetch: done");
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   c.stats.d2h_ms = ms;
