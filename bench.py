@@ -432,7 +432,8 @@ def bench_idtable_row(ctx, n, n_cpu, peaks):
         t0 = time.perf_counter(); ctx.idtable_build(ids); eb.append(time.perf_counter() - t0); tb.append(ctx.stats().execute_ms * 1e-3)
         t0 = time.perf_counter(); out = ctx.idtable_query(q); eq.append(time.perf_counter() - t0); tq.append(ctx.stats().execute_ms * 1e-3)
     assert int((out >= 0).sum()) == n // 2
-    # algorithmic bytes: build 8 R + 12 W (keys) + 12 R + 12 W (one sort pass); query 8 R + 8 W + 8 probe
+    # algorithmic bytes (kept from round 1 so that the fractions compare): build 8 R + 12 W (keys) + 12 R + 12 W (one pass over the
+    # pairs); query 8 R + 8 W + 8 probe.  The hash table of round 2 moves one random 32-byte sector per entry and ~1.5 per query.
     bbytes, qbytes = 44, 24
     k = float(np.min(tb)) + float(np.min(tq))
     row = {"table_entries": int(n), "queries": int(len(q)), "build_kernel_ms": float(np.min(tb)) * 1e3, "query_kernel_ms": float(np.min(tq)) * 1e3,
@@ -489,6 +490,14 @@ def bench_dropin_row(wl, particles, dev, csnap, cpu_threads):
     row = {"api": "SubhaloSnapshot_t::RefineParticles() via libhbtdropin_v32.so", "particles": int(snap.npart), "subhaloes": int(nsub),
            "seconds_first_call": secs[0], "seconds": float(np.min(secs[1:])), "value": snap.npart / float(np.min(secs[1:])), "unit": UNIT,
            "host_threads": cpu_threads, "sum_nbound": int(r.io["nbound"].sum())}
+    try:  # where the last call's wall time went inside the shim (integration/subhalo_unbind_b200.cpp: HBT_B200_LastBatchTimes)
+        import ctypes as C
+        t4 = (C.c_double * 4)()
+        drop.HBT_B200_LastBatchTimes(t4)
+        row["last_call_ms"] = {"pack_aos_to_pinned_soa": 1e3 * t4[0], "hbtu_unbind_batch": 1e3 * t4[1], "permute_particle_vectors": 1e3 * t4[2],
+                               "refine_particles_total": 1e3 * secs[-1]}
+    except AttributeError:
+        pass
     if po.have_ref():
         ref = po.load_ref()
         ref.hbtref_set_num_threads(cpu_threads)

@@ -64,8 +64,8 @@ struct Context
   SubState *d_subs = nullptr;
   int64_t *d_part_offset = nullptr, *d_slot_base = nullptr;
   int64_t cap_subs = 0;
-  uint64_t *d_idt_key = nullptr; // idtable.cu: sorted (order-preserving) particle Ids of the last hbtu_idtable_build
-  int *d_idt_val = nullptr;      // and their indices
+  void *d_idt_slots = nullptr; // idtable.cu: open-addressing table (Id, index) of the last hbtu_idtable_build, idt_cap + 1 slots
+  int64_t idt_cap = 0;
   int64_t idt_n = 0;
   unsigned long long *d_counters = nullptr;
   bool count_interactions = false;

@@ -14,7 +14,9 @@
 // Build:  g++ -std=c++11 -O2 -fopenmp $(HBT_DEFS) -I$(HBT)/src -I<repo>/include -c subhalo_unbind_b200.cpp
 // Link :  replace subhalo_unbind.o by subhalo_unbind_b200.o and add -L<repo>/hbtplus_b200/csrc -lhbtunbind
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <condition_variable>
 #include <cstring>
@@ -105,8 +107,12 @@ struct Device
   PinnedBuffer<float> pos_mass, vel;
   PinnedBuffer<int32_t> order;
   PinnedBuffer<float> energy;
+  std::vector<Particle_t> all; // batch-wide copy of the particle records (grow-only: its pages are faulted in once per process)
 };
 std::mutex g_table_mutex;
+inline double wall_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+std::mutex g_times_mutex;
+double g_last_times[4] = {0, 0, 0, 0}; // seconds of pack / library call / unpack of the last batch, and its particle count
 std::vector<Device *> g_devs;    // current device list
 std::vector<Device *> g_retired; // devices of an earlier HBT_UNBIND_DEVICES list (contexts destroyed, objects kept)
 std::string g_devices;
@@ -210,7 +216,15 @@ struct Batch
     part_offset.assign(nsub + 1, 0);
     for (int64_t s = 0; s < nsub; s++) part_offset[s + 1] = part_offset[s] + (int64_t)subs[s]->Particles.size();
     const int64_t N = part_offset[nsub];
-    std::vector<Particle_t> all(N); // the reference's Unbind also makes one full copy (subhalo_unbind.cpp:409-415)
+    const double t_begin = wall_seconds();
+    // the reference's Unbind also makes one full copy (subhalo_unbind.cpp:409-415); here the copy lives in a grow-only buffer of
+    // the device, so that a snapshot does not pay 10 page faults per thousand particles again
+    if ((int64_t)dev->all.size() < N)
+    {
+      std::vector<Particle_t>().swap(dev->all);
+      dev->all.resize(N + N / 8);
+    }
+    Particle_t *all = dev->all.data();
     float *pos_mass = dev->pos_mass.get(4 * (size_t)N), *vel = dev->vel.get(4 * (size_t)N);
     std::vector<hbtu_sub_io> io(nsub);
     // work items of the pack / unpack loops: (subhalo, chunk of <= kChunk particles), so that a dominant subhalo (an AqA2
@@ -287,9 +301,11 @@ struct Batch
 #else
     float *pe = nullptr;
 #endif
+    const double t_packed = wall_seconds();
     call_library_locked(dev, "hbtu_unbind_batch", [&](hbtu_ctx *ctx) {
       return hbtu_unbind_batch(ctx, &e, nsub, part_offset.data(), pos_mass, vel, no, nl, io.data(), flags, cap, order_offset.data(), order, pe);
     });
+    const double t_called = wall_seconds();
     // unpack: the new particle lists (a list can hold particles of nested subhaloes: gather from the batch-wide copy), in chunks
     // like the pack; the vectors are resized first (serially per subhalo, cheap) so that the chunks can write independently
 #pragma omp parallel for schedule(dynamic, 16)
@@ -338,6 +354,17 @@ struct Batch
       if (sub.Particles.size() >= 2) sub.CountParticleTypes(); else sub.CountParticles(); // host bookkeeping stays on the host
 #endif
     }
+    const double t_end = wall_seconds();
+    {
+      std::lock_guard<std::mutex> lk(g_times_mutex);
+      g_last_times[0] = t_packed - t_begin;
+      g_last_times[1] = t_called - t_packed;
+      g_last_times[2] = t_end - t_called;
+      g_last_times[3] = (double)N;
+    }
+    if (getenv("HBT_B200_TRACE"))
+      fprintf(stderr, "[hbt_b200] batch of %lld subhaloes / %lld particles: pack %.1f ms, hbtu_unbind_batch %.1f ms, unpack %.1f ms\n",
+              (long long)nsub, (long long)N, 1e3 * (t_packed - t_begin), 1e3 * (t_called - t_packed), 1e3 * (t_end - t_called));
   }
 };
 
@@ -508,6 +535,14 @@ struct UnbindCombiner
   }
 } g_unbind_combiner;
 } // namespace
+
+// where the wall time of the last batch went (seconds: AoS -> pinned SoA pack, hbtu_unbind_batch, permutation of the
+// vector<Particle_t>s; out[3] = its particle count); for the bench's drop-in row and for a maintainer's own timing
+extern "C" void HBT_B200_LastBatchTimes(double out[4])
+{
+  std::lock_guard<std::mutex> lk(g_times_mutex);
+  for (int i = 0; i < 4; i++) out[i] = g_last_times[i];
+}
 
 void Subhalo_t::Unbind(const Snapshot_t &epoch)
 { // second caller: subhalo_merge.cpp:207-210 (merged hosts), one subhalo per call, from concurrent OpenMP threads

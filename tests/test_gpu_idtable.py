@@ -42,3 +42,11 @@ def test_idtable_edge_cases(make_ctx):
     assert np.array_equal(ctx.idtable_query(np.array([1, 2, 3])), [-1, -1, -1])
     ctx.idtable_build(np.array([5, -7, 2**62, 5, 0]))
     assert np.array_equal(ctx.idtable_query(np.array([5, -7, 2**62, 0, 1, -8, 2**62 - 1])), [0, 1, 2, 4, -1, -1, -1])  # duplicates: lowest index
+    # Id -1 is the table's empty-slot marker (and the reference's NullParticleId): a table that really holds it still answers
+    assert np.array_equal(ctx.idtable_query(np.array([-1, 5])), [-1, 0])
+    ctx.idtable_build(np.array([3, -1, 9, -1]))
+    assert np.array_equal(ctx.idtable_query(np.array([-1, 9, 3, -2, np.iinfo(np.int64).min])), [1, 2, 0, -1, -1])
+    # a table small enough that the probe sequence wraps around the end of the slot array
+    ids = np.arange(31, dtype=np.int64) * 1000003 + 17
+    ctx.idtable_build(ids)
+    assert np.array_equal(ctx.idtable_query(np.concatenate([ids[::-1], ids + 1])), np.concatenate([np.arange(30, -1, -1), np.full(31, -1)]))
