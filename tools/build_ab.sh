@@ -8,10 +8,11 @@ rm -f "$OUT"/*.so
 build() { # name, flags
   make -s -j8 BUILD=build_$1 LIB=$OUT/lib_$1.so EXTRA="$2" > /dev/null && echo "built $1"
 }
+# the variants of the last sweep of the round (profiles/r02_walk_notes.md section 1); edit to taste, then
+#   python tools/ab_walk.py lib=default lib=tools/ab/lib_pre.so lib=tools/ab/lib_u2.so,walk_masked_blocks=8 ...    on the GPU box
 build pre "-DHBT_M_PREFETCH=1" &
-build exold "-DHBT_M_UNROLL_D=4" &
+build u2 "-DHBT_M_UNROLL=2 -DHBT_M_UNROLL_D=2" &
 wait
 build big "-DHBT_A_PEND=24 -DHBT_M_PEND=12" &
-build u8 "-DHBT_M_UNROLL=8" &
 wait
 ls -la $OUT
