@@ -761,7 +761,7 @@ def main():
             "gpu_launches": int(launches * args.steps),
             "roofline": {"bound": "fp32_issue", "achieved": inter_rate * FLOP_PER_INTERACTION / 1e12, "peak": peak_inter * FLOP_PER_INTERACTION / 1e12,
                          "unit": "TFLOP/s", "frac": inter_rate / peak_inter, "traffic": traffic, "traffic_kernel": traffic_note,
-                         "kernel": "walk phase: walk_masked_kernel (segments >= 8192 targets) + walk_small_kernel / walk_kernel (smaller ones)",
+                         "kernel": "walk phase: walk_masked_kernel (segments >= 256 targets) + walk_small_kernel / walk_kernel (smaller ones)",
                          "interactions_per_s": inter_rate, "peak_interactions_per_s": peak_inter,
                          "peak_source": f"{nsm} SM x 128 fp32 lanes x sm_max_mhz ({peak_src}) / 8 issue slots per interaction (SURVEY.md 8(d)); 12 flop per interaction",
                          "note": "tensor cores deliberately unused (not a dense contraction); kernel share of the step = walk/total in config.phase_ms"},

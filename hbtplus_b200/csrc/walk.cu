@@ -114,7 +114,9 @@ WalkTuning &walk_tuning()
     v.forced_tpl = env("HBTU_WALK_TPL", 0);
     v.big4 = env("HBTU_WALK_BIG4", 1 << 20);
     v.big2 = env("HBTU_WALK_BIG2", 1 << 19);
-    v.group_min = env("HBTU_WALK_GROUP_MIN", 1 << 13); // segments with at least this many targets use the masked group walk (0 = never)
+    v.group_min = env("HBTU_WALK_GROUP_MIN", 256); // segments with at least this many targets use the masked group walk (0 = never).
+    // Swept on B200 with the 64-target kernel (profiles/r02_ab_group_min.jsonl): 8192 -> 256 takes the walk of cfg 3 from 36.4 to
+    // 31.4 ms, of a cfg-4 shard from 733 to 689 ms, of cfg 2 from 918 to 909 ms; flat between 512 and 64
     v.masked_pairs = env("HBTU_WALK_MASKED_PAIRS", HBT_MASKED_DEFAULT_PAIRS) == 1 ? 1 : 2;
     v.masked_blocks = env("HBTU_WALK_MASKED_BLOCKS", v.masked_pairs == 1 ? HBT_MASKED_DEFAULT_BLOCKS_NP1 : HBT_MASKED_DEFAULT_BLOCKS_NP2);
     v.small_max = env("HBTU_WALK_SMALL_MAX", HBT_SMALL_DEFAULT_MAX);

@@ -94,6 +94,57 @@ __device__ __forceinline__ unsigned decide_half(unsigned mask, unsigned lanebit,
   return openers;
 }
 
+// The same with the reciprocal square root INSIDE the predicate: only the lanes that accept need it, and a slice whose mask is
+// empty (half of the accept-all pair-elements have targets in one slice only) or whose targets all open the node issues no
+// MUFU.RSQ work at all - the XU pipe co-limits the masked walk (profiles/r02_walk_notes.md).
+template <bool COUNT>
+__device__ __forceinline__ unsigned decide_half_rsq(unsigned mask, unsigned lanebit, float lenq, float r2, float w, float &acc, unsigned &n_acc)
+{
+  unsigned openers;
+  if (COUNT)
+  {
+    unsigned accepted;
+    asm volatile("{\n\t.reg .pred pin, pop, pac;\n\t.reg .b32 t;\n\t.reg .f32 ri;\n\t"
+                 "and.b32 t, %3, %4;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "setp.gt.and.f32 pop, %5, %6, pin;\n\tsetp.le.and.f32 pac, %5, %6, pin;\n\t"
+                 "@pac rsqrt.approx.ftz.f32 ri, %6;\n\t@pac fma.rn.f32 %0, %7, ri, %0;\n\tselp.u32 %2, 1, 0, pac;\n\t"
+                 "vote.sync.ballot.b32 %1, pop, 0xffffffff;\n\t}"
+                 : "+f"(acc), "=r"(openers), "=r"(accepted)
+                 : "r"(mask), "r"(lanebit), "f"(lenq), "f"(r2), "f"(w));
+    n_acc += accepted;
+  }
+  else
+    asm volatile("{\n\t.reg .pred pin, pop, pac;\n\t.reg .b32 t;\n\t.reg .f32 ri;\n\t"
+                 "and.b32 t, %2, %3;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "setp.gt.and.f32 pop, %4, %5, pin;\n\tsetp.le.and.f32 pac, %4, %5, pin;\n\t"
+                 "@pac rsqrt.approx.ftz.f32 ri, %5;\n\t@pac fma.rn.f32 %0, %6, ri, %0;\n\t"
+                 "vote.sync.ballot.b32 %1, pop, 0xffffffff;\n\t}"
+                 : "+f"(acc), "=r"(openers)
+                 : "r"(mask), "r"(lanebit), "f"(lenq), "f"(r2), "f"(w));
+  return openers;
+}
+// accept-all element, one slice: acc += w / sqrt(r2) for the lanes of the mask, MUFU.RSQ and FFMA under the same predicate
+template <bool COUNT>
+__device__ __forceinline__ void accept_half_rsq(unsigned mask, unsigned lanebit, float r2, float w, float &acc, unsigned &n_acc)
+{
+  if (COUNT)
+  {
+    unsigned accepted;
+    asm volatile("{\n\t.reg .pred pin;\n\t.reg .b32 t;\n\t.reg .f32 ri;\n\t"
+                 "and.b32 t, %2, %3;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "@pin rsqrt.approx.ftz.f32 ri, %4;\n\t@pin fma.rn.f32 %0, %5, ri, %0;\n\tselp.u32 %1, 1, 0, pin;\n\t}"
+                 : "+f"(acc), "=r"(accepted)
+                 : "r"(mask), "r"(lanebit), "f"(r2), "f"(w));
+    n_acc += accepted;
+  }
+  else
+    asm volatile("{\n\t.reg .pred pin;\n\t.reg .b32 t;\n\t.reg .f32 ri;\n\t"
+                 "and.b32 t, %1, %2;\n\tsetp.ne.u32 pin, t, 0;\n\t"
+                 "@pin rsqrt.approx.ftz.f32 ri, %3;\n\t@pin fma.rn.f32 %0, %4, ri, %0;\n\t}"
+                 : "+f"(acc)
+                 : "r"(mask), "r"(lanebit), "f"(r2), "f"(w));
+}
+
 // squared distances of node n to the T targets of a lane: (dx*dx + dy*dy) + dz*dz as FMUL, FFMA, FFMA - two targets per
 // instruction where the layout allows it (non-periodic, even T; the sign of dx is irrelevant)
 template <int T, bool PERIODIC>

@@ -46,6 +46,16 @@
                          // 8 % of the stall samples on the first use of the loaded node, but the six extra live registers cost more than
                          // the hidden latency returns: 925 -> 982 ms on the bench (profiles/r02_walk_notes.md).  Kept for the record.
 #endif
+#ifndef HBT_M_PRED_RSQ
+#define HBT_M_PRED_RSQ 0 // 1: the masked lists issue MUFU.RSQ under the accept predicate (meant to save the XU work of empty slices and
+                         // all-open nodes).  ptxas 12.9 hoists the predicated rsqrt into an unconditional MUFU.RSQ anyway and the longer
+                         // predicate chains spill (28 -> 140 bytes at 72 registers): kept for the record, off
+#endif
+#ifndef HBT_M_POPC_SEL
+#define HBT_M_POPC_SEL 0 // 1: ONE prefix popcount per lane for its (exclusive) queue instead of one per queue (POPC shares the XU pipe with
+                         // MUFU.RSQ: 16 -> 10 POPC per iteration).  Measured: 904 -> 916 ms on the bench - the select chain in front of the
+                         // popcount costs more latency than the XU cycles return (profiles/r02_ab_cfg2_v4.jsonl).  Off.
+#endif
 #define HBT_M_PRAGMA_(x) _Pragma(#x)
 #define HBT_M_PRAGMA_UNROLL(n) HBT_M_PRAGMA_(unroll n)
 #ifndef HBT_MASKED_STAT
@@ -202,11 +212,16 @@ __device__ __forceinline__ void masked_eval_accept(const MaskedSmem &sm, int cnt
     const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
     const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
     const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+#if HBT_M_PRED_RSQ
+    accept_half_rsq<COUNT>(m.x, lanebit, r2.x, n.w, acca, n_acc);
+    accept_half_rsq<COUNT>(m.y, lanebit, r2.y, n.w, accb, n_acc);
+#else
     const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
     const bool ina = (m.x & lanebit) != 0u, inb = (m.y & lanebit) != 0u;
     if (ina) acca = fmaf(n.w, ra, acca);
     if (inb) accb = fmaf(n.w, rb, accb);
     if (COUNT) n_acc += (unsigned)ina + (unsigned)inb;
+#endif
   }
   accd[K] += (double)acca;
   accd[K + 1] += (double)accb;
@@ -235,10 +250,15 @@ __device__ __forceinline__ void masked_eval_split(MaskedSmem &sm, int cnt, int c
     const float2 dy = f2_add(pyy, make_float2(n.y, n.y));
     const float2 dz = f2_add(pzz, make_float2(n.z, n.z));
     const float2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
-    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
     // reference criterion, per target (src/gravity_tree.cpp:135): in the mask and lenq > r2 -> opener, else accumulate
+#if HBT_M_PRED_RSQ
+    const unsigned oa = decide_half_rsq<COUNT>(m.x, lanebit, lenq, r2.x, n.w, acca, n_acc);
+    const unsigned ob = decide_half_rsq<COUNT>(m.y, lanebit, lenq, r2.y, n.w, accb, n_acc);
+#else
+    const float ra = rsqrt_raw(r2.x), rb = rsqrt_raw(r2.y);
     const unsigned oa = decide_half<COUNT>(m.x, lanebit, lenq, r2.x, n.w, ra, acca, n_acc);
     const unsigned ob = decide_half<COUNT>(m.y, lanebit, lenq, r2.y, n.w, rb, accb, n_acc);
+#endif
     if (lane == 0) *reinterpret_cast<uint2 *>(&e.ma) = make_uint2(oa, ob); // the openers walk the node's children
   }
   for (int i = kMCap - cntx; i < kMCap; i++)
@@ -345,14 +365,13 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
         const ChainEntry &c = sm.stack[ncs - 1 - r];
         cur = c.cur;
         pend = c.pend;
-        int bits = 0;
+        full = true; // chain masks are subsets of the group's: the whole group walks the chain iff they are equal
 #pragma unroll
         for (int k = 0; k < T; k++)
         {
           cm[k] = c.m[k];
-          bits += __popc(cm[k]);
+          full = full && cm[k] == vm[k];
         }
-        full = bits == n0;
 #if HBT_M_PREFETCH
         pre = false;
 #endif
@@ -430,10 +449,19 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     }
     const int cO = __popc(mO);
     if (ncs + cO > kMStack) return false; // stack exhausted (pathologically deep tree): the caller redoes the group per lane
-    if (toA) sm.alist[(ab + na + __popc(mA & lt)) & 63] = xs;
+#if HBT_M_POPC_SEL
+    // a lane queues its node in exactly one of: dense ring, stack, and per pair accept-all / deciding (bare) / deciding (exact);
+    // one pair per warp: ONE prefix popcount over the ballot of the lane's own queue gives its position there
+    int psel = 0;
+    if constexpr (NP == 1) psel = __popc((toA ? mA : toO ? mO : toAcc ? mAc[0] : toD ? (bare ? mD[0] : mX[0]) : 0u) & lt);
+    const int posA = NP == 1 ? psel : __popc(mA & lt), posO = NP == 1 ? psel : __popc(mO & lt);
+#else
+    const int posA = __popc(mA & lt), posO = __popc(mO & lt);
+#endif
+    if (toA) sm.alist[(ab + na + posA) & 63] = xs;
     if (toO)
     {
-      ChainEntry &c = sm.stack[ncs + __popc(mO & lt)];
+      ChainEntry &c = sm.stack[ncs + posO];
       c.cur = cur + 1;
       c.pend = kend;
 #pragma unroll
@@ -441,7 +469,14 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
     }
     int eidx[NP]; // position of the lane's deciding element in the list of pair r
 #pragma unroll
-    for (int r = 0; r < NP; r++) eidx[r] = bare ? nd[r] + __popc(mD[r] & lt) : kMCap - 1 - nx[r] - __popc(mX[r] & lt);
+    for (int r = 0; r < NP; r++)
+    {
+#if HBT_M_POPC_SEL
+      if constexpr (NP == 1) eidx[r] = bare ? nd[r] + psel : kMCap - 1 - nx[r] - psel;
+      else
+#endif
+        eidx[r] = bare ? nd[r] + __popc(mD[r] & lt) : kMCap - 1 - nx[r] - __popc(mX[r] & lt);
+    }
     if (toP)
     { // the chain of the children waits for the openers: it remembers where its element sits in every pair's list
       ChainEntry &c = sm.pending[np + __popc(mP & lt)];
@@ -461,7 +496,11 @@ __device__ __forceinline__ bool masked_group_walk(MaskedSmem &sm, int lane, cons
       for (int r = 0; r < NP; r++)
         if (hp[r])
         {
+#if HBT_M_POPC_SEL
+          const int idx = nac[r] + (NP == 1 ? psel : __popc(mAc[r] & lt));
+#else
           const int idx = nac[r] + __popc(mAc[r] & lt);
+#endif
           sm.a_xm[r][idx] = np4;
           sm.a_m[r][idx] = make_uint2(cm[2 * r], cm[2 * r + 1]);
         }

@@ -166,6 +166,20 @@ static inline unsigned decide_half(unsigned mask, unsigned lanebit, float lenq, 
   }
   return __ballot_sync(kFull, in && open);
 }
+template <bool COUNT>
+static inline unsigned decide_half_rsq(unsigned mask, unsigned lanebit, float lenq, float r2, float w, float &acc, unsigned &n_acc)
+{ // host twin of walk_common.cuh::decide_half_rsq
+  return decide_half<COUNT>(mask, lanebit, lenq, r2, w, rsqrt_raw(r2), acc, n_acc);
+}
+template <bool COUNT>
+static inline void accept_half_rsq(unsigned mask, unsigned lanebit, float r2, float w, float &acc, unsigned &n_acc)
+{ // host twin of walk_common.cuh::accept_half_rsq
+  if ((mask & lanebit) != 0u)
+  {
+    acc = std::fma(w, rsqrt_raw(r2), acc);
+    if (COUNT) n_acc++;
+  }
+}
 namespace hbt
 {
 static inline float nearest_f(float x, float box, float half) { return x > half ? x - box : (x < -half ? x + box : x); }

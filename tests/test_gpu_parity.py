@@ -298,7 +298,7 @@ def test_multi_target_walk_variants(tpl, tmp_path):
 @pytest.mark.parametrize("route", ["masked128", "masked64", "small"])
 def test_forced_walk_kernels_on_every_segment(route):
     """Every segment forced through ONE kernel family: the masked group walk with 128-target groups (HBTU_WALK_GROUP_MIN=1; the
-    kernel of segments >= 8192 targets), the same with 64-target groups (HBTU_WALK_MASKED_PAIRS=1), and the small-subhalo
+    kernel of segments >= 256 targets), the same with 64-target groups (HBTU_WALK_MASKED_PAIRS=1), and the small-subhalo
     kernel (HBTU_WALK_SMALL_MAX huge: the dense sweep on every tree).  The device-counted accepted interactions must equal
     the oracle's, i.e. every target takes the reference's decisions under every routing."""
     code = (

@@ -27,11 +27,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--count", action="store_true")
+    ap.add_argument("--world", type=int, default=1, help="cfg4: rank 0's shard of a snapshot dealt to this many ranks")
     ap.add_argument("specs", nargs="+")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     wl = bench.WORKLOADS[args.workload]
-    snap = wl.make(args.particles, dev, 0)
+    snap = wl.make(args.particles, dev, 0, args.world)
     torch.cuda.empty_cache()
     e = capi.make_epoch(1.0)
     for spec in args.specs:

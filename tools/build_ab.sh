@@ -10,9 +10,7 @@ build() { # name, flags
 }
 # the variants of the last sweep of the round (profiles/r02_walk_notes.md section 1); edit to taste, then
 #   python tools/ab_walk.py lib=default lib=tools/ab/lib_pre.so lib=tools/ab/lib_u2.so,walk_masked_blocks=8 ...    on the GPU box
-build pre "-DHBT_M_PREFETCH=1" &
-build u2 "-DHBT_M_UNROLL=2 -DHBT_M_UNROLL_D=2" &
-wait
-build big "-DHBT_A_PEND=24 -DHBT_M_PEND=12" &
+build sel0 "-DHBT_M_POPC_SEL=0" &
+build rsq1 "-DHBT_M_PRED_RSQ=1" &
 wait
 ls -la $OUT
