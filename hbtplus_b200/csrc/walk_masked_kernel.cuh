@@ -13,12 +13,19 @@ namespace hbt
 
 static constexpr int kMW = 4; // warps per CTA (warps are independent)
 
+#ifndef HBT_MASKED_SMEM_TOTAL
+#define HBT_MASKED_SMEM_TOTAL 233472 // shared memory of an SM the resident CTAs may fill (228 KB = the largest carve-out) ...
+#endif
+#ifndef HBT_MASKED_CARVEOUT
+#define HBT_MASKED_CARVEOUT cudaSharedmemCarveoutMaxShared // ... and the matching carve-out preference (percent of the maximum)
+#endif
+
 // chain-stack entries per warp: what fits into the 228 KB of shared memory of an SM with MINB resident CTAs of kMW warps
 // (1 KB per CTA is reserved by the system; static shared memory is limited to 48 KB per CTA)
 template <int MINB, int NP>
 struct MaskedStack
 {
-  static constexpr int kPerWarp = ((233472 / MINB - 1024) / kMW) & ~15;
+  static constexpr int kPerWarp = ((HBT_MASKED_SMEM_TOTAL / MINB - 1024) / kMW) & ~15;
   static constexpr int kFixed = (int)sizeof(MaskedSmemT<8, NP>) - 8 * (int)sizeof(ChainEntryT<NP>);
   static constexpr int kBySm = (kPerWarp - kFixed) / (int)sizeof(ChainEntryT<NP>);
   static constexpr int kBy48K = ((48 * 1024 - 64) / kMW - kFixed) / (int)sizeof(ChainEntryT<NP>);
@@ -139,7 +146,7 @@ void launch_masked_variant(const WalkArgs &a, const DevConfig &cfg, cudaStream_t
   {
     for (auto *k : {walk_masked_kernel<true, true, MINB, NP>, walk_masked_kernel<true, false, MINB, NP>, walk_masked_kernel<false, true, MINB, NP>,
                     walk_masked_kernel<false, false, MINB, NP>})
-      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, HBT_MASKED_CARVEOUT);
     carved.fetch_or(bit, std::memory_order_release);
   }
   if (cfg.periodic)

@@ -10,7 +10,7 @@ build() { # name, flags
 }
 # the variants of the last sweep of the round (profiles/r02_walk_notes.md section 1); edit to taste, then
 #   python tools/ab_walk.py lib=default lib=tools/ab/lib_pre.so lib=tools/ab/lib_u2.so,walk_masked_blocks=8 ...    on the GPU box
-build sel0 "-DHBT_M_POPC_SEL=0" &
-build rsq1 "-DHBT_M_PRED_RSQ=1" &
+build l196 "-DHBT_MASKED_SMEM_TOTAL=200704 -DHBT_MASKED_CARVEOUT=86" &
+build l164 "-DHBT_MASKED_SMEM_TOTAL=167936 -DHBT_MASKED_CARVEOUT=72" &
 wait
 ls -la $OUT
