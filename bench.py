@@ -131,7 +131,7 @@ class MilliMill(Workload):
         for _ in range(4):
             sizes = np.clip((sizes * (particles / sizes.sum())).astype(np.int64), 20, int(max(5e5 * f, 2000)))
         parent = synth.nest_forest(rng, sizes, max_depth=3, p_nest=0.2, root=None)  # ~2e4 FoF groups (roots) + ~5e3 satellites
-        return sizes, parent
+        return synth.dfs_layout(sizes, parent)  # hierarchy by hierarchy, as RefineParticles visits them (subhalo_unbind.cpp:479-493)
 
     def centres(self, sizes, parent):
         return None  # groups uniformly in the periodic box
@@ -194,7 +194,7 @@ class Eagle(Workload):
 
         sizes, parent = self.sizes(particles * world)
         if world == 1:
-            return sizes, parent, np.arange(len(sizes))
+            return synth.dfs_layout(sizes, parent, return_order=True)
         root = sched.roots_of(parent)
         cap = sizes.astype(np.float64)
         cost_sub = cap * np.log2(np.maximum(cap, 2.0))
@@ -207,7 +207,10 @@ class Eagle(Workload):
         local = np.full(len(sizes), -1, np.int64)
         local[mine] = np.arange(len(mine))
         par = np.where(parent[mine] >= 0, local[np.maximum(parent[mine], 0)], -1)
-        return sizes[mine], par, mine
+        # the shard hierarchy by hierarchy, parents first: the order in which RefineParticles visits subhaloes (subhalo_unbind.cpp:479-493)
+        # and in which the drop-in shim lays a batch out; it lets hbtu_unbind_batch pipeline the upload of a box of many hierarchies
+        s2, p2, order = synth.dfs_layout(sizes[mine], par, return_order=True)
+        return s2, p2, mine[order]
 
     def make(self, particles, dev, rank, world: int = 1):
         sizes, parent, _ = self.shard(particles, rank, world)

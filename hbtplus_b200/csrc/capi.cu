@@ -5,6 +5,7 @@
 // sm_100 device is usable hbtu_create fails with HBTU_ERR_NODEVICE.
 #include <cub/cub.cuh>
 
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -129,8 +130,9 @@ void build_forest(Context &c, int64_t nsub, const int64_t *part_offset, const in
 // than a quarter of the batch: an AqA2 central), then that root, which the level-synchronous scheduler reaches last - and
 // execute_batch waits for each wave only where it is first needed, so the big upload hides behind the deeper levels' rounds.
 void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass, const float *vel,
-           const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags, bool overlap = false)
-{
+           const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags, bool overlap = false,
+           bool preloaded = false)
+{ // preloaded: the particle arrays of this batch are already in d_pos_next / d_vel_next (a part of a pipelined hbtu_unbind_batch)
   if (!epoch || nsub < 0 || !part_offset || (nsub > 0 && !io)) throw CudaError{HBTU_ERR_INVALID, "null argument"};
   if (nsub > 0x7ffffff0) throw CudaError{HBTU_ERR_UNSUPPORTED, "too many subhaloes"};
   finish_upload(c); // a previous asynchronous staging that was never executed
@@ -154,8 +156,22 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
   c.io_in.assign(io, io + nsub);
 
   cudaStream_t st = c.stream;
-  grow(c.d_pos, c.cap_particles, N);
-  grow(c.d_vel, c.cap_vel, N);
+  c.pipelined = false;
+  c.order_index_base = 0;
+  c.sub_index_base = 0;
+  if (preloaded)
+  {
+    if (c.cap_pos_next < N || c.cap_vel_next < N) throw CudaError{HBTU_ERR_INVALID, "internal: preloaded part larger than its buffers"};
+    std::swap(c.d_pos, c.d_pos_next);
+    std::swap(c.d_vel, c.d_vel_next);
+    std::swap(c.cap_particles, c.cap_pos_next);
+    std::swap(c.cap_vel, c.cap_vel_next);
+  }
+  else
+  {
+    grow(c.d_pos, c.cap_particles, N);
+    grow(c.d_vel, c.cap_vel, N);
+  }
   {
     int64_t cap0 = c.cap_slots, cap1 = c.cap_slots, cap2 = c.cap_slots;
     grow(c.d_ids, cap0, c.total_cap);
@@ -184,8 +200,10 @@ void stage(Context &c, const hbtu_epoch *epoch, int64_t nsub, const int64_t *par
   };
   c.stats.h2d_bytes = N * 32 + (nsub + 1) * 16;
   c.waves_pending = false;
-  c.staged_async = overlap;
-  if (!overlap)
+  c.staged_async = overlap && !preloaded;
+  if (preloaded)
+    c.stats.h2d_ms = 0; // the pipelined wrapper accounts for the upload
+  else if (!overlap)
   {
     HBT_CUDA(cudaEventRecord(c.ev[0], st));
     copy_range(st, 0, N);
@@ -404,6 +422,197 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
   c.stats.rounds = 1;
   c.stats.kernel_launches = c.ls.launches;
 }
+
+// ---- pipelined hbtu_unbind_batch ------------------------------------------------------------------
+// A batch of MANY independent hierarchies (a cosmological box: 5e5 subhaloes per GPU in the EAGLE-shaped configuration) has no
+// dominant root whose upload could hide behind the deeper levels: all of it is needed by the first round, and the whole
+// upload (104 ms per 1.7e8 particles alone on the link, 280 ms with eight GPUs sharing the host's memory) sat in front of
+// the kernels.  Hierarchies never interact and results do not depend on how subhaloes are grouped into batches, so such a
+// batch is cut at hierarchy boundaries into three parts of 1/8, 3/8 and 1/2 of the particles; part k+1 is uploaded into a
+// second pair of buffers while part k executes.  Only the first eighth of the upload stays exposed.
+std::atomic<long long> g_pipeline_min{-1}; // particles; 0 = never.  HBTU_PIPELINE_MIN / hbtu_set_tuning("pipeline_min_particles")
+long long pipeline_min()
+{
+  long long v = g_pipeline_min.load(std::memory_order_relaxed);
+  if (v < 0)
+  {
+    const char *e = getenv("HBTU_PIPELINE_MIN");
+    v = e ? atoll(e) : (1ll << 24);
+    if (v < 0) v = 0;
+    g_pipeline_min.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+struct BatchPart
+{
+  int64_t s0, s1; // subhaloes [s0, s1): whole hierarchies
+};
+
+// parts of a batch that qualifies for pipelining (empty: run it in one piece).  Needs every hierarchy to be a contiguous index
+// range with parents in front of their children - the layout integration/subhalo_unbind_b200.cpp::add_hierarchy produces.
+std::vector<BatchPart> plan_parts(const Context &c, int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list)
+{
+  std::vector<BatchPart> none;
+  const long long min_particles = pipeline_min();
+  if (min_particles <= 0 || nsub < 64 || c.split_n > 1) return none;
+  const int64_t N = part_offset[nsub] - part_offset[0];
+  if (N < min_particles || part_offset[0] != 0) return none;
+  std::vector<int32_t> parent((size_t)nsub, -1);
+  if (nest_offset)
+    for (int64_t s = 0; s < nsub; s++)
+      for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++)
+      {
+        const int32_t ch = nest_list[k];
+        if (ch < 0 || ch >= nsub || parent[ch] != -1) return none; // malformed: let stage() report it
+        parent[ch] = (int32_t)s;
+      }
+  std::vector<int64_t> hstart; // first subhalo of every hierarchy
+  for (int64_t s = 0; s < nsub; s++)
+  {
+    if (parent[s] < 0) hstart.push_back(s);
+    else if (hstart.empty() || parent[s] < hstart.back() || parent[s] >= s) return none; // not depth-first contiguous
+  }
+  if (hstart.size() < 16) return none;
+  hstart.push_back(nsub);
+  for (size_t h = 0; h + 1 < hstart.size(); h++)
+    if (part_offset[hstart[h + 1]] - part_offset[hstart[h]] > N / 4) return none; // a dominant hierarchy: the two-wave upload handles it
+  const int64_t cuts[2] = {N / 8, N / 2};
+  std::vector<BatchPart> parts;
+  int64_t begin = 0;
+  size_t h = 0;
+  for (int k = 0; k < 2; k++)
+  {
+    while (h + 1 < hstart.size() && part_offset[hstart[h]] < cuts[k]) h++;
+    if (hstart[h] > begin && hstart[h] < nsub)
+    {
+      parts.push_back(BatchPart{begin, hstart[h]});
+      begin = hstart[h];
+    }
+  }
+  parts.push_back(BatchPart{begin, nsub});
+  if (parts.size() < 2) return none;
+  return parts;
+}
+
+// upload particles [p0, p1) of the caller's arrays into d_pos_next / d_vel_next on the copy stream, from the helper thread
+void start_prefetch(Context &c, const float *pos_mass, const float *vel, int64_t p0, int64_t p1)
+{
+  finish_upload(c);
+  grow(c.d_pos_next, c.cap_pos_next, p1 - p0);
+  grow(c.d_vel_next, c.cap_vel_next, p1 - p0);
+  const char *env = getenv("HBTU_UPLOAD_CHUNK_MB");
+  const int64_t chunk = std::max<int64_t>(1, env ? atoll(env) : 32) * (int64_t)(1 << 20) / 32;
+  c.up_wave_done = 0;
+  c.up_error.clear();
+  const int device = c.device;
+  cudaStream_t cs = c.copy_stream;
+  float4 *d_pos = c.d_pos_next, *d_vel = c.d_vel_next;
+  Context *cp = &c;
+  c.uploader = std::thread([=]() {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string err;
+    if (cudaSetDevice(device) != cudaSuccess) err = "cudaSetDevice failed in the upload helper";
+    for (int64_t b = p0; b < p1 && err.empty(); b += chunk)
+    {
+      const int64_t e = std::min(p1, b + chunk);
+      cudaError_t e1 = cudaMemcpyAsync(d_pos + (b - p0), pos_mass + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs);
+      cudaError_t e2 = cudaMemcpyAsync(d_vel + (b - p0), vel + 4 * b, sizeof(float4) * (size_t)(e - b), cudaMemcpyHostToDevice, cs);
+      cudaError_t e3 = cudaStreamSynchronize(cs);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        err = std::string("particle upload failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+    }
+    std::lock_guard<std::mutex> lk(cp->up_m);
+    if (!err.empty()) cp->up_error = err;
+    cp->up_wave_done = 2;
+    cp->up_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    cp->up_cv.notify_all();
+  });
+}
+
+void add_stats(hbtu_stats &a, const hbtu_stats &b)
+{
+  a.kernel_launches += b.kernel_launches;
+  a.tree_builds += b.tree_builds;
+  a.walk_targets += b.walk_targets;
+  a.pair_interactions += b.pair_interactions;
+  a.nodes_visited += b.nodes_visited;
+  a.rounds += b.rounds;
+  a.walk_ms += b.walk_ms;
+  a.build_ms += b.build_ms;
+  a.other_ms += b.other_ms;
+  a.h2d_ms += b.h2d_ms;
+  a.d2h_ms += b.d2h_ms;
+  a.h2d_bytes += b.h2d_bytes;
+  a.d2h_bytes += b.d2h_bytes;
+  a.execute_ms += b.execute_ms;
+  a.tree_sources += b.tree_sources;
+  a.walk_fallbacks += b.walk_fallbacks;
+  a.stage_wall_ms += b.stage_wall_ms;
+  a.execute_wall_ms += b.execute_wall_ms;
+  a.fetch_wall_ms += b.fetch_wall_ms;
+  for (int i = 0; i < 8; i++) a.phase_ms[i] += b.phase_ms[i];
+}
+
+void unbind_batch_pipelined(Context &c, const std::vector<BatchPart> &parts, const hbtu_epoch *epoch, const int64_t *part_offset, const float *pos_mass,
+                            const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_sub_io *io, int32_t flags,
+                            int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
+{
+  if (!epoch || !io || !order_offset || !pos_mass || !vel || (!order_out && order_capacity > 0)) throw CudaError{HBTU_ERR_INVALID, "null argument"};
+  hbtu_stats total;
+  std::memset(&total, 0, sizeof(total));
+  int64_t o0 = 0; // order entries written so far
+  start_prefetch(c, pos_mass, vel, part_offset[parts[0].s0], part_offset[parts[0].s1]);
+  std::vector<int64_t> po, no;
+  std::vector<int32_t> nl;
+  for (size_t k = 0; k < parts.size(); k++)
+  {
+    const int64_t s0 = parts[k].s0, s1 = parts[k].s1, ns = s1 - s0, p0 = part_offset[s0];
+    po.resize((size_t)ns + 1);
+    for (int64_t i = 0; i <= ns; i++) po[i] = part_offset[s0 + i] - p0;
+    const int64_t *nop = nullptr;
+    const int32_t *nlp = nullptr;
+    if (nest_offset)
+    {
+      const int64_t n0 = nest_offset[s0];
+      no.resize((size_t)ns + 1);
+      for (int64_t i = 0; i <= ns; i++) no[i] = nest_offset[s0 + i] - n0;
+      nl.resize((size_t)no[ns]);
+      for (int64_t j = 0; j < no[ns]; j++) nl[j] = nest_list[n0 + j] - (int32_t)s0;
+      nop = no.data();
+      nlp = nl.data();
+    }
+    double t_stage = 0, t_exec = 0, t_fetch = 0, t_up;
+    {
+      WallTimer wt(t_stage);
+      wait_upload_wave(c, 2); // this part's particles are in d_pos_next / d_vel_next
+      finish_upload(c);
+      t_up = c.up_ms;
+      stage(c, epoch, ns, po.data(), pos_mass + 4 * p0, vel + 4 * p0, nop, nlp, io + s0, flags, true, true);
+      c.sub_index_base = s0;
+      if (k + 1 < parts.size()) start_prefetch(c, pos_mass, vel, part_offset[parts[k + 1].s0], part_offset[parts[k + 1].s1]);
+    }
+    {
+      WallTimer wt(t_exec);
+      execute_batch(c);
+    }
+    {
+      WallTimer wt(t_fetch);
+      c.order_index_base = p0;
+      fetch_batch(c, io + s0, order_capacity - o0, order_offset + s0, order_out ? order_out + o0 : nullptr, energy_out ? energy_out + o0 : nullptr);
+      for (int64_t i = 0; i <= ns; i++) order_offset[s0 + i] += o0;
+      o0 = order_offset[s1];
+    }
+    hbtu_stats part = c.stats;
+    part.stage_wall_ms = t_stage;
+    part.execute_wall_ms = t_exec;
+    part.fetch_wall_ms = t_fetch;
+    part.h2d_ms = t_up;
+    add_stats(total, part);
+  }
+  c.stats = total;
+  c.pipelined = true;
+}
 } // namespace
 
 extern "C" {
@@ -496,6 +705,8 @@ void hbtu_destroy(hbtu_ctx *ctx)
   c.arena.release();
   cudaFree(c.d_pos);
   cudaFree(c.d_vel);
+  cudaFree(c.d_pos_next);
+  cudaFree(c.d_vel_next);
   cudaFree(c.d_ids);
   cudaFree(c.d_ids_orig);
   cudaFree(c.d_E);
@@ -563,6 +774,22 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
                       const float *vel, const int64_t *nest_offset, const int32_t *nest_list, hbtu_sub_io *io, int32_t flags,
                       int64_t order_capacity, int64_t *order_offset, int32_t *order_out, float *energy_out)
 {
+  // many independent hierarchies and no dominant one: run the batch in parts, uploading the next part behind the kernels of the
+  // current one (unbind_batch_pipelined above); results do not depend on the grouping
+  if (ctx && nsub > 0 && part_offset)
+  {
+    std::vector<BatchPart> parts;
+    int rc0 = guarded(ctx, [&](Context &c) { parts = plan_parts(c, nsub, part_offset, nest_offset, nest_list); });
+    if (rc0 != HBTU_OK) return rc0;
+    if (!parts.empty())
+    {
+      int rc = guarded(ctx, [&](Context &c) {
+        unbind_batch_pipelined(c, parts, epoch, part_offset, pos_mass, vel, nest_offset, nest_list, io, flags, order_capacity, order_offset, order_out, energy_out);
+      });
+      finish_upload(ctx->c); // never leave copies from the caller's buffers in flight behind the return
+      return rc;
+    }
+  }
   // stage with the uploads on the copy stream (they overlap the kernels of the deeper nesting levels when the source arrays
   // are pinned - hbtu_host_alloc - and are plain staged copies otherwise), then execute + fetch
   int rc = guarded(ctx, [&](Context &c) {
@@ -664,6 +891,7 @@ int hbtu_set_tuning(const char *key, int64_t value)
   else if (k == "walk_big4") t.big4 = (int)value;
   else if (k == "walk_big2") t.big2 = (int)value;
   else if (k == "walk_group_min") t.group_min = (int)value;
+  else if (k == "pipeline_min_particles") g_pipeline_min.store(value < 0 ? 0 : value, std::memory_order_relaxed);
   else if (k == "walk_masked_pairs") t.masked_pairs = value == 1 ? 1 : 2;
   else if (k == "walk_masked_blocks") t.masked_blocks = (int)value;
   else if (k == "walk_small_max") t.small_max = (int)value;
@@ -679,6 +907,7 @@ int64_t hbtu_get_tuning(const char *key)
   if (k == "walk_big4") return t.big4;
   if (k == "walk_big2") return t.big2;
   if (k == "walk_group_min") return t.group_min;
+  if (k == "pipeline_min_particles") return pipeline_min();
   if (k == "walk_masked_pairs") return t.masked_pairs;
   if (k == "walk_masked_blocks") return t.masked_blocks;
   if (k == "walk_small_max") return t.small_max;

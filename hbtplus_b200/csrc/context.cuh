@@ -57,6 +57,13 @@ struct Context
   // persistent device buffers (grow-only)
   float4 *d_pos = nullptr, *d_vel = nullptr;
   int64_t cap_particles = 0, cap_vel = 0;
+  // pipelined hbtu_unbind_batch (capi.cu): while one part of the batch executes, the upload helper fills this second pair of
+  // buffers with the next part's particles; staging that part swaps the pairs
+  float4 *d_pos_next = nullptr, *d_vel_next = nullptr;
+  int64_t cap_pos_next = 0, cap_vel_next = 0;
+  int64_t order_index_base = 0; // added to the particle indices fetch_batch returns (first particle of the part in the caller's arrays)
+  int64_t sub_index_base = 0;   // first subhalo of the part in the caller's batch (the sampled mode's permutation is keyed by subhalo index)
+  bool pipelined = false;       // the last hbtu_unbind_batch ran in parts: only its last part is resident
   int *d_ids = nullptr, *d_ids_orig = nullptr;
   float *d_E = nullptr;
   int *d_rho = nullptr; // periodic runs: index of every Elist entry in the REFERENCE's Elist order (unbind_batch.cu, rho_*)

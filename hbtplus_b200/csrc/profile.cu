@@ -365,6 +365,8 @@ void profile_executed(Context &c, hbtu_profile_io *io)
 {
   if (!io) throw CudaError{HBTU_ERR_INVALID, "bad argument"};
   if (!c.staged || !c.executed) throw CudaError{HBTU_ERR_INVALID, "hbtu_profile_executed needs an executed batch (hbtu_stage + hbtu_execute)"};
+  if (c.pipelined)
+    throw CudaError{HBTU_ERR_INVALID, "the last hbtu_unbind_batch ran in pipelined parts, only the last of which is resident: use hbtu_profile_batch"};
   const int64_t nsub = c.nsub;
   if (nsub == 0) return;
   std::vector<int64_t> off(nsub), len(nsub);

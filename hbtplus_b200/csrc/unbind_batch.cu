@@ -825,7 +825,7 @@ __global__ void finalize_kernel(const Segment *__restrict__ segs, int nseg, SubS
 __global__ void __launch_bounds__(kBlock) pack_output_kernel(const int64_t *__restrict__ out_off, const int64_t *__restrict__ slot_base,
                                                               const int *__restrict__ nbound, int nsub, int64_t total,
                                                               const int *__restrict__ ids, const float *__restrict__ E,
-                                                              int *__restrict__ out_ids, float *__restrict__ out_E)
+                                                              int *__restrict__ out_ids, float *__restrict__ out_E, int id_base)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < total;
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(kBlock) pack_output_kernel(const int64_t *__re
   int s = find_seg_warp(out_off, nsub, i);
   if (!valid) return;
   int64_t o = i - out_off[s];
-  out_ids[i] = ids[slot_base[s] + o];
+  out_ids[i] = ids[slot_base[s] + o] + id_base; // id_base: this batch is a part of a pipelined hbtu_unbind_batch
   if (out_E) out_E[i] = (o < nbound[s]) ? E[slot_base[s] + o] : 0.f;
 }
 
@@ -1484,7 +1484,7 @@ void execute_batch(Context &c)
         if (M > 0 && nu > M)
         { // random_shuffle of the source before sampling (src/subhalo_unbind.cpp:302)
           shuffled = true;
-          shuf.push_back(ShuffleJob{h.slot_base, s, nu});
+          shuf.push_back(ShuffleJob{h.slot_base, s + (int)c.sub_index_base, nu}); // the key uses the subhalo's index in the CALLER's batch
           shuf_off.push_back(shuf_off.back() + nu);
         }
       }
@@ -1697,7 +1697,7 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
     int *d_nb = upload(c, nb);
     int *d_out = c.arena.alloc<int>(total);
     float *d_oe = energy_out ? c.arena.alloc<float>(total) : nullptr;
-    pack_output_kernel<<<grid_for(total), kBlock, 0, st>>>(d_off, d_sb, d_nb, nsub, total, c.d_ids, c.d_E, d_out, d_oe);
+    pack_output_kernel<<<grid_for(total), kBlock, 0, st>>>(d_off, d_sb, d_nb, nsub, total, c.d_ids, c.d_E, d_out, d_oe, (int)c.order_index_base);
     HBT_CHECK_LAUNCH();
     if (trace_on())
     {

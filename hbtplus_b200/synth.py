@@ -208,6 +208,31 @@ def nest_forest(rng: np.random.Generator, sizes: np.ndarray, max_depth: int = 4,
     return parent
 
 
+def dfs_layout(sizes: np.ndarray, parent: np.ndarray, return_order: bool = False):
+    """Relabel a nest forest depth first: every hierarchy (a root and everything nested in it) becomes a contiguous index range
+    with parents in front of their children - the order in which the reference visits subhaloes (RecursiveUnbind from every
+    host's central, src/subhalo_unbind.cpp:479-493) and in which integration/subhalo_unbind_b200.cpp::add_hierarchy lays a batch
+    out.  Returns (sizes, parent) in the new labelling (and, with return_order, the old index of every new one)."""
+    sizes = np.asarray(sizes, np.int64)
+    parent = np.asarray(parent, np.int64)
+    nsub = len(sizes)
+    order = np.argsort(parent, kind="stable")  # children grouped by parent, roots (-1) first, original order inside a group
+    first = np.searchsorted(parent[order], np.arange(-1, nsub), side="left")
+    last = np.searchsorted(parent[order], np.arange(-1, nsub), side="right")
+    new_of = np.full(nsub, -1, np.int64)
+    out = []
+    stack = list(order[first[0]:last[0]][::-1])
+    while stack:
+        s = stack.pop()
+        new_of[s] = len(out)
+        out.append(s)
+        stack.extend(order[first[s + 1]:last[s + 1]][::-1])
+    out = np.asarray(out, np.int64)
+    assert len(out) == nsub, "parent[] is not a forest"
+    new_parent = np.where(parent[out] >= 0, new_of[np.maximum(parent[out], 0)], -1)
+    return (sizes[out], new_parent, out) if return_order else (sizes[out], new_parent)
+
+
 def make_snapshot_torch(sizes, *, device, seed: int = 20240002, box_size: float = 100.0, particle_mass: float = 1e-6,
                         f_contam: float = 0.2, contam_scale: float = 2.0, contam_hot: float = 4.0, parent=None, centre=None,
                         wrap: bool = False, frame_noise: float = 0.05, pin: bool = True) -> Snapshot:

@@ -63,7 +63,7 @@ def test_masked_walk_reproduces_every_targets_decisions(memul, n, periodic):
     else:
         assert np.array_equal(per_lane(am, ntgt, memul), per_lane(asc, ntgt, memul))
     # periodic: the group's common image is more accurate than NEAREST(dx) of a wrapped pair (ulp(62) = 4e-6 against
-    # pair distances of 1e-2); the same holds for walk_group.cu's dense ring
+    # pair distances of 1e-2); the same holds for the dense ring
     assert np.allclose(sm, ss, rtol=5e-5 if periodic else 2e-6, atol=0)
 
 
