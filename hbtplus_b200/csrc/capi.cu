@@ -737,6 +737,33 @@ int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int6
   if (nsub < 0 || !part_offset) return HBTU_ERR_INVALID;
   try
   {
+    { // fast path (parents in front of their nested subhaloes): capacity = sum of own particles x (nesting depth + 1), since every
+      // subhalo's slot range holds its own particles plus everything its descendants can feed upwards.  Anything unusual falls
+      // through to the full forest construction below, which also diagnoses malformed nesting.
+      std::vector<int32_t> parent((size_t)nsub, -1);
+      bool ok = true;
+      if (nest_offset)
+        for (int64_t s = 0; s < nsub && ok; s++)
+          for (int64_t k = nest_offset[s]; k < nest_offset[s + 1]; k++)
+          {
+            const int32_t ch = nest_list[k];
+            if (ch <= s || ch >= nsub || parent[ch] != -1) { ok = false; break; }
+            parent[ch] = (int32_t)s;
+          }
+      if (ok)
+      {
+        std::vector<int32_t> depth((size_t)nsub, 0);
+        int64_t total = 0;
+        for (int64_t s = 0; s < nsub; s++)
+        {
+          const int64_t n = part_offset[s + 1] - part_offset[s];
+          if (n < 0 || n > 0x3fffffff) { ok = false; break; }
+          if (parent[s] >= 0) depth[s] = depth[parent[s]] + 1;
+          total += n * (depth[s] + 1);
+        }
+        if (ok && total <= 0x7fffffff00ll) return total;
+      }
+    }
     Context tmp;
     build_forest(tmp, nsub, part_offset, nest_offset, nest_list);
     return tmp.total_cap;

@@ -3,7 +3,9 @@
 #include <condition_variable>
 #include <mutex>
 #include <string>
+#include <algorithm>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "device_tree.cuh"
@@ -96,6 +98,38 @@ struct Context
   hbtu_stats stats{};
 };
 
+// Host-side loops over the subhaloes / segments of a batch with 1e5..1e6 of them are bound by a few hundred bytes of host
+// memory traffic per element and run while the GPU waits for the round they plan.  [0, n) is cut into up to 8 contiguous
+// chunks of at least `grain` elements; run_chunks calls fn(chunk, begin, end) for every chunk, each on its own host thread
+// (the caller's thread takes chunk 0).  fn must not throw.
+inline std::vector<std::pair<int64_t, int64_t>> chunk_ranges(int64_t n, int64_t grain)
+{
+  const unsigned hw = std::thread::hardware_concurrency();
+  int64_t k = std::min<int64_t>(std::min<unsigned>(8u, hw ? hw : 1u), grain > 0 ? n / grain : 1);
+  if (k < 1) k = 1;
+  const int64_t per = (n + k - 1) / k;
+  std::vector<std::pair<int64_t, int64_t>> r;
+  for (int64_t t = 0; t < k; t++) r.push_back({std::min(n, t * per), std::min(n, (t + 1) * per)});
+  return r;
+}
+template <class F>
+inline void run_chunks(const std::vector<std::pair<int64_t, int64_t>> &r, F &&fn)
+{
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < r.size(); t++) pool.emplace_back([&fn, &r, t] { fn((int)t, r[t].first, r[t].second); });
+  if (!r.empty()) fn(0, r[0].first, r[0].second);
+  for (auto &th : pool) th.join();
+}
+template <class F>
+inline void parallel_ranges(int64_t n, int64_t grain, F &&fn)
+{
+  run_chunks(chunk_ranges(n, grain), [&fn](int, int64_t b, int64_t e) { fn(b, e); });
+}
+
+// reserve `bytes` in the pinned mapped staging ring (returns the host pointer; may synchronise the stream to wrap) ...
+char *ring_reserve(Context &c, size_t bytes);
+// ... and, once the host has filled them, copy them to `dst` (device) with a kernel on c.stream
+void ring_commit(Context &c, void *dst, const char *staged, size_t bytes);
 void execute_batch(Context &c);
 // block the calling host thread until upload wave `wave` (1 or 2) of an asynchronously staged batch has landed
 void wait_upload_wave(Context &c, int wave);

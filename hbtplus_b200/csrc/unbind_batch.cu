@@ -845,9 +845,8 @@ __global__ void __launch_bounds__(kBlock) ring_copy_kernel(uint4 *__restrict__ d
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-void upload_bytes(Context &c, void *dst, const void *src, size_t bytes)
+char *ring_reserve(Context &c, size_t bytes)
 {
-  if (bytes == 0) return;
   const size_t need = (bytes + 15) & ~(size_t)15;
   if (c.ring_used + need > c.ring_cap)
   { // wrap: everything staged so far must have been consumed
@@ -864,12 +863,27 @@ void upload_bytes(Context &c, void *dst, const void *src, size_t bytes)
       c.ring_cap = cap;
     }
   }
-  std::memcpy(c.h_ring + c.ring_used, src, bytes);
-  const size_t n16 = need / 16;
-  const int grid = (int)std::min<size_t>((n16 + kBlock - 1) / kBlock, 148 * 4);
-  ring_copy_kernel<<<grid, kBlock, 0, c.stream>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(c.d_ring + c.ring_used), n16);
-  HBT_CHECK_LAUNCH();
+  char *p = c.h_ring + c.ring_used;
   c.ring_used += need;
+  return p;
+}
+
+void ring_commit(Context &c, void *dst, const char *staged, size_t bytes)
+{
+  if (bytes == 0) return;
+  const size_t n16 = ((bytes + 15) & ~(size_t)15) / 16;
+  const int grid = (int)std::min<size_t>((n16 + kBlock - 1) / kBlock, 148 * 4);
+  ring_copy_kernel<<<grid, kBlock, 0, c.stream>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(c.d_ring + (staged - c.h_ring)), n16);
+  HBT_CHECK_LAUNCH();
+}
+
+void upload_bytes(Context &c, void *dst, const void *src, size_t bytes)
+{
+  if (bytes == 0) return;
+  char *p = ring_reserve(c, bytes);
+  const char *q = static_cast<const char *>(src);
+  parallel_ranges((int64_t)bytes, 4 << 20, [=](int64_t b, int64_t e) { std::memcpy(p + b, q + b, (size_t)(e - b)); });
+  ring_commit(c, dst, p, bytes);
 }
 
 void *readback_buffer(Context &c, size_t bytes)
@@ -917,50 +931,94 @@ static void run_round(Context &c, std::vector<int> &active)
   // walk warps per walk class (device_tree.cuh: T=1, 2, 4 per-lane walks and the group walk); a segment belongs to one class
   std::vector<int> warp_off[kWalkClasses];
   for (auto &v : warp_off) v.resize(nseg + 1);
+  // planned on several host threads (the GPU is idle meanwhile): every chunk of segments fills its records and sums its sources,
+  // targets and warps per walk class; the chunk totals are scanned; every chunk then writes its offsets
+  struct ChunkSum
+  {
+    int64_t S = 0, T = 0, W[kWalkClasses] = {};
+    bool hoare = false;
+  };
+  const auto chunks = chunk_ranges(nseg, 1 << 13);
+  std::vector<ChunkSum> csum(chunks.size());
+  const int64_t max_sample = c.cfg.max_sample;
+  const SubHost *subs = c.subs.data();
+  const int *act = active.data();
+  Segment *segp = segs.data();
+  run_chunks(chunks, [&, subs, act, segp](int k, int64_t a0, int64_t a1) {
+    ChunkSum cs;
+    for (int64_t a = a0; a < a1; a++)
+    {
+      const SubHost &h = subs[act[a]];
+      Segment &sg = segp[a];
+      sg.slot_base = h.slot_base;
+      sg.sub = act[a];
+      sg.mode = h.correction ? kWalkUnbindCorrect : kWalkUnbindFull;
+      if (h.correction)
+      {
+        sg.tree_first = h.nbound;
+        sg.tree_n = h.nlast - h.nbound;
+      }
+      else
+      {
+        sg.tree_first = 0;
+        sg.tree_n = h.nbound;
+      }
+      sg.keep_order = 0;
+      sg.mass_factor = 1.f;
+      if (max_sample > 0 && h.nbound > max_sample)
+      { // sampled potential: tree of the first MaxSampleSize entries, masses scaled by Nlast/MaxSampleSize (:333-339)
+        sg.keep_order = 1;
+        if (!h.correction)
+        {
+          sg.tree_n = (int)max_sample;
+          sg.mass_factor = (float)h.nbound / (float)max_sample;
+          cs.hoare = true;
+        }
+      }
+      sg.tgt_n = h.nbound;
+      const WalkClass wcl = walk_class(sg.tgt_n, sg.tree_n);
+      cs.S += sg.tree_n;
+      cs.T += sg.tgt_n;
+      cs.W[wcl.index] += (sg.tgt_n + wcl.targets_per_warp - 1) / wcl.targets_per_warp;
+    }
+    csum[k] = cs;
+  });
   int64_t S = 0, T = 0, W[kWalkClasses] = {};
   bool any_hoare = false;
-  for (int a = 0; a < nseg; a++)
+  std::vector<ChunkSum> cbase(chunks.size());
+  for (size_t k = 0; k < chunks.size(); k++)
   {
-    SubHost &h = c.subs[active[a]];
-    Segment &sg = segs[a];
-    sg.slot_base = h.slot_base;
-    sg.sub = active[a];
-    sg.mode = h.correction ? kWalkUnbindCorrect : kWalkUnbindFull;
-    if (h.correction)
-    {
-      sg.tree_first = h.nbound;
-      sg.tree_n = h.nlast - h.nbound;
-    }
-    else
-    {
-      sg.tree_first = 0;
-      sg.tree_n = h.nbound;
-    }
-    sg.keep_order = 0;
-    sg.mass_factor = 1.f;
-    if (c.cfg.max_sample > 0 && h.nbound > c.cfg.max_sample)
-    { // sampled potential: tree of the first MaxSampleSize entries, masses scaled by Nlast/MaxSampleSize (:333-339)
-      sg.keep_order = 1;
-      if (!h.correction)
+    cbase[k].S = S;
+    cbase[k].T = T;
+    for (int q = 0; q < kWalkClasses; q++) cbase[k].W[q] = W[q];
+    S += csum[k].S;
+    T += csum[k].T;
+    for (int q = 0; q < kWalkClasses; q++) W[q] += csum[k].W[q];
+    any_hoare = any_hoare || csum[k].hoare;
+  }
+  if (S > 0x3fffffff || T > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "round larger than 2^30 particles"};
+  {
+    int *toff = tree_off.data(), *goff = tgt_off.data();
+    int *woff[kWalkClasses];
+    for (int q = 0; q < kWalkClasses; q++) woff[q] = warp_off[q].data();
+    run_chunks(chunks, [&, segp, toff, goff](int k, int64_t a0, int64_t a1) {
+      int64_t s = cbase[k].S, t = cbase[k].T, w[kWalkClasses];
+      for (int q = 0; q < kWalkClasses; q++) w[q] = cbase[k].W[q];
+      for (int64_t a = a0; a < a1; a++)
       {
-        sg.tree_n = (int)c.cfg.max_sample;
-        sg.mass_factor = (float)h.nbound / (float)c.cfg.max_sample;
-        any_hoare = true;
+        Segment &sg = segp[a];
+        const WalkClass wcl = walk_class(sg.tgt_n, sg.tree_n);
+        sg.tree_off = (int)s;
+        sg.tgt_off = (int)t;
+        sg.warp_off = (int)w[wcl.index];
+        toff[a] = (int)s;
+        goff[a] = (int)t;
+        for (int q = 0; q < kWalkClasses; q++) woff[q][a] = (int)w[q];
+        s += sg.tree_n;
+        t += sg.tgt_n;
+        w[wcl.index] += (sg.tgt_n + wcl.targets_per_warp - 1) / wcl.targets_per_warp;
       }
-    }
-    sg.tgt_n = h.nbound;
-    sg.tree_off = (int)S;
-    sg.tgt_off = (int)T;
-    const WalkClass wcl = walk_class(sg.tgt_n, sg.tree_n);
-    const int cls = wcl.index;
-    sg.warp_off = (int)W[cls];
-    tree_off[a] = (int)S;
-    tgt_off[a] = (int)T;
-    for (int q = 0; q < kWalkClasses; q++) warp_off[q][a] = (int)W[q];
-    S += sg.tree_n;
-    T += sg.tgt_n;
-    W[cls] += (sg.tgt_n + wcl.targets_per_warp - 1) / wcl.targets_per_warp;
-    if (S > 0x3fffffff || T > 0x3fffffff) throw CudaError{HBTU_ERR_UNSUPPORTED, "round larger than 2^30 particles"};
+    });
   }
   tree_off[nseg] = (int)S;
   tgt_off[nseg] = (int)T;
@@ -1188,23 +1246,36 @@ static void run_round(Context &c, std::vector<int> &active)
   c.stats.walk_targets += T;
   c.stats.tree_sources += S;
 
+  // results back into the host records (chunks of segments on several threads), then the next round's list in order
+  std::vector<uint8_t> fate(nseg); // 0 finished, 1 active in the next round, 2 finished and to be refined
+  {
+    SubHost *subs_w = c.subs.data();
+    const bool refine = c.params.refine_mostbound_particle && c.cfg.max_sample > 0;
+    uint8_t *fp = fate.data();
+    run_chunks(chunks, [=](int, int64_t a0, int64_t a1) {
+      for (int64_t a = a0; a < a1; a++)
+      {
+        SubHost &h = subs_w[act[a]];
+        h.nbound = res[a].nbound;
+        h.nlast = res[a].nlast;
+        h.correction = res[a].correction;
+        h.iterations++;
+        uint8_t f = 1;
+        if (res[a].status != kActive)
+        {
+          h.done = true;
+          h.disrupted = res[a].status == kDisrupted;
+          f = (res[a].status == kConverged && refine && h.nbound > max_sample) ? 2 : 0;
+        }
+        fp[a] = f;
+      }
+    });
+  }
   std::vector<int> next;
   for (int a = 0; a < nseg; a++)
   {
-    SubHost &h = c.subs[active[a]];
-    h.nbound = res[a].nbound;
-    h.nlast = res[a].nlast;
-    h.correction = res[a].correction;
-    h.iterations++;
-    if (res[a].status == kActive)
-      next.push_back(active[a]);
-    else
-    {
-      h.done = true;
-      h.disrupted = res[a].status == kDisrupted;
-      if (res[a].status == kConverged && c.params.refine_mostbound_particle && c.cfg.max_sample > 0 && h.nbound > c.cfg.max_sample)
-        c.refine_list.push_back(active[a]);
-    }
+    if (fate[a] == 1) next.push_back(active[a]);
+    else if (fate[a] == 2) c.refine_list.push_back(active[a]);
   }
   active.swap(next);
 }
@@ -1368,47 +1439,56 @@ void execute_batch(Context &c)
   HBT_CUDA(cudaEventRecord(c.ev_exec[0], st));
   if (c.count_interactions) HBT_CUDA(cudaMemsetAsync(c.d_counters, 0, kWalkCounters * sizeof(unsigned long long), st));
 
-  // (re)initialise per-subhalo state from the staged inputs
-  std::vector<SubState> init(nsub);
-  for (int s = 0; s < nsub; s++)
+  // (re)initialise per-subhalo state from the staged inputs: written straight into the staging ring, on several host threads
+  // (one thread needs ~0.3 us per subhalo for this loop: 150 ms of idle GPU at the 5e5 subhaloes of an EAGLE-shaped shard)
+  if (nsub > 0)
   {
-    SubHost &h = c.subs[s];
-    const hbtu_sub_io &io = c.io_in[s];
-    SubState z;
-    std::memset(&z, 0, sizeof(z));
-    z.slot_base = h.slot_base;
-    z.part_begin = h.part_begin;
-    z.n_own = h.n_own;
-    z.n_src = h.n_own;
-    z.status = kPending;
-    z.death = io.snapshot_index_of_death;
-    z.sink = io.snapshot_index_of_sink;
-    z.sinktrack = io.sink_track_id;
-    // the orphan rule belongs to RecursiveUnbind (src/subhalo_unbind.cpp:434-446); a subhalo the caller enters through plain
-    // Unbind (HBTU_SUB_PLAIN_UNBIND) is unbound like any other whatever its entry Nbound
-    const bool orphan = io.nbound <= 1 && !(io.flags & HBTU_SUB_PLAIN_UNBIND);
-    z.is_orphan = orphan;
-    for (int j = 0; j < 3; j++)
-    {
-      z.ref_pos[j] = (float)io.avg_pos[j];
-      z.ref_vel[j] = (float)io.avg_vel[j];
-      z.mb_pos[j] = (float)io.mostbound_pos[j];
-      z.mb_vel[j] = (float)io.mostbound_vel[j];
-      z.am[j] = io.specific_angular_momentum[j];
-    }
-    z.spec_pot = io.specific_self_potential_energy;
-    z.spec_kin = io.specific_self_kinetic_energy;
-    z.mbound = io.mbound;
-    z.nbound = (int)io.nbound;
-    init[s] = z;
-    h.n_src = h.n_own;
-    h.nbound = h.nlast = 0;
-    h.correction = 0;
-    h.done = h.disrupted = false;
-    h.iterations = 0;
-    h.is_orphan = orphan;
+    char *staged = ring_reserve(c, sizeof(SubState) * (size_t)nsub);
+    SubState *init = reinterpret_cast<SubState *>(staged);
+    SubHost *subs = c.subs.data();
+    const hbtu_sub_io *io_in = c.io_in.data();
+    parallel_ranges(nsub, 1 << 14, [=](int64_t s0, int64_t s1) {
+      for (int64_t s = s0; s < s1; s++)
+      {
+        SubHost &h = subs[s];
+        const hbtu_sub_io &io = io_in[s];
+        SubState z;
+        std::memset(&z, 0, sizeof(z));
+        z.slot_base = h.slot_base;
+        z.part_begin = h.part_begin;
+        z.n_own = h.n_own;
+        z.n_src = h.n_own;
+        z.status = kPending;
+        z.death = io.snapshot_index_of_death;
+        z.sink = io.snapshot_index_of_sink;
+        z.sinktrack = io.sink_track_id;
+        // the orphan rule belongs to RecursiveUnbind (src/subhalo_unbind.cpp:434-446); a subhalo the caller enters through plain
+        // Unbind (HBTU_SUB_PLAIN_UNBIND) is unbound like any other whatever its entry Nbound
+        const bool orphan = io.nbound <= 1 && !(io.flags & HBTU_SUB_PLAIN_UNBIND);
+        z.is_orphan = orphan;
+        for (int j = 0; j < 3; j++)
+        {
+          z.ref_pos[j] = (float)io.avg_pos[j];
+          z.ref_vel[j] = (float)io.avg_vel[j];
+          z.mb_pos[j] = (float)io.mostbound_pos[j];
+          z.mb_vel[j] = (float)io.mostbound_vel[j];
+          z.am[j] = io.specific_angular_momentum[j];
+        }
+        z.spec_pot = io.specific_self_potential_energy;
+        z.spec_kin = io.specific_self_kinetic_energy;
+        z.mbound = io.mbound;
+        z.nbound = (int)io.nbound;
+        init[s] = z;
+        h.n_src = h.n_own;
+        h.nbound = h.nlast = 0;
+        h.correction = 0;
+        h.done = h.disrupted = false;
+        h.iterations = 0;
+        h.is_orphan = orphan;
+      }
+    });
+    ring_commit(c, c.d_subs, staged, sizeof(SubState) * (size_t)nsub); // d_subs holds nsub + 1 records: room for the 16-byte granularity
   }
-  upload_bytes(c, c.d_subs, init.data(), sizeof(SubState) * nsub); // d_subs holds nsub + 1 records: room for the 16-byte granularity
   if (c.N > 0)
   {
     init_ids_kernel<<<grid_for(c.N), kBlock, 0, st>>>(c.d_part_offset, c.d_slot_base, nsub, c.N, c.d_ids);
@@ -1671,19 +1751,8 @@ void fetch_batch(Context &c, hbtu_sub_io *io, int64_t order_capacity, int64_t *o
     }
   };
   // ~700 bytes of host memory traffic per subhalo: a snapshot with 5e5 subhaloes per GPU (EAGLE-shaped shard) spent 165 ms
-  // here on one thread, so the conversion is dealt to a few helper threads in contiguous ranges
-  const int nthr = nsub < (1 << 15) ? 1 : (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
-  if (nthr <= 1)
-    convert(0, nsub);
-  else
-  {
-    std::vector<std::thread> pool;
-    const int per = (nsub + nthr - 1) / nthr;
-    for (int t = 1; t < nthr; t++)
-      pool.emplace_back(convert, std::min(nsub, t * per), std::min(nsub, (t + 1) * per));
-    convert(0, std::min(nsub, per));
-    for (auto &th : pool) th.join();
-  }
+  // here on one thread
+  parallel_ranges(nsub, 1 << 14, [&](int64_t s0, int64_t s1) { convert((int)s0, (int)s1); });
   for (int s = 0; s < nsub; s++) out_off[s + 1] += out_off[s];
   const int64_t total = out_off[nsub];
   HBT_TRACE(trace_t0, "fetch: records read back and converted (%d subhaloes)", nsub);

@@ -160,7 +160,11 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
 /* Pinned (page-locked) host memory for the caller's staging arrays.  hbtu_unbind_batch uploads the particle arrays on a copy
  * stream in two waves (everything but the dominant root subhalo first, that root - which the level-synchronous scheduler
  * reaches last - behind the kernels of the deeper levels); from pinned memory these are asynchronous DMA transfers, from any
- * other host memory they are plain staged copies.  NULL when the allocation fails. */
+ * other host memory they are plain staged copies.  A batch of many independent hierarchies without a dominant one (a
+ * cosmological box; at least "pipeline_min_particles" particles - hbtu_set_tuning / HBTU_PIPELINE_MIN, default 2^24, 0 = never -
+ * laid out hierarchy by hierarchy, parents in front of their nested subhaloes) is run in three parts instead, the next part
+ * uploading behind the kernels of the current one; the results do not depend on it, bit for bit, but afterwards only the last
+ * part is resident (hbtu_profile_executed refuses).  NULL when the allocation fails. */
 void *hbtu_host_alloc(size_t bytes);
 void hbtu_host_free(void *p);
 
@@ -339,7 +343,8 @@ int hbtu_get_stats(const hbtu_ctx *ctx, hbtu_stats *out);
  * interactions and warp node visits into hbtu_stats (costs a few percent; off by default). */
 int hbtu_set_counting(hbtu_ctx *ctx, int on);
 /* diagnostics (no reference counterpart): process-wide kernel-routing knobs of the walk ("walk_group_min", "walk_masked_pairs",
- * "walk_masked_blocks", "walk_tpl", "walk_big2", "walk_big4", "walk_small_max"; defaults = measured best, also settable
+ * "walk_masked_blocks", "walk_tpl", "walk_big2", "walk_big4", "walk_small_max") and of the upload pipeline
+ * ("pipeline_min_particles"; defaults = measured best, also settable
  * through HBTU_WALK_* environment variables read at the first use).  Results do not depend on them beyond fp64 summation
  * order.  hbtu_get_tuning returns -1 for an unknown key. */
 int hbtu_set_tuning(const char *key, int64_t value);
