@@ -428,8 +428,8 @@ void tree_potential(Context &c, const hbtu_epoch *epoch, int64_t nsrc, const flo
 // dominant root whose upload could hide behind the deeper levels: all of it is needed by the first round, and the whole
 // upload (104 ms per 1.7e8 particles alone on the link, 280 ms with eight GPUs sharing the host's memory) sat in front of
 // the kernels.  Hierarchies never interact and results do not depend on how subhaloes are grouped into batches, so such a
-// batch is cut at hierarchy boundaries into three parts of 1/8, 3/8 and 1/2 of the particles; part k+1 is uploaded into a
-// second pair of buffers while part k executes.  Only the first eighth of the upload stays exposed.
+// batch is cut at a hierarchy boundary into two parts of 1/4 and 3/4 of the particles; the second part is uploaded into a
+// second pair of buffers while the first executes.  Only the first quarter of the upload stays exposed.
 std::atomic<long long> g_pipeline_min{-1}; // particles; 0 = never.  HBTU_PIPELINE_MIN / hbtu_set_tuning("pipeline_min_particles")
 long long pipeline_min()
 {
@@ -477,11 +477,14 @@ std::vector<BatchPart> plan_parts(const Context &c, int64_t nsub, const int64_t 
   hstart.push_back(nsub);
   for (size_t h = 0; h + 1 < hstart.size(); h++)
     if (part_offset[hstart[h + 1]] - part_offset[hstart[h]] > N / 4) return none; // a dominant hierarchy: the two-wave upload handles it
-  const int64_t cuts[2] = {N / 8, N / 2};
+  // Two parts: the first quarter's upload is the exposed one (26 ms per 1.7e8 particles), the rest travels behind its kernels.
+  // Every part pays its own ~28 rounds of planning and small launches (~1 ms each), which is why three parts (1/8, 3/8, 1/2)
+  // measured no better (tools/gpu/c25.sh, c27.sh).
+  const int64_t cuts[1] = {N / 4};
   std::vector<BatchPart> parts;
   int64_t begin = 0;
   size_t h = 0;
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 1; k++)
   {
     while (h + 1 < hstart.size() && part_offset[hstart[h]] < cuts[k]) h++;
     if (hstart[h] > begin && hstart[h] < nsub)

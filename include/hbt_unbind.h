@@ -162,8 +162,8 @@ int hbtu_unbind_batch(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, cons
  * reaches last - behind the kernels of the deeper levels); from pinned memory these are asynchronous DMA transfers, from any
  * other host memory they are plain staged copies.  A batch of many independent hierarchies without a dominant one (a
  * cosmological box; at least "pipeline_min_particles" particles - hbtu_set_tuning / HBTU_PIPELINE_MIN, default 2^24, 0 = never -
- * laid out hierarchy by hierarchy, parents in front of their nested subhaloes) is run in three parts instead, the next part
- * uploading behind the kernels of the current one; the results do not depend on it, bit for bit, but afterwards only the last
+ * laid out hierarchy by hierarchy, parents in front of their nested subhaloes) is run in two parts (1/4 and 3/4 of the particles) instead, the second
+ * uploading behind the kernels of the first; the results do not depend on it, bit for bit, but afterwards only the last
  * part is resident (hbtu_profile_executed refuses).  NULL when the allocation fails. */
 void *hbtu_host_alloc(size_t bytes);
 void hbtu_host_free(void *p);

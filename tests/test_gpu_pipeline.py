@@ -1,5 +1,5 @@
 """The pipelined form of ``hbtu_unbind_batch`` (capi.cu::unbind_batch_pipelined): a batch of many independent hierarchies is run in
-three parts, the next part uploading behind the kernels of the current one.  Hierarchies never interact
+two parts, the second uploading behind the kernels of the first.  Hierarchies never interact
 (src/subhalo_unbind.cpp:479-513 visits them one host halo at a time), so the catalogue must not depend on it - bit for bit."""
 import ctypes as C
 
