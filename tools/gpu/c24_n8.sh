@@ -4,5 +4,5 @@ N=${1:-8}
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --workload cfg4 --steps 3 --warmup 3 \
-  > gpurun_out/r02_n${N}_weak_cfg4_v7.json 2> gpurun_out/r02_n${N}_weak_cfg4_v7.err
-echo "rc=$?"; tail -c 1500 gpurun_out/r02_n${N}_weak_cfg4_v7.json; tail -3 gpurun_out/r02_n${N}_weak_cfg4_v7.err
+  > gpurun_out/r02_n${N}_weak_cfg4_v8.json 2> gpurun_out/r02_n${N}_weak_cfg4_v8.err
+echo "rc=$?"; tail -c 1500 gpurun_out/r02_n${N}_weak_cfg4_v8.json; tail -3 gpurun_out/r02_n${N}_weak_cfg4_v8.err
