@@ -66,6 +66,55 @@ def test_order_capacity_matches_host_mirror():
     assert lib.hbtu_order_capacity(5, P(part_offset, C.c_int64), P(cyc_off, C.c_int64), P(cyc, C.c_int32)) == capi.HBTU_ERR_INVALID
 
 
+def test_order_capacity_both_layouts_and_dfs_layout():
+    """hbtu_order_capacity has a fast path for batches whose parents precede their nested subhaloes (the shim's depth-first
+    layout, synth.dfs_layout) and the full forest construction otherwise: both must give sum(own particles x (depth + 1))."""
+    from hbtplus_b200 import synth
+
+    lib = capi.load_library()
+    P = capi._ptr
+    rng = np.random.default_rng(17)
+    for depth_first in (False, True):
+        sizes = synth.subhalo_sizes(rng, 4000, 20, 5000)
+        parent = synth.nest_forest(rng, sizes, max_depth=4, p_nest=0.5, root=None)
+        if depth_first:
+            old_sizes, old_parent = sizes, parent
+            sizes, parent, order = synth.dfs_layout(sizes, parent, return_order=True)
+            # a relabelling: same multiset of (size, parent size) pairs, every hierarchy contiguous with parents first
+            assert np.array_equal(sizes, old_sizes[order])
+            assert np.array_equal(np.where(parent >= 0, sizes[np.maximum(parent, 0)], -1), np.where(old_parent[order] >= 0, old_sizes[np.maximum(old_parent[order], 0)], -1))
+            start = 0
+            for s in range(len(sizes)):
+                if parent[s] < 0:
+                    start = s
+                else:
+                    assert start <= parent[s] < s
+        depth = synth.forest_depth(parent)
+        part_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        kids = [[] for _ in sizes]
+        for s, p_ in enumerate(parent):
+            if p_ >= 0:
+                kids[p_].append(s)
+        nest_offset = np.concatenate([[0], np.cumsum([len(k) for k in kids])]).astype(np.int64)
+        nest_list = np.array([c for k in kids for c in k], np.int32)
+        want = int((sizes * (depth + 1)).sum())
+        got = lib.hbtu_order_capacity(len(sizes), P(part_offset, C.c_int64), P(nest_offset, C.c_int64), P(nest_list, C.c_int32))
+        assert got == want == capi.order_capacity(part_offset, nest_offset, nest_list)
+
+
+def test_tuning_knobs_round_trip():
+    lib = capi.load_library()
+    lib.hbtu_set_tuning.argtypes = [C.c_char_p, C.c_int64]
+    lib.hbtu_get_tuning.argtypes = [C.c_char_p]
+    lib.hbtu_get_tuning.restype = C.c_int64
+    assert lib.hbtu_get_tuning(b"walk_group_min") == 256 and lib.hbtu_get_tuning(b"pipeline_min_particles") == 1 << 24
+    for key in (b"walk_group_min", b"pipeline_min_particles", b"walk_small_max"):
+        old = lib.hbtu_get_tuning(key)
+        assert lib.hbtu_set_tuning(key, 12345) == 0 and lib.hbtu_get_tuning(key) == 12345
+        assert lib.hbtu_set_tuning(key, old) == 0
+    assert lib.hbtu_get_tuning(b"no_such_knob") == -1 and lib.hbtu_set_tuning(b"no_such_knob", 1) != 0
+
+
 def test_create_rejects_bad_abi_and_has_no_cpu_fallback():
     lib = capi.load_library()
     p = capi.make_params(box_size=62.5, softening=5e-3)
