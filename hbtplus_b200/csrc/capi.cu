@@ -777,6 +777,27 @@ int64_t hbtu_order_capacity(int64_t nsub, const int64_t *part_offset, const int6
   }
 }
 
+int hbtu_plan_pipeline(int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list, int64_t *part_begin,
+                       int max_parts)
+{ // diagnostics: the parts hbtu_unbind_batch would run this batch in (host only, no device needed)
+  if (nsub < 0 || !part_offset || !part_begin || max_parts < 1) return HBTU_ERR_INVALID;
+  try
+  {
+    Context tmp;
+    std::vector<BatchPart> parts;
+    if (nsub > 0) parts = plan_parts(tmp, nsub, part_offset, nest_offset, nest_list);
+    if (parts.empty()) parts.push_back(BatchPart{0, nsub});
+    if ((int)parts.size() > max_parts) return HBTU_ERR_CAPACITY;
+    for (size_t k = 0; k < parts.size(); k++) part_begin[k] = parts[k].s0;
+    part_begin[parts.size()] = nsub;
+    return (int)parts.size();
+  }
+  catch (...)
+  {
+    return HBTU_ERR_INVALID;
+  }
+}
+
 int hbtu_stage(hbtu_ctx *ctx, const hbtu_epoch *epoch, int64_t nsub, const int64_t *part_offset, const float *pos_mass,
                const float *vel, const int64_t *nest_offset, const int32_t *nest_list, const hbtu_sub_io *io, int32_t flags)
 {

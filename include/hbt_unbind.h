@@ -347,6 +347,11 @@ int hbtu_set_counting(hbtu_ctx *ctx, int on);
  * ("pipeline_min_particles"; defaults = measured best, also settable
  * through HBTU_WALK_* environment variables read at the first use).  Results do not depend on them beyond fp64 summation
  * order.  hbtu_get_tuning returns -1 for an unknown key. */
+/* diagnostics (no reference counterpart, host only): the parts hbtu_unbind_batch would run this batch in - see hbtu_host_alloc
+ * above.  part_begin[0 .. parts] receives the first subhalo of every part and nsub; returns the number of parts (1 = in one
+ * piece), HBTU_ERR_CAPACITY when max_parts is too small. */
+int hbtu_plan_pipeline(int64_t nsub, const int64_t *part_offset, const int64_t *nest_offset, const int32_t *nest_list,
+                       int64_t *part_begin, int max_parts);
 int hbtu_set_tuning(const char *key, int64_t value);
 int64_t hbtu_get_tuning(const char *key);
 

@@ -102,6 +102,54 @@ def test_order_capacity_both_layouts_and_dfs_layout():
         assert got == want == capi.order_capacity(part_offset, nest_offset, nest_list)
 
 
+def test_pipeline_planner():
+    """capi.cu::plan_parts through the host-only diagnostic: a batch of many hierarchies laid out depth first is cut at a
+    hierarchy boundary near a quarter of the particles; other layouts, small batches and dominant hierarchies are not cut."""
+    from hbtplus_b200 import synth
+
+    lib = capi.load_library()
+    lib.hbtu_set_tuning.argtypes = [C.c_char_p, C.c_int64]
+    lib.hbtu_get_tuning.argtypes = [C.c_char_p]
+    lib.hbtu_get_tuning.restype = C.c_int64
+    P = capi._ptr
+
+    def plan(sizes, parent):
+        part_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        kids = [[] for _ in sizes]
+        for s, p_ in enumerate(parent):
+            if p_ >= 0:
+                kids[p_].append(s)
+        nest_offset = np.concatenate([[0], np.cumsum([len(k) for k in kids])]).astype(np.int64)
+        nest_list = np.array([c for k in kids for c in k], np.int32)
+        out = np.zeros(8, np.int64)
+        n = lib.hbtu_plan_pipeline(len(sizes), P(part_offset, C.c_int64), P(nest_offset, C.c_int64), P(nest_list, C.c_int32), P(out, C.c_int64), 7)
+        assert n >= 1 and out[0] == 0 and out[n] == len(sizes)
+        return out[:n + 1], part_offset
+
+    rng = np.random.default_rng(23)
+    sizes = synth.subhalo_sizes(rng, 3000, 20, 4000)
+    parent = synth.nest_forest(rng, sizes, max_depth=3, p_nest=0.3, root=None)
+    dsizes, dparent = synth.dfs_layout(sizes, parent)
+    old = lib.hbtu_get_tuning(b"pipeline_min_particles")
+    try:
+        assert len(plan(dsizes, dparent)[0]) == 2  # below the default threshold of 2^24 particles: one piece
+        lib.hbtu_set_tuning(b"pipeline_min_particles", 1000)
+        cuts, po = plan(dsizes, dparent)
+        assert len(cuts) == 3
+        assert dparent[cuts[1]] < 0  # a hierarchy starts at the cut ...
+        n_all = po[-1]
+        assert n_all / 4 <= po[cuts[1]] <= n_all / 4 + dsizes.max() * 4  # ... the first one at or after a quarter of the particles
+        assert len(plan(sizes, parent)[0]) == 2  # children listed away from their parents: one piece
+        big = np.concatenate([[int(dsizes.sum())], dsizes])  # one hierarchy holds half of the batch: the two-wave upload instead
+        bigp = np.concatenate([[-1], np.where(dparent >= 0, dparent + 1, -1)])
+        assert len(plan(big, bigp)[0]) == 2
+        assert len(plan(dsizes[:40], np.full(40, -1))[0]) == 2  # fewer than 64 subhaloes
+        lib.hbtu_set_tuning(b"pipeline_min_particles", 0)
+        assert len(plan(dsizes, dparent)[0]) == 2  # switched off
+    finally:
+        lib.hbtu_set_tuning(b"pipeline_min_particles", old)
+
+
 def test_tuning_knobs_round_trip():
     lib = capi.load_library()
     lib.hbtu_set_tuning.argtypes = [C.c_char_p, C.c_int64]
