@@ -81,3 +81,45 @@ def test_two_rank_gloo_gather_matches_single_process(oracle_lib):
     want = po.run_batch(oracle_lib, "hbto", p, e, snap, flags=capi.HBTU_FLAG_TRUNCATE_SOURCE)
     for f in ("nbound", "mbound", "snapshot_index_of_death", "nsource", "avg_pos", "avg_vel"):
         assert np.array_equal(table[f], want.io[f]), f
+
+
+def test_eagle_workload_shards_partition_the_snapshot_depth_first():
+    """bench.py --workload cfg4: every rank draws the same global forest and keeps its own hierarchies.  The shards must
+    partition the global subhalo list, keep every hierarchy whole, balance the LPT cost, and come out hierarchy by hierarchy
+    with parents first (the layout the drop-in shim produces and hbtu_unbind_batch's pipeline needs)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    wl = bench.WORKLOADS["cfg4"]
+    world, particles = 4, 2.0e5  # per rank
+    gsizes, gparent = wl.sizes(particles * world)
+    seen = np.zeros(len(gsizes), np.int64)
+    costs = []
+    for rank in range(world):
+        sizes, parent, gidx = wl.shard(particles, rank, world)
+        seen[gidx] += 1
+        assert np.array_equal(sizes, gsizes[gidx])
+        # the parent of a local subhalo is the local copy of its global parent (hierarchies are whole)
+        has = parent >= 0
+        assert np.array_equal(gidx[parent[has]], gparent[gidx[has]]) and np.all(gparent[gidx[~has]] < 0)
+        start = 0
+        for s in range(len(sizes)):  # depth first: every hierarchy a contiguous range, parents in front
+            if parent[s] < 0:
+                start = s
+            else:
+                assert start <= parent[s] < s
+        n = sizes.astype(np.float64)
+        costs.append(float((n * np.log2(np.maximum(n, 2.0))).sum()))
+    assert np.all(seen == 1)
+    assert max(costs) / np.mean(costs) < 1.05
+    # cfg 3 is generated depth first as well
+    sizes, parent = bench.WORKLOADS["cfg3"].sizes(2.0e5)
+    start = 0
+    for s in range(len(sizes)):
+        if parent[s] < 0:
+            start = s
+        else:
+            assert start <= parent[s] < s
